@@ -1,0 +1,114 @@
+"""ctypes binding of libast_b200.so (the C ABI declared in include/ast.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libast_b200.so")
+
+AST_F32, AST_BF16 = 0, 1
+AST_MAX_TAPS = 81
+CONV_RELU, CONV_REFLECT, CONV_TENSOR = 1, 2, 4
+
+_DTYPES = {torch.float32: AST_F32, torch.bfloat16: AST_BF16}
+
+
+class Image(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int32),
+                ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("c", ctypes.c_int32),
+                ("sn", ctypes.c_int64), ("sh", ctypes.c_int64), ("sw", ctypes.c_int64), ("sc", ctypes.c_int64)]
+
+
+class GatherGeom(ctypes.Structure):
+    _fields_ = [("mi", ctypes.c_int32), ("mj", ctypes.c_int32), ("si", ctypes.c_int32), ("so", ctypes.c_int32),
+                ("oy0", ctypes.c_int32), ("ox0", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+                ("flags", ctypes.c_int32),
+                ("dy", ctypes.c_int16 * AST_MAX_TAPS), ("dx", ctypes.c_int16 * AST_MAX_TAPS),
+                ("w_img_stride", ctypes.c_int64)]
+
+
+_lib = None
+_P = ctypes.POINTER
+_vp = ctypes.c_void_p
+
+_SIGNATURES = {
+    "ast_conv_gather": [_P(Image), _vp, _vp, _vp, _P(Image), _P(Image), _P(Image), _P(GatherGeom), _vp],
+    "ast_wgrad_gather": [_P(Image), _P(Image), _vp, _vp, ctypes.c_int64, ctypes.c_int64, _P(GatherGeom), _vp],
+    "ast_pack_weights": [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                         _vp, ctypes.c_int32, _vp],
+    "ast_instnorm_stats": [_P(Image), _vp, _vp, ctypes.c_float, _vp, _vp],
+    "ast_instnorm_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, _vp],
+    "ast_instnorm_bwd_stats": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
+                               _vp, _vp, _vp],
+    "ast_instnorm_bwd_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
+                               _vp, _vp, _P(Image), _P(Image), _vp],
+    "ast_maxpool2_fwd": [_P(Image), _P(Image), _vp],
+    "ast_maxpool2_bwd": [_P(Image), _P(Image), _P(Image), _P(Image), _P(Image), _vp],
+    "ast_gram": [_P(Image), _vp, ctypes.c_float, ctypes.c_int32, _vp],
+    "ast_mse": [_P(Image), _P(Image), _vp, ctypes.c_float, _P(Image), ctypes.c_float, _vp],
+    "ast_copy_image": [_P(Image), _P(Image), _vp, ctypes.c_int32, _vp],
+    "ast_accumulate": [_P(Image), _P(Image), _vp],
+    "ast_mask_add": [_P(Image), _P(Image), _P(Image), _P(Image), _vp],
+}
+EXPORTS = sorted(list(_SIGNATURES) + ["ast_instnorm_workspace_bytes", "ast_last_error", "ast_abi_version",
+                                      "ast_launch_count"])
+
+
+def load():
+    """Load the shared library (no CUDA call is made here, so this also works on a CPU-only box)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C artist_style_transfer_b200/csrc`). There is no CPU/PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.ast_instnorm_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    lib.ast_instnorm_workspace_bytes.restype = ctypes.c_int64
+    lib.ast_last_error.restype = ctypes.c_char_p
+    lib.ast_abi_version.restype = ctypes.c_int
+    lib.ast_launch_count.restype = ctypes.c_int64
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ast_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def image(t):
+    """ast_image of a 4-D tensor given in logical (N, H, W, C) order with arbitrary strides."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("artist_style_transfer_b200 kernels need CUDA tensors (no CPU fallback)")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    return Image(t.data_ptr(), _DTYPES[t.dtype], n, h, w, c, sn, sh, sw, sc)
+
+
+def ref(img):
+    return None if img is None else ctypes.byref(img)
+
+
+def launch_count():
+    return int(load().ast_launch_count())

@@ -1,0 +1,345 @@
+"""B200-native mirror of the reference transform network (`/root/reference/cnn.py`).
+
+Same class names, constructor arguments, forward signatures and `state_dict` keys as the reference
+(`StyleTransfer` cnn.py:10-49, `ConvLayer` :52-79, `ResidualLayer` :82-99, `DeconvLayer` :102-124), so
+reference checkpoints load with `strict=True`.  Underneath, every layer is a sequence of calls into
+libast_b200.so (hand-written sm_100a kernels); there is no PyTorch-op or CPU fallback.
+
+Internal data flow: activations are NHWC; each stage is
+    gather-conv (raw, pre-norm)  ->  InstanceNorm stats  ->  fused apply (+ReLU, +residual) that writes the
+    next conv's reflection-padded input buffer directly.
+The backward pass runs the same stages in reverse inside one autograd.Function.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import conv_geometry as cg
+from . import ops
+
+# precision modes (north_star): 'fp32' = strict, FFMA kernels, fp32 activations;
+# 'fast' = bf16 activations/weights for the transform net on tcgen05 where the shape is supported.
+_MODES = ("fp32", "fast")
+_default_mode = "fp32"
+
+
+def set_default_precision(mode):
+    global _default_mode
+    if mode not in _MODES:
+        raise ValueError(f"precision must be one of {_MODES}")
+    _default_mode = mode
+
+
+def get_default_precision():
+    return _default_mode
+
+
+class _ConvParams(nn.Module):
+    """Parameter holder laid out like nn.Conv2d / nn.ConvTranspose2d (weight, bias) with PyTorch's default init."""
+
+    def __init__(self, weight_shape, fan_in, bias_size):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(weight_shape))
+        self.bias = nn.Parameter(torch.empty(bias_size))
+        bound = 1.0 / math.sqrt(fan_in)
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)   # == kaiming_uniform_(a=sqrt(5))
+            self.bias.uniform_(-bound, bound)
+
+
+class _NormParams(nn.Module):
+    """Parameter holder of nn.InstanceNorm2d(affine=True): weight=1, bias=0, no running stats."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+
+
+class _Stage:
+    __slots__ = ("kind", "cin", "cout", "k", "stride", "opad", "norm", "relu", "res_from", "conv", "normp")
+
+    def __init__(self, kind, cin, cout, k, stride, opad, norm, relu, res_from, conv, normp):
+        self.kind, self.cin, self.cout, self.k, self.stride, self.opad = kind, cin, cout, k, stride, opad
+        self.norm, self.relu, self.res_from, self.conv, self.normp = norm, relu, res_from, conv, normp
+
+    @property
+    def in_pad(self):
+        return self.k // 2 if (self.kind == "conv" and self.k > 1) else 0
+
+
+def _interior(t, p):
+    return t if p == 0 else t[:, p:t.shape[1] - p, p:t.shape[2] - p, :]
+
+
+def _fwd_geometry(st, hin, win):
+    if st.kind == "conv":
+        ls = cg.conv_fwd(st.k, st.stride, 0, hin, win)
+        return ls, ls[0].mi, ls[0].mj
+    ho = cg.convT_out_size(hin, st.k, st.stride, st.k // 2, st.opad)
+    wo = cg.convT_out_size(win, st.k, st.stride, st.k // 2, st.opad)
+    return cg.convT_fwd(st.k, st.stride, st.k // 2, st.opad, hin, win), ho, wo
+
+
+def _pack_fwd(st, w, launches, dtype):
+    k2 = st.k * st.k
+    if st.kind == "conv":      # (Co,Ci,k,k) -> [t][co][ci]
+        return ops.pack_weights(w, launches, st.cout, st.cin, st.cin * k2, k2, st.k, 1, dtype)
+    return ops.pack_weights(w, launches, st.cout, st.cin, k2, st.cout * k2, st.k, 1, dtype)  # (Ci,Co,k,k)
+
+
+def _pack_dgrad(st, w, launches, dtype):
+    k2 = st.k * st.k
+    if st.kind == "conv":      # [t][ci][co]
+        return ops.pack_weights(w, launches, st.cin, st.cout, k2, st.cin * k2, st.k, 1, dtype)
+    return ops.pack_weights(w, launches, st.cin, st.cout, st.cout * k2, k2, st.k, 1, dtype)
+
+
+class _StageFunction(torch.autograd.Function):
+    """Forward/backward of a list of stages as ONE autograd node (x: NCHW fp32 in, NCHW fp32 out)."""
+
+    @staticmethod
+    def forward(ctx, x, stages, mode, *params):
+        if not x.is_cuda:
+            raise RuntimeError("StyleTransfer kernels run on CUDA only (no CPU fallback); move the module and "
+                               "input to a B200")
+        adt = torch.bfloat16 if mode == "fast" else torch.float32
+        x = x.detach().to(torch.float32)
+        n, _, h, w = x.shape
+        dev = x.device
+        pit = iter(params)
+        P = []
+        for st in stages:
+            cw, cb = next(pit), next(pit)
+            P.append((cw, cb, next(pit), next(pit)) if st.norm else (cw, cb, None, None))
+        p0 = stages[0].in_pad
+        node = torch.empty((n, h + 2 * p0, w + 2 * p0, stages[0].cin), dtype=adt, device=dev)
+        ops.copy_image(x.permute(0, 2, 3, 1), node, pad=p0)
+        nodes, node_pad, saved = [node], [p0], []
+        out = None
+        for i, st in enumerate(stages):
+            cw, cb, gam, bet = P[i]
+            xin = nodes[-1]
+            launches, ho, wo = _fwd_geometry(st, xin.shape[1], xin.shape[2])
+            wp = _pack_fwd(st, cw.detach(), launches, adt)
+            last = i == len(stages) - 1
+            if not st.norm:
+                assert last, "a stage without norm must be the last one"
+                out = torch.empty((n, st.cout, ho, wo), dtype=torch.float32, device=dev)
+                ops.conv_gather(xin, wp, launches, out.permute(0, 2, 3, 1), bias=cb.detach(), relu=st.relu)
+                saved.append((launches, None, None, None))
+            else:
+                raw = torch.empty((n, ho, wo, st.cout), dtype=adt, device=dev)
+                ops.conv_gather(xin, wp, launches, raw)     # conv bias is dead under InstanceNorm
+                mean, rstd = ops.instnorm_stats(raw)
+                pn = 0 if last else stages[i + 1].in_pad
+                post = torch.empty((n, ho + 2 * pn, wo + 2 * pn, st.cout), dtype=adt, device=dev)
+                res = None
+                if st.res_from is not None:
+                    j = st.res_from + 1
+                    res = _interior(nodes[j], node_pad[j])
+                ops.instnorm_apply(raw, mean, rstd, gam.detach(), bet.detach(), post, pn, st.relu, residual=res)
+                nodes.append(post)
+                node_pad.append(pn)
+                saved.append((launches, raw, mean, rstd))
+                if last:
+                    out = torch.empty((n, st.cout, ho, wo), dtype=torch.float32, device=dev)
+                    ops.copy_image(post, out.permute(0, 2, 3, 1))
+        ctx.stages, ctx.mode, ctx.P = stages, mode, P
+        ctx.nodes, ctx.node_pad, ctx.saved = nodes, node_pad, saved
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        stages, P, nodes, node_pad, saved = ctx.stages, ctx.P, ctx.nodes, ctx.node_pad, ctx.saved
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. the input image is not part of the training path "
+                                      "(train_cnn.py:298-299 feeds data that does not require grad)")
+        adt = nodes[0].dtype
+        gout = gout.to(torch.float32)
+        L = len(stages)
+        gpad = [None] * (L + 1)
+        gextra = [None] * (L + 1)
+        grads = []
+        for i in reversed(range(L)):
+            st = stages[i]
+            cw, cb, gam, bet = P[i]
+            launches, raw, mean, rstd = saved[i]
+            xin = nodes[i]
+            if not st.norm:
+                d_raw = gout.permute(0, 2, 3, 1)
+                g_cb = gout.sum(dim=(0, 2, 3))
+                g_gam = g_bet = None
+            else:
+                j = i + 1
+                n, ho, wo, c = raw.shape
+                if i == L - 1:
+                    ge = torch.empty((n, ho, wo, c), dtype=torch.float32, device=raw.device)
+                    ops.copy_image(gout.permute(0, 2, 3, 1), ge)
+                    gextra[j] = ge
+                d_raw = torch.empty_like(raw)
+                gtotal = torch.empty_like(raw) if st.res_from is not None else None
+                s1, s2 = ops.instnorm_bwd(raw, mean, rstd, gam.detach(), bet.detach(), gpad[j], node_pad[j],
+                                          gextra[j], st.relu, d_raw, gtotal)
+                g_bet = s1.view(n, c).sum(0)
+                g_gam = s2.view(n, c).sum(0)
+                g_cb = torch.zeros_like(cb)          # exactly zero under InstanceNorm
+                if gtotal is not None:
+                    assert gextra[st.res_from + 1] is None
+                    gextra[st.res_from + 1] = gtotal
+                gpad[j] = gextra[j] = None           # free
+            k2 = st.k * st.k
+            g_cw = torch.zeros_like(cw, dtype=torch.float32)
+            if st.kind == "conv":
+                ops.wgrad_gather(xin, d_raw, launches, g_cw, st.cin * k2, k2, st.k, 1)
+            else:
+                ops.wgrad_gather(xin, d_raw, launches, g_cw, k2, st.cout * k2, st.k, 1)
+            if i > 0:
+                if st.kind == "conv":
+                    dl = cg.conv_dgrad(st.k, st.stride, 0, xin.shape[1], xin.shape[2])
+                else:
+                    dl = cg.convT_dgrad(st.k, st.stride, st.k // 2, d_raw.shape[1], d_raw.shape[2])
+                wpd = _pack_dgrad(st, cw.detach(), dl, adt)
+                g_in = torch.empty(xin.shape, dtype=adt, device=xin.device)
+                src = d_raw
+                if src.dtype != adt:               # fp32 NCHW grad of the last conv feeding a bf16 dgrad
+                    src = torch.empty(d_raw.shape, dtype=adt, device=xin.device)
+                    ops.copy_image(d_raw, src)
+                ops.conv_gather(src, wpd, dl, g_in)
+                gpad[i] = g_in
+            grads.append((g_cw, g_cb, g_gam, g_bet))
+        grads.reverse()
+        flat = []
+        for st, (g_cw, g_cb, g_gam, g_bet) in zip(stages, grads):
+            flat += [g_cw, g_cb]
+            if st.norm:
+                flat += [g_gam, g_bet]
+        ctx.nodes = ctx.saved = None
+        return (None, None, None, *flat)
+
+
+def _run_stages(x, stages, mode):
+    params = []
+    for st in stages:
+        params += [st.conv.weight, st.conv.bias]
+        if st.norm:
+            params += [st.normp.weight, st.normp.bias]
+    return _StageFunction.apply(x, tuple(stages), mode, *params)
+
+
+class _Precision:
+    precision = None  # None -> module default (set_default_precision)
+
+    def _mode(self):
+        return self.precision or _default_mode
+
+
+class ConvLayer(nn.Module, _Precision):
+    """ReflectionPad(k//2) -> Conv2d(k, stride) -> InstanceNorm2d(affine) (cnn.py:52-79)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, norm="instance"):
+        super().__init__()
+        if norm not in ("instance", "None"):
+            raise ValueError("only norm='instance' or 'None' is on the accelerated path (cnn.py:66-70 'batch' is unused)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.norm_type = kernel_size, stride, norm
+        self.conv_layer = _ConvParams((out_channels, in_channels, kernel_size, kernel_size),
+                                      in_channels * kernel_size * kernel_size, out_channels)
+        if norm == "instance":
+            self.norm_layer = _NormParams(out_channels)
+
+    def _stage(self, relu=False, res_from=None):
+        return _Stage("conv", self.in_channels, self.out_channels, self.kernel_size, self.stride, 0,
+                      self.norm_type == "instance", relu, res_from, self.conv_layer,
+                      getattr(self, "norm_layer", None))
+
+    def forward(self, x):
+        return _run_stages(x, [self._stage()], self._mode())
+
+
+class ResidualLayer(nn.Module, _Precision):
+    """conv2(relu(conv1(x))) + x, no activation after the add (cnn.py:82-99)."""
+
+    def __init__(self, channels=128, kernel_size=3):
+        super().__init__()
+        self.conv1 = ConvLayer(channels, channels, kernel_size, stride=1)
+        self.relu = nn.ReLU()
+        self.conv2 = ConvLayer(channels, channels, kernel_size, stride=1)
+
+    def _stages(self, base):
+        """`base` = index of the stage whose output is this block's input (-1 = the run's input)."""
+        return [self.conv1._stage(relu=True), self.conv2._stage(relu=False, res_from=base)]
+
+    def forward(self, x):
+        return _run_stages(x, self._stages(-1), self._mode())
+
+
+class DeconvLayer(nn.Module, _Precision):
+    """ConvTranspose2d(k, stride, padding=k//2, output_padding) -> InstanceNorm2d(affine) (cnn.py:102-124)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, output_padding, norm="instance"):
+        super().__init__()
+        if norm != "instance":
+            raise ValueError("only norm='instance' is on the accelerated path")
+        if (kernel_size, stride, output_padding) not in ((1, 1, 0), (3, 2, 1)):
+            raise ValueError("DeconvLayer supports (k,stride,output_padding) = (1,1,0) or (3,2,1) (cnn.py:33-37)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.output_padding, self.norm_type = kernel_size, stride, output_padding, norm
+        self.conv_transpose = _ConvParams((in_channels, out_channels, kernel_size, kernel_size),
+                                          out_channels * kernel_size * kernel_size, out_channels)
+        self.norm_layer = _NormParams(out_channels)
+
+    def _stage(self, relu=False):
+        return _Stage("deconv", self.in_channels, self.out_channels, self.kernel_size, self.stride,
+                      self.output_padding, True, relu, None, self.conv_transpose, self.norm_layer)
+
+    def forward(self, x):
+        return _run_stages(x, [self._stage()], self._mode())
+
+
+class StyleTransfer(nn.Module, _Precision):
+    """Johnson-style image transform net with the reference's two extra 1x1 layers (cnn.py:10-49).
+
+    `StyleTransfer(state_dict_filename=None, device=None, precision=None)`; master parameters stay fp32
+    (the reference's `.double()` at cnn.py:43 is not reproduced: fp64 has no tensor-core path).
+    """
+
+    def __init__(self, state_dict_filename=None, device=None, precision=None):
+        if device is None:
+            device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        super().__init__()
+        self.precision = precision
+        self.ConvBlock = nn.Sequential(
+            ConvLayer(3, 32, 9, 1), nn.ReLU(),
+            ConvLayer(32, 64, 3, 2), nn.ReLU(),
+            ConvLayer(64, 128, 3, 2), nn.ReLU(),
+            ConvLayer(128, 128, 1, 1), nn.ReLU())
+        self.ResidualBlock = nn.Sequential(*[ResidualLayer(128, 3) for _ in range(5)])
+        self.DeconvBlock = nn.Sequential(
+            DeconvLayer(128, 128, 1, 1, 0), nn.ReLU(),
+            DeconvLayer(128, 64, 3, 2, 1), nn.ReLU(),
+            DeconvLayer(64, 32, 3, 2, 1), nn.ReLU(),
+            ConvLayer(32, 3, 9, 1, norm="None"))
+        if state_dict_filename is not None:
+            self.load_state_dict(torch.load(state_dict_filename, map_location=device), strict=True)
+        self.to(device)
+
+    def _stages(self):
+        stages = []
+        for block in (self.ConvBlock, self.ResidualBlock, self.DeconvBlock):
+            mods = list(block)
+            for idx, m in enumerate(mods):
+                nxt_relu = idx + 1 < len(mods) and isinstance(mods[idx + 1], nn.ReLU)
+                if isinstance(m, (ConvLayer, DeconvLayer)):
+                    stages.append(m._stage(relu=nxt_relu))
+                elif isinstance(m, ResidualLayer):
+                    stages += m._stages(len(stages) - 1)
+        return stages
+
+    def forward(self, x):
+        return _run_stages(x, self._stages(), self._mode())
+
+
+TransformerNet = StyleTransfer  # north_star's name for the same network

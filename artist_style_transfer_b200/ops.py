@@ -1,0 +1,270 @@
+"""Thin Python wrappers over the C ABI (include/ast.h).  Tensors are passed in logical (N,H,W,C) order.
+
+Everything here launches CUDA kernels from libast_b200.so on the current torch stream; nothing falls back
+to PyTorch ops.
+"""
+import functools
+
+import torch
+
+from . import _lib
+from . import conv_geometry as cg
+from ._lib import CONV_REFLECT, CONV_RELU, CONV_TENSOR, GatherGeom, check, image, ptr, ref, stream_ptr
+
+_DT = {torch.float32: _lib.AST_F32, torch.bfloat16: _lib.AST_BF16}
+
+# ---- optional per-family CUDA-event timing (bench.py roofline leg); off by default, zero cost when off
+_prof = None
+
+
+class _timed:
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.label, self.e0, e1))
+        return False
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {label: (total_ms, launches)} measured with CUDA events on the launching stream."""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for label, e0, e1 in _prof or []:
+        ms, cnt = out.get(label, (0.0, 0))
+        out[label] = (ms + e0.elapsed_time(e1), cnt + 1)
+    _prof = None
+    return out
+
+
+def _geom(launch, flags=0, w_img_stride=0):
+    g = GatherGeom()
+    g.mi, g.mj, g.si, g.so, g.oy0, g.ox0 = launch.mi, launch.mj, launch.si, launch.so, launch.oy0, launch.ox0
+    g.ntaps = len(launch.taps)
+    g.flags = flags
+    for t, (dy, dx) in enumerate(launch.taps):
+        g.dy[t] = dy
+        g.dx[t] = dx
+    g.w_img_stride = w_img_stride
+    return g
+
+
+@functools.lru_cache(maxsize=None)
+def _tap_offsets_cached(key, device_index):
+    return torch.tensor(list(key), dtype=torch.int32, device=torch.device("cuda", device_index))
+
+
+def tap_offsets(wtaps, s_u, s_v, device):
+    """int32 device table of weight offsets u*s_u + v*s_v for each tap."""
+    return _tap_offsets_cached(tuple(u * s_u + v * s_v for u, v in wtaps), device.index or 0)
+
+
+def _pack_weights_impl(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
+    """Pack fp32 master weights into [taps][a][b] (`dtype`) for the given launches (ast_pack_weights)."""
+    wt = cg.all_wtaps(launches)
+    offs = tap_offsets(wt, s_u, s_v, w.device)
+    out = torch.empty((len(wt), a, b), dtype=dtype, device=w.device)
+    check(_lib.load().ast_pack_weights(ptr(w), ptr(offs), len(wt), a, b, s_a, s_b, ptr(out), _DT[dtype],
+                                       stream_ptr()), "ast_pack_weights")
+    return out
+
+
+def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
+                reflect=False, tensor=False, w_img_stride=0):
+    """Run every launch of an op. x/out/add/mask: (N,H,W,C)-ordered tensors; wpacked: [taps][cout][cin]."""
+    lib = _lib.load()
+    flags = (CONV_RELU if relu else 0) | (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
+    xi, oi, ai, mi = image(x), image(out), image(add), image(mask)
+    cout, cin = wpacked.shape[-2], wpacked.shape[-1]
+    esz = wpacked.element_size()
+    for l in launches:
+        g = _geom(l, flags, w_img_stride)
+        wp = _lib.ctypes.c_void_p(wpacked.data_ptr() + l.woff * cout * cin * esz)
+        check(lib.ast_conv_gather(ref(xi), wp, ptr(bias), ptr(in_shift), ref(ai), ref(mi), ref(oi), ref(g),
+                                  stream_ptr()), "ast_conv_gather")
+    return out
+
+
+def _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False):
+    """dw (fp32, pre-zeroed) += filter gradient for every launch of the op."""
+    lib = _lib.load()
+    flags = CONV_REFLECT if reflect else 0
+    xi, gi = image(x), image(gout)
+    for l in launches:
+        offs = tap_offsets(l.wtaps, s_u, s_v, dw.device)
+        g = _geom(l, flags)
+        check(lib.ast_wgrad_gather(ref(xi), ref(gi), ptr(dw), ptr(offs), s_co, s_ci, ref(g), stream_ptr()),
+              "ast_wgrad_gather")
+    return dw
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index or 0)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _instnorm_stats_impl(x, eps=1e-5):
+    n, _, _, c = x.shape
+    mean = torch.empty(n * c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    lib = _lib.load()
+    ws = _workspace(lib.ast_instnorm_workspace_bytes(n, c), x.device)
+    xi = image(x)
+    check(lib.ast_instnorm_stats(ref(xi), ptr(mean), ptr(rstd), eps, ptr(ws), stream_ptr()), "ast_instnorm_stats")
+    return mean, rstd
+
+
+def _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=None):
+    xi, oi, ri = image(x), image(out), image(residual)
+    check(_lib.load().ast_instnorm_apply(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(ri), ref(oi),
+                                         pad, int(relu), stream_ptr()), "ast_instnorm_apply")
+    return out
+
+
+def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None):
+    """Returns (s1, s2) with dbeta = s1.view(N,C).sum(0), dgamma = s2.view(N,C).sum(0); fills dx (and gtotal)."""
+    n, _, _, c = x.shape
+    s1 = torch.empty(n * c, dtype=torch.float32, device=x.device)
+    s2 = torch.empty_like(s1)
+    lib = _lib.load()
+    xi, gp, ge, dxi, gt = image(x), image(gpad), image(gextra), image(dx), image(gtotal)
+    check(lib.ast_instnorm_bwd_stats(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge),
+                                     int(relu), ptr(s1), ptr(s2), stream_ptr()), "ast_instnorm_bwd_stats")
+    check(lib.ast_instnorm_bwd_apply(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge),
+                                     int(relu), ptr(s1), ptr(s2), ref(dxi), ref(gt), stream_ptr()),
+          "ast_instnorm_bwd_apply")
+    return s1, s2
+
+
+def _maxpool2_fwd_impl(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+    xi, yi = image(x), image(y)
+    check(_lib.load().ast_maxpool2_fwd(ref(xi), ref(yi), stream_ptr()), "ast_maxpool2_fwd")
+    return y
+
+
+def _maxpool2_bwd_impl(x, gy, gadd=None):
+    gx = torch.empty(x.shape, dtype=gy.dtype, device=x.device)
+    xi, gyi, gai, gxi = image(x), image(gy), image(gadd), image(gx)
+    check(_lib.load().ast_maxpool2_bwd(ref(xi), None, ref(gyi), ref(gai), ref(gxi), stream_ptr()), "ast_maxpool2_bwd")
+    return gx
+
+
+def _gram_impl(x, scale, tensor=False):
+    n, _, _, c = x.shape
+    g = torch.empty((n, c, c), dtype=torch.float32, device=x.device)
+    xi = image(x)
+    check(_lib.load().ast_gram(ref(xi), ptr(g), scale, CONV_TENSOR if tensor else 0, stream_ptr()), "ast_gram")
+    return g
+
+
+def _mse_impl(a, b, loss, scale, grad=None, gscale=0.0):
+    ai, bi, gi = image(a), image(b), image(grad)
+    check(_lib.load().ast_mse(ref(ai), ref(bi), ptr(loss), scale, ref(gi), gscale, stream_ptr()), "ast_mse")
+    return loss
+
+
+def _copy_image_impl(src, dst, shift=None, pad=0):
+    si, di = image(src), image(dst)
+    check(_lib.load().ast_copy_image(ref(si), ref(di), ptr(shift), pad, stream_ptr()), "ast_copy_image")
+    return dst
+
+
+def _accumulate_impl(x, acc):
+    xi, ai = image(x), image(acc)
+    check(_lib.load().ast_accumulate(ref(xi), ref(ai), stream_ptr()), "ast_accumulate")
+    return acc
+
+
+def _mask_add_impl(a, b, mask, out):
+    ai, bi, mi, oi = image(a), image(b), image(mask), image(out)
+    check(_lib.load().ast_mask_add(ref(ai), ref(bi), ref(mi), ref(oi), stream_ptr()), "ast_mask_add")
+    return out
+
+
+def pack_weights(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
+    with _timed("pack"):
+        return _pack_weights_impl(w, launches, a, b, s_a, s_b, s_u, s_v, dtype)
+
+
+def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
+                reflect=False, tensor=False, w_img_stride=0):
+    with _timed("conv_gather"):
+        return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu, reflect=reflect, tensor=tensor, w_img_stride=w_img_stride)
+
+
+def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False):
+    with _timed("wgrad_gather"):
+        return _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=reflect)
+
+
+def instnorm_stats(x, eps=1e-5):
+    with _timed("instnorm"):
+        return _instnorm_stats_impl(x, eps=eps)
+
+
+def instnorm_apply(x, mean, rstd, gamma, beta, out, pad, relu, residual=None):
+    with _timed("instnorm"):
+        return _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=residual)
+
+
+def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None):
+    with _timed("instnorm"):
+        return _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=gtotal)
+
+
+def maxpool2_fwd(x):
+    with _timed("pointwise"):
+        return _maxpool2_fwd_impl(x)
+
+
+def maxpool2_bwd(x, gy, gadd=None):
+    with _timed("pointwise"):
+        return _maxpool2_bwd_impl(x, gy, gadd=gadd)
+
+
+def gram(x, scale, tensor=False):
+    with _timed("gram"):
+        return _gram_impl(x, scale, tensor=tensor)
+
+
+def mse(a, b, loss, scale, grad=None, gscale=0.0):
+    with _timed("pointwise"):
+        return _mse_impl(a, b, loss, scale, grad=grad, gscale=gscale)
+
+
+def copy_image(src, dst, shift=None, pad=0):
+    with _timed("pointwise"):
+        return _copy_image_impl(src, dst, shift=shift, pad=pad)
+
+
+def accumulate(x, acc):
+    with _timed("pointwise"):
+        return _accumulate_impl(x, acc)
+
+
+def mask_add(a, b, mask, out):
+    with _timed("pointwise"):
+        return _mask_add_impl(a, b, mask, out)

@@ -1,0 +1,396 @@
+"""B200-native mirror of the loss side of `/root/reference/train_cnn.py`.
+
+Drop-in pieces (same names / signatures / return types as the reference):
+  VGG16(just_content=False, vgg_path=...)            train_cnn.py:50-78
+  gram(f)                                             train_cnn.py:101-107
+and the loop body / style-setup blocks restated as functions:
+  style_grams_single(...)                             train_cnn.py:184-190 ('random'), :199-204 ('average')
+  style_grams_smartaverage(...)                       train_cnn.py:224-244
+  perceptual_step(...)                                train_cnn.py:295-333
+  PerceptualTrainer                                   train_cnn.py:247-248,295-334 (+ data-parallel allreduce)
+All arithmetic runs in libast_b200.so; `nn.MSELoss` on the returned tensors still works and differentiates.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import cnn as _cnn
+from . import conv_geometry as cg
+from . import ops
+from .cnn import _ConvParams
+
+CONTENT_WEIGHT = 17  # train_cnn.py:40
+STYLE_WEIGHT = 25    # train_cnn.py:41
+LR = 0.0024          # train_cnn.py:38
+IMAGENET_NEG_MEAN = (-103.939, -116.779, -123.68)  # BGR, train_cnn.py:164
+
+_VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]
+_TAPS = {3: "relu1_2", 8: "relu2_2", 15: "relu3_3", 22: "relu4_3"}
+
+
+def _vgg_layout():
+    """[(idx, kind, cin, cout)] of torchvision vgg16().features."""
+    layers, cin, idx = [], 3, 0
+    for v in _VGG_CFG:
+        if v == "M":
+            layers.append((idx, "pool", cin, cin)); idx += 1
+        else:
+            layers.append((idx, "conv", cin, v)); layers.append((idx + 1, "relu", v, v)); idx += 2
+            cin = v
+    return layers
+
+
+class _VGGFunction(torch.autograd.Function):
+    """conv3x3(pad 1)+ReLU / maxpool chain up to `upto`, returning the tapped activations (NCHW views)."""
+
+    @staticmethod
+    def forward(ctx, x, module, upto, shift, *weights):
+        if not x.is_cuda:
+            raise RuntimeError("VGG16 kernels run on CUDA only (no CPU fallback)")
+        tensor = module._mode() == "fast"
+        x32 = x.detach().to(torch.float32)
+        n, _, h, w = x32.shape
+        dev = x32.device
+        cur = x32.permute(0, 2, 3, 1)            # NCHW tensor described as an (N,H,W,C) view; conv1_1 reads it directly
+        acts, taps, plan = {}, [], []
+        packed = module._packed(tensor)
+        for idx, kind, cin, cout in module._layout:
+            if idx > upto:
+                break
+            if kind == "conv":
+                launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
+                out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
+                wp, bias = packed[idx]
+                ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None,
+                                relu=True, tensor=tensor and cin % 32 == 0)
+                plan.append((idx, "conv", cur, out))
+                cur = out
+            elif kind == "pool":
+                out = ops.maxpool2_fwd(cur)
+                plan.append((idx, "pool", cur, out))
+                cur = out
+            if idx in _TAPS:
+                taps.append((idx, cur))
+        ctx.module, ctx.plan, ctx.tensor = module, plan, tensor
+        ctx.tap_idx = [i for i, _ in taps]
+        outs = tuple(t.permute(0, 3, 1, 2) for _, t in taps)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gtaps):
+        module, plan, tensor = ctx.module, ctx.plan, ctx.tensor
+        tapg = {}
+        for idx, g in zip(ctx.tap_idx, gtaps):
+            if g is not None:
+                g = g.to(torch.float32).permute(0, 2, 3, 1)
+                if not g.is_contiguous():
+                    gc = torch.empty(g.shape, dtype=torch.float32, device=g.device)
+                    ops.copy_image(g, gc)
+                    g = gc
+                tapg[idx] = g
+        packed = module._packed_dgrad(tensor)
+        g = None            # gradient w.r.t. the OUTPUT of the current plan entry (already ReLU-masked for convs)
+        gx = None
+        for pos in reversed(range(len(plan))):
+            idx, kind, xin, out = plan[pos]
+            if kind == "pool":
+                if g is None:
+                    continue
+                # out = pool(xin); xin is the ReLU output of the conv before: route + add its tap grad + mask
+                prev_relu_idx = idx - 1
+                g = ops.maxpool2_bwd(xin, g, tapg.pop(prev_relu_idx, None))
+                continue
+            relu_idx = idx + 1
+            if relu_idx in tapg:   # tap gradient not yet folded in (only when no pool/conv consumer did it)
+                t = tapg.pop(relu_idx)
+                m = torch.empty_like(t)
+                ops.mask_add(t, g, out, m)       # (tap grad + downstream grad) * (relu out > 0)
+                g = m
+            if g is None:
+                continue
+            # g is d/d(relu out) masked == d/d(conv out).  dgrad to the conv input:
+            if idx == 0:
+                gx = torch.empty((out.shape[0], 3, out.shape[1], out.shape[2]), dtype=torch.float32, device=g.device)
+                launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
+                ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1))
+                break
+            launches = cg.conv_dgrad(3, 1, 1, xin.shape[1], xin.shape[2])
+            gin = torch.empty(xin.shape, dtype=torch.float32, device=g.device)
+            # the conv input is either a ReLU output (mask here, add its tap grad) or a pool output (no mask)
+            prev_kind = plan[pos - 1][1]
+            cout_prev = xin.shape[3]
+            use_tc = tensor and cout_prev % 32 == 0 and g.shape[3] % 32 == 0
+            if prev_kind == "conv":
+                ops.conv_gather(g, packed[idx], launches, gin, add=tapg.pop(idx - 1, None), mask=xin, tensor=use_tc)
+            else:
+                ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc)
+            g = gin
+        ctx.plan = None
+        return (gx, None, None, None) + tuple(None for _ in module._weights())
+
+
+class VGG16(nn.Module, _cnn._Precision):
+    """Frozen VGG16 feature extractor returning {'relu1_2','relu2_2','relu3_3','relu4_3'} (train_cnn.py:50-78).
+
+    Input is BGR, 0-255, Caffe-mean-subtracted (train_cnn.py:164,300-301).  `forward(x, shift=...)` can fuse
+    that subtraction into conv1_1's loader; `forward(x, upto='relu2_2')` stops early (content branch).
+    """
+
+    def __init__(self, just_content=False, vgg_path="models/vgg16-00b39a1b.pth", precision=None):
+        super().__init__()
+        self.precision = precision
+        self._layout = _vgg_layout()
+        mods = []
+        for idx, kind, cin, cout in self._layout:
+            if kind == "conv":
+                m = _ConvParams((cout, cin, 3, 3), cin * 9, cout)
+                with torch.no_grad():           # torchvision vgg init: kaiming_normal_(fan_out, relu), bias 0
+                    m.weight.normal_(0.0, math.sqrt(2.0 / (cout * 9)))
+                    m.bias.zero_()
+            elif kind == "relu":
+                m = nn.ReLU(inplace=True)       # structural placeholders; compute is in libast_b200.so
+            else:
+                m = nn.MaxPool2d(2, 2)
+            mods.append(m)
+        self.features = nn.Sequential(*mods)
+        if vgg_path is not None and os.path.exists(vgg_path):
+            self.load_state_dict(torch.load(vgg_path, map_location="cpu"), strict=False)   # train_cnn.py:55
+        self.just_content = just_content
+        for p in self.features.parameters():    # train_cnn.py:60-61
+            p.requires_grad = False
+        self._pack_cache = {}
+
+    def _weights(self):
+        return [p for p in self.features.parameters()]
+
+    def _cache_key(self, kind, tensor):
+        return (kind, tensor, tuple(p._version for p in self.features.parameters()),
+                tuple(p.data_ptr() for p in self.features.parameters()))
+
+    def _packed(self, tensor):
+        key = self._cache_key("fwd", tensor)
+        if self._pack_cache.get("fwd_key") != key:
+            out = {}
+            launches = cg.conv_fwd(3, 1, 1, 8, 8)
+            for idx, kind, cin, cout in self._layout:
+                if kind == "conv" and idx <= 21:
+                    m = self.features[idx]
+                    w = m.weight.detach().float()
+                    out[idx] = (ops.pack_weights(w, launches, cout, cin, cin * 9, 9, 3, 1, torch.float32),
+                                m.bias.detach().float())
+            self._pack_cache["fwd_key"], self._pack_cache["fwd"] = key, out
+        return self._pack_cache["fwd"]
+
+    def _packed_dgrad(self, tensor):
+        key = self._cache_key("dgrad", tensor)
+        if self._pack_cache.get("dgrad_key") != key:
+            out = {}
+            launches = cg.conv_dgrad(3, 1, 1, 8, 8)
+            for idx, kind, cin, cout in self._layout:
+                if kind == "conv" and idx <= 21:
+                    w = self.features[idx].weight.detach().float()
+                    out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1, torch.float32)
+            self._pack_cache["dgrad_key"], self._pack_cache["dgrad"] = key, out
+        return self._pack_cache["dgrad"]
+
+    def forward(self, x, shift=None, upto=None):
+        if self.just_content or upto == "relu2_2":
+            last = 8
+        elif upto is None or upto == "relu4_3":
+            last = 22
+        else:
+            last = {v: k for k, v in _TAPS.items()}[upto]
+        if x.dim() == 3:
+            x = x.unsqueeze(0)
+        outs = _VGGFunction.apply(x, self, last, shift, *self._weights())
+        if self.just_content:
+            return outs[-1]                                        # train_cnn.py:64-68
+        names = [v for k, v in _TAPS.items() if k <= last]
+        return dict(zip(names, outs))                              # insertion order relu1_2..relu4_3 (:70-77)
+
+
+class _GramFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, tensor):
+        b, c, h, w = f.shape
+        fv = f.detach()
+        if fv.dtype not in (torch.float32, torch.bfloat16):
+            fv = fv.float()
+        ctx.save_for_backward(fv)
+        ctx.tensor = tensor
+        return ops.gram(fv.permute(0, 2, 3, 1), 1.0 / (c * h * w), tensor=tensor)
+
+    @staticmethod
+    def backward(ctx, dg):
+        (fv,) = ctx.saved_tensors
+        b, c, h, w = fv.shape
+        # dF = (dG + dG^T) F / (CHW): a 1x1 gather-conv with per-image C x C weights
+        d = ((dg + dg.transpose(1, 2)) * (1.0 / (c * h * w))).to(fv.dtype).contiguous()
+        x = fv.permute(0, 2, 3, 1)
+        out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
+        launches = cg.conv_fwd(1, 1, 0, h, w)
+        ops.conv_gather(x, d.view(b, 1, c, c), launches, out, w_img_stride=c * c,
+                        tensor=ctx.tensor and x.is_contiguous() and c % 32 == 0 and fv.dtype == torch.float32)
+        return out.permute(0, 3, 1, 2), None
+
+
+def gram(f, precision=None):
+    """G = F F^T / (C H W) for F = f.view(b, c, h*w) (train_cnn.py:103-107). f: [B,C,H,W] -> [B,C,C]."""
+    if not f.is_cuda:
+        raise RuntimeError("gram() runs on CUDA only (no CPU fallback)")
+    mode = precision or _cnn.get_default_precision()
+    return _GramFunction.apply(f, mode == "fast")
+
+
+def neg_mean(device):
+    return torch.tensor(IMAGENET_NEG_MEAN, dtype=torch.float32, device=device)
+
+
+def style_grams_single(vgg, style_tensor, batch_size):
+    """'random' / 'average' style setup (train_cnn.py:184-190): one (3,H,W) image -> 4 x [B,C,C].
+
+    The reference expands the image to the batch and runs B identical VGG passes; the Grams are identical
+    per row, so one pass is computed and the result expanded (same values, 1/B of the work).
+    """
+    with torch.no_grad():
+        feats = vgg(style_tensor.float().unsqueeze(0) if style_tensor.dim() == 3 else style_tensor.float(),
+                    shift=neg_mean(style_tensor.device))
+        return {k: gram(v).expand(batch_size, -1, -1).contiguous() for k, v in feats.items()}
+
+
+def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group=None):
+    """'smartaverage' artist style (train_cnn.py:224-244).
+
+    mode='reference': sum the VGG features over the artist's paintings, divide by the count, ONE Gram of the
+    mean feature (exactly the reference).  mode='mean_gram': mean of per-painting Grams (north-star
+    wording).  With `group` (torch.distributed), each rank passes ITS shard of the paintings and the sums are
+    all-reduced (NCCL) before the division; `paintings` is a list of (3,H,W) tensors or a [P,3,H,W] tensor.
+    """
+    import torch.distributed as dist
+    acc, count = None, 0
+    shift = None
+    with torch.no_grad():
+        for p in paintings:
+            shift = neg_mean(p.device) if shift is None else shift
+            feats = vgg(p.float().unsqueeze(0), shift=shift)
+            cur = {}
+            for k, v in feats.items():
+                cur[k] = v.permute(0, 2, 3, 1) if mode == "reference" else gram(v)
+            if acc is None:
+                acc = {k: torch.zeros(v.shape, dtype=torch.float32, device=v.device) for k, v in cur.items()}
+            for k, v in cur.items():
+                if mode == "reference":
+                    ops.accumulate(v, acc[k])                      # train_cnn.py:239 in-place feature sum
+                else:
+                    ops.accumulate(v.unsqueeze(0), acc[k].unsqueeze(0))
+            count += 1
+        total = torch.tensor([float(count)], device=next(iter(acc.values())).device)
+        if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            for k in acc:
+                dist.all_reduce(acc[k], op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        length = float(total.item())
+        out = {}
+        for k, v in acc.items():
+            if mode == "reference":
+                # gram(sum/len) == gram(sum)/len^2: folds train_cnn.py:242-243's divide into a C x C scale
+                g = gram(v.permute(0, 3, 1, 2)) / (length * length)
+            else:
+                g = v / length
+            out[k] = g.expand(batch_size, -1, -1).contiguous()
+        return out
+
+
+class _MSEFunction(torch.autograd.Function):
+    """mean((a-b)^2) with the gradient w.r.t. `a` produced in the same pass (nn.MSELoss, train_cnn.py:249,307)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        av = a.detach().permute(0, 2, 3, 1)
+        bv = b.detach().permute(0, 2, 3, 1)
+        loss = torch.zeros(1, dtype=torch.float32, device=a.device)
+        grad = torch.empty(av.shape, dtype=torch.float32, device=a.device) if a.requires_grad else None
+        numel = a.numel()
+        ops.mse(av, bv, loss, 1.0 / numel, grad, 2.0 / numel)
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        ga = ctx.grad.permute(0, 3, 1, 2) * g if ctx.grad is not None else None
+        return ga, None
+
+
+def mse_loss(a, b):
+    """Fused MSE forward+gradient for two [B,C,H,W] tensors (b is treated as a constant)."""
+    return _MSEFunction.apply(a, b)
+
+
+def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CONTENT_WEIGHT,
+                    style_weight=STYLE_WEIGHT, backward=True):
+    """The loop body of train_cnn.py:295-333 (methods 'random'/'average'/'smartaverage'), without the optimizer.
+
+    Returns (content_loss, style_loss, total_loss) as 0-d device tensors (no host sync).
+    Differences from the reference that do not change results: the mean shift is fused into conv1_1's loader,
+    and the content branch stops at relu2_2 (the reference computes relu3_3/relu4_3 and discards them).
+    """
+    shift = neg_mean(content_batch.device)
+    generated = transfer(content_batch)                                        # :299
+    with torch.no_grad():
+        content_feat = vgg(content_batch, shift=shift, upto="relu2_2")["relu2_2"]   # :300
+    gen_feats = vgg(generated, shift=shift)                                    # :301
+    content_loss = mse_loss(gen_feats["relu2_2"], content_feat) * content_weight    # :307-308
+    style_loss = 0
+    for key, value in gen_feats.items():                                       # :321-325
+        g = gram(value)
+        style_loss = style_loss + mse_loss(g.unsqueeze(1), style_gram[key].unsqueeze(1))
+    style_loss = style_loss * style_weight
+    total = content_loss + style_loss                                          # :329
+    if backward:
+        total.backward()                                                       # :333
+    return content_loss.detach(), style_loss.detach(), total.detach()
+
+
+class PerceptualTrainer:
+    """Optimizer side of train() (train_cnn.py:247-248,295,334,375) plus data-parallel gradient averaging.
+
+    One process per GPU; when torch.distributed is initialised the TransformerNet gradients are flattened
+    into one 1,712,771-float bucket and averaged with a single NCCL all-reduce per step.
+    """
+
+    def __init__(self, transfer, vgg, style_gram, lr=LR, weight_decay=1e-4, num_epochs=200, num_steps=2,
+                 content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT, group=None):
+        self.transfer, self.vgg, self.style_gram = transfer, vgg, style_gram
+        self.content_weight, self.style_weight = content_weight, style_weight
+        self.params = [p for p in transfer.parameters()]
+        self.optimizer = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay)          # :247
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=max(1, num_epochs // num_steps),
+                                                         gamma=0.5)                                # :248
+        self.group = group
+        self._flat = None
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        grads = [p.grad for p in self.params]
+        if self._flat is None:
+            self._flat = torch.empty(sum(g.numel() for g in grads), dtype=torch.float32, device=grads[0].device)
+        torch._foreach_copy_(list(self._flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        dist.all_reduce(self._flat, op=dist.ReduceOp.AVG if grads[0].is_cuda else dist.ReduceOp.SUM, group=self.group)
+        if not grads[0].is_cuda:
+            self._flat /= dist.get_world_size(self.group)
+        torch._foreach_copy_([g.reshape(-1) for g in grads], list(self._flat.split([g.numel() for g in grads])))
+
+    def step(self, content_batch):
+        self.optimizer.zero_grad(set_to_none=True)                                                 # :295
+        losses = perceptual_step(self.transfer, self.vgg, content_batch, self.style_gram,
+                                 self.content_weight, self.style_weight, backward=True)
+        self._allreduce_grads()
+        self.optimizer.step()                                                                      # :334
+        return losses
+
+    def end_epoch(self):
+        self.scheduler.step()                                                                      # :375

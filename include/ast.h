@@ -1,0 +1,138 @@
+/*
+ * ast.h - C ABI of libast_b200.so: the B200 (sm_100a) kernels behind the perceptual-loss
+ * training step of edogariu/artist-style-transfer.
+ *
+ * Drop-in boundary: the reference has no native code; the "FFI" it binds for this
+ * path is the set of PyTorch library calls listed next to each entry point below.  Host code stays
+ * Python/PyTorch (artist_style_transfer_b200/{cnn,train_cnn}.py mirror the reference modules) and
+ * reaches these functions through ctypes with raw device pointers - no torch types cross the ABI.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 for an argument/shape/unsupported-config error
+ *     (never a silent fallback), >0 for a cudaError_t / CUresult; ast_last_error() has the text.
+ *   - the caller owns every buffer (inputs, outputs, workspaces) and keeps it alive until the work
+ *     queued on `stream` has completed; the library never allocates device memory and keeps no
+ *     pointers after return.  Launches are asynchronous on `stream`.
+ *   - images are N x H x W x C views with explicit element strides (ast_image); the internal layout
+ *     is NHWC (sc == 1), but NCHW tensors of the reference API are described with sc == H*W.
+ */
+#ifndef AST_B200_H
+#define AST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AST_ABI_VERSION 1
+
+typedef enum { AST_F32 = 0, AST_BF16 = 1 } ast_dtype;
+
+/* strided 4-D view; strides in ELEMENTS.  */
+typedef struct {
+  void*   ptr;
+  int32_t dtype;          /* ast_dtype */
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw, sc;
+} ast_image;
+
+#define AST_MAX_TAPS 81
+
+/* A "gather" convolution: for every point (i,j) of an Mi x Mj iteration grid
+ *   out[n, oy0 + so*i, ox0 + so*j, co] = epi( sum_t sum_ci  in[n, si*i + dy[t], si*j + dx[t], ci] * W[t][co][ci] )
+ * Out-of-range input coordinates read 0 (or are mirrored when AST_CONV_REFLECT is set).
+ * This single primitive expresses (tap tables are built by the host mirror, conv_geometry.py):
+ *   nn.Conv2d stride 1/2 after nn.ReflectionPad2d      cnn.py:58,63,73-74   (si = stride)
+ *   its data gradient (aten::convolution_backward)      train_cnn.py:333     (so = stride, 4 phases)
+ *   nn.ConvTranspose2d k3 s2 p1 op1 and k1 s1           cnn.py:107-109,119   (so = 2, 4 sub-pixel phases)
+ *   torchvision VGG16 Conv2d(3x3, pad 1) + ReLU         train_cnn.py:54,72-73
+ *   the Gram backward  dF = (dG + dG^T) F / (CHW)       train_cnn.py:107,333 (1 tap, per-image weights)
+ */
+typedef struct {
+  int32_t mi, mj;          /* iteration grid per image */
+  int32_t si, so;          /* input / output coordinate multipliers */
+  int32_t oy0, ox0;        /* output phase offset */
+  int32_t ntaps;
+  int32_t flags;           /* AST_CONV_* */
+  int16_t dy[AST_MAX_TAPS];
+  int16_t dx[AST_MAX_TAPS];
+  int64_t w_img_stride;    /* elements between per-image weight sets, 0 = shared weights */
+} ast_gather_geom;
+
+#define AST_CONV_RELU     1   /* epilogue max(v,0)                       (nn.ReLU, train_cnn.py VGG idx 1,3,...)   */
+#define AST_CONV_REFLECT  2   /* mirror out-of-range input coordinates   (nn.ReflectionPad2d, cnn.py:58)          */
+#define AST_CONV_TENSOR   4   /* request the tcgen05/TMA kernel; error if the shape is not supported              */
+
+/* weights: packed [ntaps][cout][cin], same dtype as `in`.  bias: fp32[cout] or NULL.
+ * in_shift: fp32[cin] added to in-range inputs before the product (VGG mean shift, train_cnn.py:300-301) or NULL.
+ * add:  optional image added before the activation (tap-gradient accumulation in the VGG backward).
+ * mask: optional image; out = (mask > 0) ? v : 0 after the activation (ReLU backward, threshold_backward). */
+int ast_conv_gather(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
+                    const ast_image* add, const ast_image* mask, const ast_image* out,
+                    const ast_gather_geom* geom, void* stream);
+
+/* Weight gradient of the same gather convolution (aten::convolution_backward, filter part):
+ *   dw[tap_off[t] + co*s_co + ci*s_ci] += sum_{n,i,j} gout[n, oy0+so*i, ox0+so*j, co] * x[n, si*i+dy[t], si*j+dx[t], ci]
+ * dw is fp32 and must be zeroed (or hold a running sum) by the caller; accumulation uses fp32 atomics. */
+int ast_wgrad_gather(const ast_image* x, const ast_image* gout, float* dw, const int32_t* tap_off,
+                     int64_t s_co, int64_t s_ci, const ast_gather_geom* geom, void* stream);
+
+/* Re-pack fp32 master weights into the [ntaps][a][b] operand layout of ast_conv_gather:
+ *   dst[t][ia][ib] = src[tap_off[t] + ia*s_a + ib*s_b]      (dst dtype = ast_dtype) */
+int ast_pack_weights(const float* src, const int32_t* tap_off, int32_t ntaps, int32_t a, int32_t b,
+                     int64_t s_a, int64_t s_b, void* dst, int32_t dst_dtype, void* stream);
+
+/* nn.InstanceNorm2d(affine=True), eps 1e-5, biased variance (cnn.py:68,114).
+ * stats: mean[n*c], rstd[n*c] (fp32).  workspace: ast_instnorm_workspace_bytes(). */
+int64_t ast_instnorm_workspace_bytes(int32_t n, int32_t c);
+int ast_instnorm_stats(const ast_image* x, float* mean, float* rstd, float eps, void* workspace, void* stream);
+/* y = gamma*(x-mean)*rstd + beta (+ residual) (ReLU if relu), written to the interior of `out`, which is an
+ * (h+2*pad) x (w+2*pad) image whose border is filled by mirroring (the next layer's nn.ReflectionPad2d). */
+int ast_instnorm_apply(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, const ast_image* residual, const ast_image* out, int32_t pad,
+                       int32_t relu, void* stream);
+/* Backward of (ReflectionPad o ReLU o (+residual) o InstanceNorm).
+ *   g'   = (fold_reflect(gpad, pad) + gextra) * (relu ? y>0 : 1)
+ *   s1[n,c] = sum g' ; s2[n,c] = sum g'*xhat                       (pass 1, ast_instnorm_bwd_stats)
+ *   dx   = gamma*rstd*(g' - s1/HW - xhat*s2/HW) ; gtotal = g'      (pass 2, ast_instnorm_bwd_apply)
+ * gpad may be NULL (no padded consumer), gextra may be NULL, gtotal may be NULL. */
+int ast_instnorm_bwd_stats(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, const ast_image* gpad, int32_t pad, const ast_image* gextra,
+                           int32_t relu, float* s1, float* s2, void* stream);
+int ast_instnorm_bwd_apply(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, const ast_image* gpad, int32_t pad, const ast_image* gextra,
+                           int32_t relu, const float* s1, const float* s2, const ast_image* dx,
+                           const ast_image* gtotal, void* stream);
+
+/* nn.MaxPool2d(2,2) of torchvision vgg16.features idx 4/9/16 and its backward fused with the tap-gradient add
+ * and the ReLU mask of the producing layer:  gx = (route(gy) + gadd) * (x > 0). */
+int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, void* stream);
+int ast_maxpool2_bwd(const ast_image* x, const ast_image* y, const ast_image* gy, const ast_image* gadd,
+                     const ast_image* gx, void* stream);
+
+/* gram(), train_cnn.py:103-107:  G[n] = F[n] F[n]^T * scale, F = x viewed as (c, h*w).  G fp32 [n][c][c], zeroed here. */
+int ast_gram(const ast_image* x, float* g, float scale, int32_t flags, void* stream);
+
+/* nn.MSELoss pieces (train_cnn.py:249,307,323): loss[0] += scale * sum((a-b)^2) ; grad = gscale*(a-b) (optional).
+ * a/b/grad are images of identical logical shape. */
+int ast_mse(const ast_image* a, const ast_image* b, float* loss, float scale, const ast_image* grad,
+            float gscale, void* stream);
+
+/* dst = src converted/re-strided (NCHW fp32 <-> NHWC bf16/fp32), optional per-channel shift, reflect pad. */
+int ast_copy_image(const ast_image* src, const ast_image* dst, const float* shift, int32_t pad, void* stream);
+/* acc(fp32 image) += x   ('smartaverage' in-place feature sum, train_cnn.py:239) */
+int ast_accumulate(const ast_image* x, const ast_image* acc, void* stream);
+
+/* out = (a + b) * (mask > 0)   (b may be NULL; nn.ReLU backward on an incoming tap gradient) */
+int ast_mask_add(const ast_image* a, const ast_image* b, const ast_image* mask, const ast_image* out, void* stream);
+
+const char* ast_last_error(void);
+int ast_abi_version(void);
+/* number of kernel launches issued through this library by the calling process (bench.py gpu_launches) */
+int64_t ast_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

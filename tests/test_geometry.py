@@ -1,0 +1,95 @@
+"""CPU check of the tap tables (conv_geometry.py) against torch.nn.functional, through a torch emulation
+of the gather primitive's definition in include/ast.h (no CUDA)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from artist_style_transfer_b200 import conv_geometry as cg
+
+
+def emulate_gather(x, wt, launches, out_hw, reflect=False):
+    """x: [N,H,W,Ci]; wt: [T][Co][Ci]; returns [N,Ho,Wo,Co] following the formula in ast.h."""
+    n, h, w, ci = x.shape
+    co = wt.shape[1]
+    out = torch.full((n, out_hw[0], out_hw[1], co), float("nan"), dtype=x.dtype)
+    for l in launches:
+        acc = torch.zeros((n, l.mi, l.mj, co), dtype=x.dtype)
+        ii = torch.arange(l.mi)
+        jj = torch.arange(l.mj)
+        for t, (dy, dx) in enumerate(l.taps):
+            y = l.si * ii + dy
+            xx = l.si * jj + dx
+            if reflect:
+                y = y.abs(); y = torch.where(y >= h, 2 * (h - 1) - y, y)
+                xx = xx.abs(); xx = torch.where(xx >= w, 2 * (w - 1) - xx, xx)
+                oky = torch.ones_like(y, dtype=torch.bool); okx = torch.ones_like(xx, dtype=torch.bool)
+            else:
+                oky = (y >= 0) & (y < h); okx = (xx >= 0) & (xx < w)
+            g = x[:, y.clamp(0, h - 1)][:, :, xx.clamp(0, w - 1)]
+            g = g * (oky[:, None] & okx[None, :])[None, :, :, None]
+            acc += g @ wt[l.woff + t].T
+        oy = l.oy0 + l.so * ii
+        ox = l.ox0 + l.so * jj
+        ky, kx = oy < out_hw[0], ox < out_hw[1]
+        out[:, oy[ky][:, None], ox[kx][None, :]] = acc[:, ky][:, :, kx]
+    assert not torch.isnan(out).any(), "launches do not cover the output"
+    return out
+
+
+def pack(w, launches, a_dim, b_dim):
+    """[T][a][b] from a 4-D weight whose dims (a_dim, b_dim, 2, 3) = (a, b, u, v)."""
+    return torch.stack([w.select(3, v).select(2, u).permute(*((0, 1) if a_dim < b_dim else (1, 0)))
+                        for u, v in cg.all_wtaps(launches)])
+
+
+@pytest.mark.parametrize("k,s,h,w", [(9, 1, 12, 14), (3, 1, 8, 8), (3, 2, 10, 12), (1, 1, 5, 6), (3, 2, 9, 11)])
+def test_conv_fwd_reflect_padded(k, s, h, w):
+    torch.manual_seed(0)
+    x = torch.randn(2, 5, h, w, dtype=torch.float64)
+    wt = torch.randn(7, 5, k, k, dtype=torch.float64)
+    xp = F.pad(x, (k // 2,) * 4, mode="reflect") if k > 1 else x
+    ref = F.conv2d(xp, wt, stride=s)
+    ls = cg.conv_fwd(k, s, 0, xp.shape[2], xp.shape[3])
+    got = emulate_gather(xp.permute(0, 2, 3, 1), pack(wt, ls, 0, 1), ls, ref.shape[2:])
+    torch.testing.assert_close(got.permute(0, 3, 1, 2), ref)
+    # same thing from the unpadded image with the REFLECT flag
+    ls2 = cg.conv_fwd(k, s, k // 2, h, w)
+    got2 = emulate_gather(x.permute(0, 2, 3, 1), pack(wt, ls2, 0, 1), ls2, ref.shape[2:], reflect=True)
+    torch.testing.assert_close(got2.permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("k,s,pad,h,w", [(3, 1, 1, 8, 9), (3, 1, 0, 10, 10), (3, 2, 0, 10, 12), (9, 1, 0, 20, 20),
+                                         (1, 1, 0, 4, 4), (3, 2, 0, 11, 9)])
+def test_conv_dgrad(k, s, pad, h, w):
+    torch.manual_seed(1)
+    x = torch.randn(2, 4, h, w, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(6, 4, k, k, dtype=torch.float64)
+    y = F.conv2d(x, wt, stride=s, padding=pad)
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    ls = cg.conv_dgrad(k, s, pad, h, w)
+    got = emulate_gather(gy.permute(0, 2, 3, 1), pack(wt, ls, 1, 0), ls, (h, w))   # [t][ci][co]
+    torch.testing.assert_close(got.permute(0, 3, 1, 2), gx)
+
+
+@pytest.mark.parametrize("k,s,op,h,w", [(3, 2, 1, 6, 7), (1, 1, 0, 5, 5)])
+def test_convT_fwd_and_dgrad(k, s, op, h, w):
+    torch.manual_seed(2)
+    x = torch.randn(2, 4, h, w, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(4, 6, k, k, dtype=torch.float64)       # ConvTranspose2d layout (Ci,Co,k,k)
+    y = F.conv_transpose2d(x, wt, stride=s, padding=k // 2, output_padding=op)
+    ls = cg.convT_fwd(k, s, k // 2, op, h, w)
+    got = emulate_gather(x.detach().permute(0, 2, 3, 1), pack(wt, ls, 1, 0), ls, y.shape[2:])   # [t][co][ci]
+    torch.testing.assert_close(got.permute(0, 3, 1, 2), y.detach())
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    ld = cg.convT_dgrad(k, s, k // 2, y.shape[2], y.shape[3])
+    gotd = emulate_gather(gy.permute(0, 2, 3, 1), pack(wt, ld, 0, 1), ld, (h, w))               # [t][ci][co]
+    torch.testing.assert_close(gotd.permute(0, 3, 1, 2), gx)
+
+
+def test_sizes():
+    assert cg.conv_out_size(258, 3, 2, 0) == 128
+    assert cg.convT_out_size(64, 3, 2, 1, 1) == 128
+    assert sum(len(l.taps) for l in cg.convT_fwd(3, 2, 1, 1, 8, 8)) == 9
+    assert [len(l.taps) for l in cg.convT_fwd(3, 2, 1, 1, 8, 8)] == [1, 2, 2, 4]      # SURVEY 8c sub-pixel phases
