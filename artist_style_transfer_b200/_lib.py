@@ -55,7 +55,7 @@ _SIGNATURES = {
     "ast_mask_add": [_P(Image), _P(Image), _P(Image), _P(Image), _vp],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["ast_instnorm_workspace_bytes", "ast_last_error", "ast_abi_version",
-                                      "ast_launch_count"])
+                                      "ast_launch_count", "ast_capabilities"])
 
 
 def load():
@@ -77,6 +77,7 @@ def load():
     lib.ast_last_error.restype = ctypes.c_char_p
     lib.ast_abi_version.restype = ctypes.c_int
     lib.ast_launch_count.restype = ctypes.c_int64
+    lib.ast_capabilities.restype = ctypes.c_int
     _lib = lib
     return lib
 
@@ -108,6 +109,14 @@ def image(t):
 
 def ref(img):
     return None if img is None else ctypes.byref(img)
+
+
+def has_tc_conv():
+    return bool(load().ast_capabilities() & 1)
+
+
+def has_tc_gram():
+    return bool(load().ast_capabilities() & 2)
 
 
 def launch_count():

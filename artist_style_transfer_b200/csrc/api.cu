@@ -19,3 +19,6 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* ast_last_error(void) { return ast::g_err; }
 extern "C" int ast_abi_version(void) { return AST_ABI_VERSION; }
 extern "C" int64_t ast_launch_count(void) { return ast::g_launches.load(); }
+
+namespace ast { int tc_capabilities(); }
+extern "C" int ast_capabilities(void) { return ast::tc_capabilities(); }

@@ -10,4 +10,5 @@ int gram_tc(const ast_image*, float*, float, cudaStream_t) {
   set_error("tcgen05 gram kernel not built into this library");
   return -2;
 }
+int tc_capabilities() { return 0; }
 }  // namespace ast

@@ -175,6 +175,8 @@ def _maxpool2_bwd_impl(x, gy, gadd=None):
 def _gram_impl(x, scale, tensor=False):
     n, _, _, c = x.shape
     g = torch.empty((n, c, c), dtype=torch.float32, device=x.device)
+    if n == 0 or c == 0:
+        return g
     xi = image(x)
     check(_lib.load().ast_gram(ref(xi), ptr(g), scale, CONV_TENSOR if tensor else 0, stream_ptr()), "ast_gram")
     return g

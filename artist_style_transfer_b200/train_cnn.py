@@ -16,6 +16,7 @@ import os
 import torch
 import torch.nn as nn
 
+from . import _lib
 from . import cnn as _cnn
 from . import conv_geometry as cg
 from . import ops
@@ -49,7 +50,7 @@ class _VGGFunction(torch.autograd.Function):
     def forward(ctx, x, module, upto, shift, *weights):
         if not x.is_cuda:
             raise RuntimeError("VGG16 kernels run on CUDA only (no CPU fallback)")
-        tensor = module._mode() == "fast"
+        tensor = module._mode() == "fast" and _lib.has_tc_conv()
         x32 = x.detach().to(torch.float32)
         n, _, h, w = x32.shape
         dev = x32.device
@@ -232,7 +233,7 @@ class _GramFunction(torch.autograd.Function):
         out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
         launches = cg.conv_fwd(1, 1, 0, h, w)
         ops.conv_gather(x, d.view(b, 1, c, c), launches, out, w_img_stride=c * c,
-                        tensor=ctx.tensor and x.is_contiguous() and c % 32 == 0 and fv.dtype == torch.float32)
+                        tensor=ctx.tensor and _lib.has_tc_conv() and x.is_contiguous() and c % 32 == 0 and fv.dtype == torch.float32)
         return out.permute(0, 3, 1, 2), None
 
 
@@ -241,7 +242,7 @@ def gram(f, precision=None):
     if not f.is_cuda:
         raise RuntimeError("gram() runs on CUDA only (no CPU fallback)")
     mode = precision or _cnn.get_default_precision()
-    return _GramFunction.apply(f, mode == "fast")
+    return _GramFunction.apply(f, mode == "fast" and _lib.has_tc_gram())
 
 
 def neg_mean(device):

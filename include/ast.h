@@ -127,6 +127,8 @@ int ast_accumulate(const ast_image* x, const ast_image* acc, void* stream);
 /* out = (a + b) * (mask > 0)   (b may be NULL; nn.ReLU backward on an incoming tap gradient) */
 int ast_mask_add(const ast_image* a, const ast_image* b, const ast_image* mask, const ast_image* out, void* stream);
 
+/* bitmask of the tensor-core kernels compiled into this build: 1 = tcgen05 gather conv, 2 = tcgen05 Gram/wgrad */
+int ast_capabilities(void);
 const char* ast_last_error(void);
 int ast_abi_version(void);
 /* number of kernel launches issued through this library by the calling process (bench.py gpu_launches) */

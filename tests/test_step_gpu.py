@@ -180,7 +180,11 @@ def test_trainer_step_matches_oracle_adam(ast):
     for name, p in net.named_parameters():
         if name.endswith("conv_layer.bias") or name.endswith("conv_transpose.bias"):
             continue
-        assert rel(p, params[name]) < 1e-4, name
+        # Adam's first steps move every weight by ~lr*sign(g): fp32-vs-fp64 noise on near-zero gradients flips a few
+        # signs, so compare the mean displacement against lr rather than element-wise
+        diff = (p.detach().double().cpu() - params[name]).abs()
+        assert float(diff.mean()) < 0.05 * 1e-3, (name, float(diff.mean()))
+        assert float(diff.max()) < 2.5 * 2 * 1e-3, (name, float(diff.max()))
 
 
 def test_launch_counter(ast):
