@@ -1,0 +1,413 @@
+// tcgen05 / TMEM / TMA implicit-GEMM "gather" convolution for sm_100a (Blackwell B200).
+//
+//   D[128 pixels x BN couts] (fp32, TMEM)  +=  A_tap[128 pixels x KC cin] (smem, TMA)  x  W_tap[BN x KC]^T (smem, TMA)
+//
+// One persistent CTA per SM, warp-specialised (DESIGN.md "conv_tc"):
+//   warp 0      TMA producer: per (tap, cin-chunk) one 4-D box of the NHWC activation tensor (OOB = zero padding,
+//               elementStrides = input stride) and one 2-D box of the packed weights, 128B/64B-swizzled, K-major
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::f16 for bf16, kind::tf32 for fp32 data),
+//               tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld 32x32b -> bias / tap-gradient add / ReLU / ReLU-mask / tf32 rounding ->
+//               16-byte vector stores straight to the NHWC output (double-buffered accumulator in TMEM)
+// Replaces cuDNN/oneDNN convolution forward / backward-data at the call sites listed in include/ast.h.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ast {
+
+constexpr int TC_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+struct TcParams {
+  int mi, mj, tw, th, tiles_i, tiles_j, n_img, n_tiles_n, bn;
+  int ntaps, kchunks, kc;
+  int si, so, oy0, ox0;
+  int cout, flags;
+  int w_rows_per_img;
+  int stages, a_bytes, stage_bytes, rowb;
+  unsigned idesc, layout_type, sbo;
+  long long total_tiles;
+  short dy[AST_MAX_TAPS];
+  short dx[AST_MAX_TAPS];
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                       unsigned idesc, unsigned accumulate) {
+  if (KIND == 0)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, float* v) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO | SBO | version=1 | swizzle
+__device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, unsigned sbo_bytes, unsigned layout_type) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
+  d |= (unsigned long long)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (unsigned long long)(sbo_bytes >> 4) << 32;        // stride byte offset: 8 rows of one swizzle atom
+  d |= (unsigned long long)1 << 46;                       // descriptor version 1 (Blackwell)
+  d |= (unsigned long long)layout_type << 61;
+  return d;
+}
+__device__ __forceinline__ float round_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------ kernel
+template <int KIND>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const TcParams p,
+               const float* __restrict__ bias, const Img add, const Img mask, const Img out) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ unsigned tmem_slot;
+
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ksteps = p.ntaps * p.kchunks;
+  const unsigned tmem_cols = (2 * p.bn <= 32) ? 32 : (2 * p.bn <= 64) ? 64 : (2 * p.bn <= 128) ? 128 : (2 * p.bn <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    int s = 0; unsigned ph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long r = tile;
+      const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
+      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
+      const int ti = (int)(r % p.tiles_i);
+      const int img = (int)(r / p.tiles_i);
+      const int x0 = p.si * tj * p.tw, y0 = p.si * ti * p.th;
+      const int wrow0 = img * p.w_rows_per_img + nt * p.bn;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int cx = x0 + p.dx[t], cy = y0 + p.dy[t];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (lane == 0) {
+            unsigned char* sa = smem + (size_t)s * p.stage_bytes;
+            mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
+            tma_load_4d(sa, &tm_in, &full_bar[s], kc * p.kc, cx, cy, img);
+            tma_load_2d(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
+    const int kmma = p.rowb / 32;   // UMMA_K spans 32 bytes for both bf16 (16 elems) and tf32 (8 elems)
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const unsigned d_tmem = tmem_base + (unsigned)(as * p.bn);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const unsigned b_addr = a_addr + p.a_bytes;
+          for (int k = 0; k < kmma; ++k) {
+            const unsigned long long ad = make_smem_desc(a_addr + k * 32, p.sbo, p.layout_type);
+            const unsigned long long bd = make_smem_desc(b_addr + k * 32, p.sbo, p.layout_type);
+            tc_mma<KIND>(d_tmem, ad, bd, p.idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
+          if (ks == ksteps - 1) tc_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else {
+    // ============================ epilogue (warps 2..5) ============================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int ty = row / p.tw, tx = row % p.tw;
+    int as = 0; unsigned aph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long r = tile;
+      const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
+      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
+      const int ti = (int)(r % p.tiles_i);
+      const int img = (int)(r / p.tiles_i);
+      const int i = ti * p.th + ty, j = tj * p.tw + tx;
+      const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
+      const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        float v[32];
+        tc_ld32(taddr0 + c0, v);
+        const int co = nt * p.bn + c0;
+        if (valid && co < p.cout) {
+          if (bias) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += __ldg(bias + co + e);
+          }
+          if (add.ptr) {
+            const long long o = img_off(add, img, oy, ox, co);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) { float t[4]; ld4_img(add, o + e, t); v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3]; }
+          }
+          if (p.flags & AST_CONV_RELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (mask.ptr) {
+            const long long o = img_off(mask, img, oy, ox, co);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              float t[4]; ld4_img(mask, o + e, t);
+              v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f;
+              v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;
+            }
+          }
+          if (p.flags & AST_CONV_ROUND_TF32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+          }
+          const long long oo = img_off(out, img, oy, ox, co);
+          if (out.dtype == AST_F32) {
+            float* op = (float*)out.ptr + oo;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          } else {
+            __nv_bfloat16* op = (__nv_bfloat16*)out.ptr + oo;
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              h[0] = __floats2bfloat162_rn(v[e], v[e + 1]); h[1] = __floats2bfloat162_rn(v[e + 2], v[e + 3]);
+              h[2] = __floats2bfloat162_rn(v[e + 4], v[e + 5]); h[3] = __floats2bfloat162_rn(v[e + 6], v[e + 7]);
+              *reinterpret_cast<uint4*>(op + e) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static bool pick_tile(int mi, int mj, int* tw, int* th) {
+  double best = -1;
+  for (int w = 128; w >= 8; w >>= 1) {
+    const int h = 128 / w;
+    const double cover = (double)((mi + h - 1) / h * h) * ((mj + w - 1) / w * w);
+    const double eff = (double)mi * mj / cover;
+    if (eff > best + 1e-9) { best = eff; *tw = w; *th = h; }
+  }
+  return best > 0;
+}
+
+int tc_capabilities() { return 1; }
+
+int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
+                   const ast_image* add, const ast_image* mask, const ast_image* out, const ast_gather_geom* g,
+                   cudaStream_t stream) {
+  const int esz = in->dtype == AST_F32 ? 4 : 2;
+  AST_CHECK_ARG(!in_shift, "conv_tc: in_shift is only supported by the SIMT kernel");
+  AST_CHECK_ARG(!(g->flags & AST_CONV_REFLECT), "conv_tc: reflect addressing needs a physically padded input");
+  AST_CHECK_ARG(in->sc == 1 && out->sc == 1, "conv_tc: NHWC tensors required");
+  AST_CHECK_ARG((in->c * esz) % 64 == 0, "conv_tc: cin*elemsize must be a multiple of 64 bytes (cin=%d)", in->c);
+  AST_CHECK_ARG(out->c % 32 == 0, "conv_tc: cout must be a multiple of 32 (cout=%d)", out->c);
+  AST_CHECK_ARG(g->si >= 1 && g->si <= 2, "conv_tc: input stride must be 1 or 2");
+  AST_CHECK_ARG(((uintptr_t)in->ptr & 15) == 0 && ((uintptr_t)weights & 15) == 0 && ((uintptr_t)out->ptr & 15) == 0,
+                "conv_tc: pointers must be 16-byte aligned");
+  AST_CHECK_ARG((in->sw * esz) % 16 == 0 && (in->sh * esz) % 16 == 0 && (in->sn * esz) % 16 == 0,
+                "conv_tc: input strides must be multiples of 16 bytes");
+  AST_CHECK_ARG(out->sw % 4 == 0 && out->sh % 4 == 0 && out->sn % 4 == 0, "conv_tc: output strides must be multiples of 4 elements");
+  AST_CHECK_ARG(!add || (add->sc == 1 && add->sw % 4 == 0 && add->sh % 4 == 0 && add->sn % 4 == 0), "conv_tc: add layout");
+  AST_CHECK_ARG(!mask || (mask->sc == 1 && mask->sw % 4 == 0 && mask->sh % 4 == 0 && mask->sn % 4 == 0), "conv_tc: mask layout");
+  if (in->n == 0) return 0;
+  EncodeTiledFn encode = get_encode();
+  AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.mi = g->mi; p.mj = g->mj; p.si = g->si; p.so = g->so; p.oy0 = g->oy0; p.ox0 = g->ox0;
+  p.ntaps = g->ntaps; p.flags = g->flags; p.cout = out->c; p.n_img = in->n;
+  for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = g->dy[t]; p.dx[t] = g->dx[t]; }
+  pick_tile(p.mi, p.mj, &p.tw, &p.th);
+  p.tiles_i = (p.mi + p.th - 1) / p.th;
+  p.tiles_j = (p.mj + p.tw - 1) / p.tw;
+  p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
+  p.kc = p.rowb / esz;
+  p.kchunks = in->c / p.kc;
+  p.bn = out->c % 256 == 0 ? 256 : (out->c <= 256 ? out->c : (out->c % 128 == 0 ? 128 : (out->c % 64 == 0 ? 64 : 32)));
+  AST_CHECK_ARG(p.bn == 32 || p.bn == 64 || p.bn == 128 || p.bn == 256, "conv_tc: unsupported cout %d", out->c);
+  p.n_tiles_n = out->c / p.bn;
+  p.w_rows_per_img = 0;
+  if (g->w_img_stride) {
+    AST_CHECK_ARG(g->w_img_stride == (int64_t)g->ntaps * out->c * in->c, "conv_tc: per-image weights must be densely packed");
+    p.w_rows_per_img = g->ntaps * out->c;
+  }
+  p.a_bytes = 128 * p.rowb;
+  p.stage_bytes = p.a_bytes + p.bn * p.rowb;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.layout_type = p.rowb == 128 ? 2u : 4u;       // SWIZZLE_128B / SWIZZLE_64B
+  p.sbo = 8u * p.rowb;
+  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;   // TF32 / BF16
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j * p.n_tiles_n;
+
+  // ---- tensor maps
+  alignas(64) CUtensorMap tm_in, tm_w;
+  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {(cuuint64_t)in->sw * esz, (cuuint64_t)in->sh * esz, (cuuint64_t)in->sn * esz};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.tw * p.si), (cuuint32_t)(p.th * p.si), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.si, (cuuint32_t)p.si, 1};
+    CUresult r = encode(&tm_in, dt, 4, in->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return (int)r; }
+  }
+  {
+    const long long rows = (long long)g->ntaps * out->c * (g->w_img_stride ? in->n : 1);
+    cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
+  cudaError_t e;
+  if (in->dtype == AST_BF16) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_tc_kernel<0><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+  } else {
+    e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+  }
+  if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+int gram_tc(const ast_image*, float*, float, cudaStream_t) {
+  set_error("tcgen05 gram kernel not built into this library");
+  return -2;
+}
+
+}  // namespace ast

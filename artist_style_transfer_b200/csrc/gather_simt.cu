@@ -155,6 +155,7 @@ conv_gather_simt_kernel(Img in, const TI* __restrict__ wts, const float* __restr
       if (add.ptr) v += ld_elem(add, img_off(add, n, oy, ox, co));
       if (g.flags & AST_CONV_RELU) v = fmaxf(v, 0.f);
       if (mask.ptr) v = ld_elem(mask, img_off(mask, n, oy, ox, co)) > 0.f ? v : 0.f;
+      if (g.flags & AST_CONV_ROUND_TF32) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
       st_elem(out, img_off(out, n, oy, ox, co), v);
     }
   }
@@ -269,7 +270,7 @@ wgrad_gather_simt_kernel(Img x, Img gout, float* __restrict__ dw, const int* __r
   }
 }
 
-template <typename TO>
+template <typename TO, bool ROUND_TF32 = false>
 __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps,
                                     int a, int b, long long s_a, long long s_b, TO* __restrict__ dst) {
   const long long total = (long long)ntaps * a * b;
@@ -278,7 +279,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __
     const int ib = (int)(idx % b);
     const int ia = (int)((idx / b) % a);
     const int t = (int)(idx / ((long long)a * b));
-    DT<TO>::st(dst + idx, src[tap_off[t] + ia * s_a + ib * s_b]);
+    float v = src[tap_off[t] + ia * s_a + ib * s_b];
+    if (ROUND_TF32) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
+    DT<TO>::st(dst + idx, v);
   }
 }
 
@@ -363,6 +366,8 @@ extern "C" int ast_pack_weights(const float* src, const int32_t* tap_off, int32_
   const int blocks = (int)min((total + 255) / 256, (long long)num_sms() * 8);
   if (dst_dtype == AST_F32)
     pack_weights_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, tap_off, ntaps, a, b, s_a, s_b, (float*)dst);
+  else if (dst_dtype == AST_TF32)
+    pack_weights_kernel<float, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, tap_off, ntaps, a, b, s_a, s_b, (float*)dst);
   else if (dst_dtype == AST_BF16)
     pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, tap_off, ntaps, a, b, s_a, s_b, (__nv_bfloat16*)dst);
   else AST_CHECK_ARG(false, "ast_pack_weights: bad dtype %d", dst_dtype);

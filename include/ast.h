@@ -27,7 +27,7 @@ extern "C" {
 
 #define AST_ABI_VERSION 1
 
-typedef enum { AST_F32 = 0, AST_BF16 = 1 } ast_dtype;
+typedef enum { AST_F32 = 0, AST_BF16 = 1, AST_TF32 = 2 /* fp32 storage rounded to TF32; pack_weights only */ } ast_dtype;
 
 /* strided 4-D view; strides in ELEMENTS.  */
 typedef struct {
@@ -63,6 +63,7 @@ typedef struct {
 #define AST_CONV_RELU     1   /* epilogue max(v,0)                       (nn.ReLU, train_cnn.py VGG idx 1,3,...)   */
 #define AST_CONV_REFLECT  2   /* mirror out-of-range input coordinates   (nn.ReflectionPad2d, cnn.py:58)          */
 #define AST_CONV_TENSOR   4   /* request the tcgen05/TMA kernel; error if the shape is not supported              */
+#define AST_CONV_ROUND_TF32 8 /* round the fp32 result to TF32 (cvt.rna) so a kind::tf32 consumer sees exact operands */
 
 /* weights: packed [ntaps][cout][cin], same dtype as `in`.  bias: fp32[cout] or NULL.
  * in_shift: fp32[cin] added to in-range inputs before the product (VGG mean shift, train_cnn.py:300-301) or NULL.

@@ -1,0 +1,134 @@
+"""tcgen05/TMA gather-conv kernel against the SIMT kernel and torch fp64 on identical inputs (B200 only)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from artist_style_transfer_b200 import _lib, conv_geometry as cg, ops
+    if not _lib.has_tc_conv():
+        pytest.skip("library built without the tcgen05 conv kernel")
+    return cg, ops
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def tf32_round(x):
+    return (x.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32) if x.dtype == torch.float32 else x
+
+
+CASES = [
+    # dtype, cin, cout, k, stride, pad, n, h, w
+    (torch.bfloat16, 128, 128, 3, 1, 1, 2, 16, 16),
+    (torch.bfloat16, 64, 128, 3, 1, 1, 1, 8, 16),
+    (torch.bfloat16, 128, 128, 1, 1, 0, 2, 16, 8),
+    (torch.bfloat16, 32, 64, 3, 1, 1, 1, 16, 16),
+    (torch.bfloat16, 64, 32, 3, 1, 1, 1, 20, 12),
+    (torch.bfloat16, 32, 64, 3, 2, 0, 2, 18, 18),
+    (torch.bfloat16, 64, 128, 3, 2, 0, 1, 34, 18),
+    (torch.float32, 64, 64, 3, 1, 1, 2, 16, 16),
+    (torch.float32, 128, 256, 3, 1, 1, 1, 16, 16),
+    (torch.float32, 256, 512, 3, 1, 1, 1, 8, 8),
+    (torch.float32, 512, 512, 3, 1, 1, 2, 4, 4),
+    (torch.float32, 64, 128, 3, 1, 1, 1, 13, 21),
+]
+
+
+@pytest.mark.parametrize("dtype,cin,cout,k,s,pad,n,h,w", CASES)
+def test_conv_fwd_tc(env, dtype, cin, cout, k, s, pad, n, h, w):
+    cg, ops = env
+    torch.manual_seed(cin * 7 + cout + k + s)
+    x = torch.randn(n, h, w, cin, device="cuda").to(dtype)
+    wt = (torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5)
+    bias = torch.randn(cout, device="cuda")
+    launches = cg.conv_fwd(k, s, pad, h, w)
+    ho, wo = launches[0].mi, launches[0].mj
+    wp = ops.pack_weights(wt, launches, cout, cin, cin * k * k, k * k, k, 1, dtype)
+    y_tc = torch.full((n, ho, wo, cout), float("nan"), device="cuda", dtype=torch.float32)
+    ops.conv_gather(x, wp, launches, y_tc, bias=bias, relu=True, tensor=True)
+    y_simt = torch.empty_like(y_tc)
+    ops.conv_gather(x, wp, launches, y_simt, bias=bias, relu=True)
+    torch.cuda.synchronize()
+    xr = x.double().cpu().permute(0, 3, 1, 2)
+    wr = wp.double().cpu().view(k, k, cout, cin).permute(2, 3, 0, 1)
+    if dtype == torch.float32:   # kind::tf32 truncates the operands to 10 mantissa bits
+        tol = 2e-3
+    else:
+        tol = 1e-5               # same bf16 operands, fp32 accumulate: only summation order differs
+    yr = F.relu(F.conv2d(xr, wr, bias.double().cpu(), stride=s, padding=pad)).permute(0, 2, 3, 1)
+    assert not torch.isnan(y_tc).any()
+    assert rel(y_simt, yr) < 1e-5
+    assert rel(y_tc, yr) < tol, rel(y_tc, yr)
+
+
+def test_conv_tc_tf32_exact_when_prerounded(env):
+    """With operands already rounded to TF32 the tensor-core result matches fp32 FFMA to accumulation order."""
+    cg, ops = env
+    from artist_style_transfer_b200 import _lib
+    torch.manual_seed(1)
+    n, h, w, cin, cout = 2, 16, 16, 64, 128
+    x = tf32_round(torch.randn(n, h, w, cin, device="cuda"))
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") / 24
+    launches = cg.conv_fwd(3, 1, 1, h, w)
+    wp = ops.pack_weights(wt, launches, cout, cin, cin * 9, 9, 3, 1, torch.float32)
+    wp = tf32_round(wp)
+    y_tc = torch.empty((n, h, w, cout), device="cuda")
+    y_simt = torch.empty_like(y_tc)
+    ops.conv_gather(x, wp, launches, y_tc, tensor=True)
+    ops.conv_gather(x, wp, launches, y_simt)
+    assert rel(y_tc, y_simt) < 2e-6
+
+
+def test_conv_tc_epilogue_add_mask_stride2_out(env):
+    """dgrad-style launch: output stride 2 phases, tap-gradient add, ReLU mask, bf16 output."""
+    cg, ops = env
+    torch.manual_seed(2)
+    n, h, w, cin, cout = 2, 8, 8, 128, 64          # convT 3x3 s2: (n,8,8,128) -> (n,16,16,64)
+    x = torch.randn(n, h, w, cin, device="cuda").bfloat16()
+    wt = torch.randn(cin, cout, 3, 3, device="cuda") / 30
+    launches = cg.convT_fwd(3, 2, 1, 1, h, w)
+    wp = ops.pack_weights(wt, launches, cout, cin, 9, cout * 9, 3, 1, torch.bfloat16)
+    add = torch.randn(n, 16, 16, cout, device="cuda")
+    mask = torch.randn(n, 16, 16, cout, device="cuda")
+    y_tc = torch.full((n, 16, 16, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    y_simt = torch.empty_like(y_tc)
+    ops.conv_gather(x, wp, launches, y_tc, add=add, mask=mask, tensor=True)
+    ops.conv_gather(x, wp, launches, y_simt, add=add, mask=mask)
+    assert not torch.isnan(y_tc.float()).any()
+    assert rel(y_tc, y_simt) < 5e-3
+    yr = F.conv_transpose2d(x.double().cpu().permute(0, 3, 1, 2), wt.bfloat16().double().cpu(), stride=2, padding=1,
+                            output_padding=1).permute(0, 2, 3, 1)
+    yr = (yr + add.double().cpu()) * (mask.double().cpu() > 0)
+    assert rel(y_tc, yr) < 5e-3
+
+
+def test_conv_tc_per_image_weights(env):
+    """Gram backward shape: 1x1 conv with a different C x C matrix per image."""
+    cg, ops = env
+    torch.manual_seed(3)
+    n, h, w, c = 3, 16, 16, 128
+    x = torch.randn(n, h, w, c, device="cuda")
+    d = torch.randn(n, 1, c, c, device="cuda") / 11
+    launches = cg.conv_fwd(1, 1, 0, h, w)
+    y_tc = torch.empty((n, h, w, c), device="cuda")
+    y_simt = torch.empty_like(y_tc)
+    ops.conv_gather(x, d, launches, y_tc, w_img_stride=c * c, tensor=True)
+    ops.conv_gather(x, d, launches, y_simt, w_img_stride=c * c)
+    assert rel(y_tc, y_simt) < 2e-3
+
+
+def test_conv_tc_rejects_unsupported(env):
+    cg, ops = env
+    x = torch.randn(1, 8, 8, 3, device="cuda")
+    wp = torch.randn(9, 64, 3, device="cuda")
+    y = torch.empty((1, 8, 8, 64), device="cuda")
+    with pytest.raises(RuntimeError, match="conv_tc"):
+        ops.conv_gather(x, wp, cg.conv_fwd(3, 1, 1, 8, 8), y, tensor=True)
