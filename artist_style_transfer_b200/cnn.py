@@ -131,7 +131,8 @@ class _StageFunction(torch.autograd.Function):
                 saved.append((launches, None, None, None))
             else:
                 raw = torch.empty((n, ho, wo, st.cout), dtype=adt, device=dev)
-                ops.conv_gather(xin, wp, launches, raw)     # conv bias is dead under InstanceNorm
+                # conv bias is dead under InstanceNorm and is not added
+                ops.conv_gather(xin, wp, launches, raw, tensor=mode == "fast" and ops.tc_eligible(xin, st.cout))
                 mean, rstd = ops.instnorm_stats(raw)
                 pn = 0 if last else stages[i + 1].in_pad
                 post = torch.empty((n, ho + 2 * pn, wo + 2 * pn, st.cout), dtype=adt, device=dev)
@@ -207,7 +208,7 @@ class _StageFunction(torch.autograd.Function):
                 if src.dtype != adt:               # fp32 NCHW grad of the last conv feeding a bf16 dgrad
                     src = torch.empty(d_raw.shape, dtype=adt, device=xin.device)
                     ops.copy_image(d_raw, src)
-                ops.conv_gather(src, wpd, dl, g_in)
+                ops.conv_gather(src, wpd, dl, g_in, tensor=ctx.mode == "fast" and ops.tc_eligible(src, st.cin))
                 gpad[i] = g_in
             grads.append((g_cw, g_cb, g_gam, g_bet))
         grads.reverse()

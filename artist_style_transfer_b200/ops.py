@@ -11,6 +11,9 @@ from . import _lib
 from . import conv_geometry as cg
 from ._lib import CONV_REFLECT, CONV_RELU, CONV_TENSOR, GatherGeom, check, image, ptr, ref, stream_ptr
 
+CONV_ROUND_TF32 = 8
+TF32 = "tf32"   # pack_weights dtype: fp32 storage rounded to TF32
+
 _DT = {torch.float32: _lib.AST_F32, torch.bfloat16: _lib.AST_BF16}
 
 # ---- optional per-family CUDA-event timing (bench.py roofline leg); off by default, zero cost when off
@@ -77,17 +80,25 @@ def _pack_weights_impl(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
     """Pack fp32 master weights into [taps][a][b] (`dtype`) for the given launches (ast_pack_weights)."""
     wt = cg.all_wtaps(launches)
     offs = tap_offsets(wt, s_u, s_v, w.device)
-    out = torch.empty((len(wt), a, b), dtype=dtype, device=w.device)
-    check(_lib.load().ast_pack_weights(ptr(w), ptr(offs), len(wt), a, b, s_a, s_b, ptr(out), _DT[dtype],
+    out = torch.empty((len(wt), a, b), dtype=torch.float32 if dtype == TF32 else dtype, device=w.device)
+    code = 2 if dtype == TF32 else _DT[dtype]
+    check(_lib.load().ast_pack_weights(ptr(w), ptr(offs), len(wt), a, b, s_a, s_b, ptr(out), code,
                                        stream_ptr()), "ast_pack_weights")
     return out
 
 
+def tc_eligible(x, cout):
+    """Shapes the tcgen05 kernel accepts (conv_tc.cu): cin*elemsize % 64 == 0, cout % 32 == 0, NHWC."""
+    return (_lib.has_tc_conv() and x.stride(3) == 1 and (x.shape[3] * x.element_size()) % 64 == 0
+            and cout % 32 == 0 and cout in (32, 64, 128, 256, 512))
+
+
 def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
-                reflect=False, tensor=False, w_img_stride=0):
+                reflect=False, tensor=False, w_img_stride=0, round_tf32=False):
     """Run every launch of an op. x/out/add/mask: (N,H,W,C)-ordered tensors; wpacked: [taps][cout][cin]."""
     lib = _lib.load()
-    flags = (CONV_RELU if relu else 0) | (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
+    flags = ((CONV_RELU if relu else 0) | (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
+             | (CONV_ROUND_TF32 if round_tf32 else 0))
     xi, oi, ai, mi = image(x), image(out), image(add), image(mask)
     cout, cin = wpacked.shape[-2], wpacked.shape[-1]
     esz = wpacked.element_size()
@@ -211,10 +222,11 @@ def pack_weights(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
         return _pack_weights_impl(w, launches, a, b, s_a, s_b, s_u, s_v, dtype)
 
 
-def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
-                reflect=False, tensor=False, w_img_stride=0):
-    with _timed("conv_gather"):
-        return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu, reflect=reflect, tensor=tensor, w_img_stride=w_img_stride)
+def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False, reflect=False,
+                tensor=False, w_img_stride=0, round_tf32=False):
+    with _timed("conv_gather_tc" if tensor else "conv_gather_simt"):
+        return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu,
+                                 reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32)
 
 
 def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False):

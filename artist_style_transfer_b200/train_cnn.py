@@ -64,8 +64,8 @@ class _VGGFunction(torch.autograd.Function):
                 launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
                 out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
                 wp, bias = packed[idx]
-                ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None,
-                                relu=True, tensor=tensor and cin % 32 == 0)
+                ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None, relu=True,
+                                tensor=tensor and ops.tc_eligible(cur, cout), round_tf32=tensor)
                 plan.append((idx, "conv", cur, out))
                 cur = out
             elif kind == "pool":
@@ -121,12 +121,12 @@ class _VGGFunction(torch.autograd.Function):
             gin = torch.empty(xin.shape, dtype=torch.float32, device=g.device)
             # the conv input is either a ReLU output (mask here, add its tap grad) or a pool output (no mask)
             prev_kind = plan[pos - 1][1]
-            cout_prev = xin.shape[3]
-            use_tc = tensor and cout_prev % 32 == 0 and g.shape[3] % 32 == 0
+            use_tc = tensor and ops.tc_eligible(g, xin.shape[3])
             if prev_kind == "conv":
-                ops.conv_gather(g, packed[idx], launches, gin, add=tapg.pop(idx - 1, None), mask=xin, tensor=use_tc)
+                ops.conv_gather(g, packed[idx], launches, gin, add=tapg.pop(idx - 1, None), mask=xin, tensor=use_tc,
+                                round_tf32=tensor)
             else:
-                ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc)
+                ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc, round_tf32=tensor)
             g = gin
         ctx.plan = None
         return (gx, None, None, None) + tuple(None for _ in module._weights())
@@ -179,8 +179,8 @@ class VGG16(nn.Module, _cnn._Precision):
                 if kind == "conv" and idx <= 21:
                     m = self.features[idx]
                     w = m.weight.detach().float()
-                    out[idx] = (ops.pack_weights(w, launches, cout, cin, cin * 9, 9, 3, 1, torch.float32),
-                                m.bias.detach().float())
+                    out[idx] = (ops.pack_weights(w, launches, cout, cin, cin * 9, 9, 3, 1,
+                                                 ops.TF32 if tensor else torch.float32), m.bias.detach().float())
             self._pack_cache["fwd_key"], self._pack_cache["fwd"] = key, out
         return self._pack_cache["fwd"]
 
@@ -192,7 +192,8 @@ class VGG16(nn.Module, _cnn._Precision):
             for idx, kind, cin, cout in self._layout:
                 if kind == "conv" and idx <= 21:
                     w = self.features[idx].weight.detach().float()
-                    out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1, torch.float32)
+                    out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1,
+                                                ops.TF32 if tensor else torch.float32)
             self._pack_cache["dgrad_key"], self._pack_cache["dgrad"] = key, out
         return self._pack_cache["dgrad"]
 
@@ -214,14 +215,14 @@ class VGG16(nn.Module, _cnn._Precision):
 
 class _GramFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, f, tensor):
+    def forward(ctx, f, fast):
         b, c, h, w = f.shape
         fv = f.detach()
         if fv.dtype not in (torch.float32, torch.bfloat16):
             fv = fv.float()
         ctx.save_for_backward(fv)
-        ctx.tensor = tensor
-        return ops.gram(fv.permute(0, 2, 3, 1), 1.0 / (c * h * w), tensor=tensor)
+        ctx.fast = fast
+        return ops.gram(fv.permute(0, 2, 3, 1), 1.0 / (c * h * w), tensor=fast and _lib.has_tc_gram())
 
     @staticmethod
     def backward(ctx, dg):
@@ -232,8 +233,9 @@ class _GramFunction(torch.autograd.Function):
         x = fv.permute(0, 2, 3, 1)
         out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
         launches = cg.conv_fwd(1, 1, 0, h, w)
+        fast = ctx.fast
         ops.conv_gather(x, d.view(b, 1, c, c), launches, out, w_img_stride=c * c,
-                        tensor=ctx.tensor and _lib.has_tc_conv() and x.is_contiguous() and c % 32 == 0 and fv.dtype == torch.float32)
+                        tensor=fast and x.is_contiguous() and ops.tc_eligible(x, c), round_tf32=fast)
         return out.permute(0, 3, 1, 2), None
 
 
@@ -242,7 +244,7 @@ def gram(f, precision=None):
     if not f.is_cuda:
         raise RuntimeError("gram() runs on CUDA only (no CPU fallback)")
     mode = precision or _cnn.get_default_precision()
-    return _GramFunction.apply(f, mode == "fast" and _lib.has_tc_gram())
+    return _GramFunction.apply(f, mode == "fast")
 
 
 def neg_mean(device):
@@ -345,7 +347,7 @@ def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CON
     content_loss = mse_loss(gen_feats["relu2_2"], content_feat) * content_weight    # :307-308
     style_loss = 0
     for key, value in gen_feats.items():                                       # :321-325
-        g = gram(value)
+        g = gram(value, precision=vgg._mode())
         style_loss = style_loss + mse_loss(g.unsqueeze(1), style_gram[key].unsqueeze(1))
     style_loss = style_loss * style_weight
     total = content_loss + style_loss                                          # :329

@@ -200,12 +200,13 @@ def run_ours(args):
     fam = {k: {"ms_per_step": v[0] / kp, "launches_per_step": v[1] / kp} for k, v in prof.items()}
     scale = (S / 256.0) ** 2
     peaks = read_peaks()
-    conv_ms = fam.get("conv_gather", {"ms_per_step": float("nan")})["ms_per_step"]
+    conv_ms = sum(fam[k]["ms_per_step"] for k in ("conv_gather_tc", "conv_gather_simt") if k in fam)
+    conv_launches = sum(fam[k]["launches_per_step"] for k in ("conv_gather_tc", "conv_gather_simt") if k in fam)
     conv_tf = GF_PER_IMG["conv_gather"] * scale * B / conv_ms            # GF/ms == TF/s
     peak_tf = peaks["bf16_tflops_sustained"]
     roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step)", "bound": "tensor",
                 "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf, "traffic": None,
-                "peak_source": f"{peaks['src']} bf16 sustained", "launch_ms_avg": conv_ms / max(1.0, fam.get('conv_gather', {}).get('launches_per_step', 1.0))}
+                "peak_source": f"{peaks['src']} bf16 sustained", "launch_ms_avg": conv_ms / max(1.0, conv_launches)}
     in_ms = fam.get("instnorm", {"ms_per_step": float("nan")})["ms_per_step"]
     esz = 2 if args.precision == "fast" else 4
     in_gb = IN_ELEMS_PER_IMG * scale * B * esz * 5 / 1e9                 # fwd 1R+1W, bwd 2R+1W
