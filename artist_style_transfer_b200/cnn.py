@@ -193,10 +193,11 @@ class _StageFunction(torch.autograd.Function):
                 gpad[j] = gextra[j] = None           # free
             k2 = st.k * st.k
             g_cw = torch.zeros_like(cw, dtype=torch.float32)
+            wtc = ctx.mode == "fast" and ops.tc_contract_eligible(xin, d_raw)
             if st.kind == "conv":
-                ops.wgrad_gather(xin, d_raw, launches, g_cw, st.cin * k2, k2, st.k, 1)
+                ops.wgrad_gather(xin, d_raw, launches, g_cw, st.cin * k2, k2, st.k, 1, tensor=wtc)
             else:
-                ops.wgrad_gather(xin, d_raw, launches, g_cw, k2, st.cout * k2, st.k, 1)
+                ops.wgrad_gather(xin, d_raw, launches, g_cw, k2, st.cout * k2, st.k, 1, tensor=wtc)
             if i > 0:
                 if st.kind == "conv":
                     dl = cg.conv_dgrad(st.k, st.stride, 0, xin.shape[1], xin.shape[2])

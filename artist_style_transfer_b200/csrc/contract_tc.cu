@@ -1,0 +1,281 @@
+// tcgen05 / TMEM / TMA pixel-contraction kernel for sm_100a: both operands are NHWC activations, i.e. MN-major
+// (channels contiguous) with the reduction running over pixels:
+//
+//   D[m][n] (fp32, TMEM, 128 x BN)  +=  sum_{pixels p in chunk}  R[p'(p)][m0+m] * C[p''(p)][n0+n]
+//
+//   * filter gradient of a gather convolution (aten::convolution_backward, train_cnn.py:333):
+//         R = dY at (oy0+so*i, ox0+so*j),  C = X at (si*i+dy_t, si*j+dx_t),  one CTA column per tap t
+//   * Gram matrix gram() (train_cnn.py:103-107):  R = C = F, one output per image, scale 1/(CHW)
+// Split-K over pixel chunks across CTAs, fp32 atomics into the (pre-zeroed) output.
+// Warp roles as in conv_tc.cu: warp 0 TMA producer (4-D boxes, 128B swizzle, OOB = zero padding, elementStrides =
+// coordinate multiplier), warp 1 tcgen05.mma issuer (MN-major A and B descriptors), warps 2-5 epilogue.
+#include "tc_common.cuh"
+
+namespace ast {
+
+constexpr int CT_THREADS = 192;
+constexpr int CT_MAX_STAGES = 8;
+
+struct CtParams {
+  int mi, mj, tw, th, tiles_i, tiles_j, n_img, kp;
+  int r_s, r_oy, r_ox, c_s;
+  int ntaps, cb, m_boxes, n_boxes, bn;
+  int m_valid, n_valid, m_blocks, n_blocks;
+  int ksplit, chunks_per_cta, per_img;
+  long long chunks_total;           // per image when per_img, else over all images
+  long long out_img_stride, s_m, s_n;
+  float scale;
+  int stages, box_bytes, stage_bytes, umma_k_bytes, kmma, upper_only;
+  unsigned sbo, layout_type;
+  unsigned idesc;
+  short dy[AST_MAX_TAPS];
+  short dx[AST_MAX_TAPS];
+};
+
+// MN-major, 128B-swizzled operand: 64-element (128 B) column blocks LBO apart, 8-row K groups SBO (=1024 B) apart
+// 16-bit types: SWIZZLE_128B (layout 2), swizzle atom = 8 K rows (SBO 1024 B).
+// 32-bit types (tf32): MN-major operands need the 32-byte-atom flavour, SWIZZLE_128B_BASE32B (layout 1), whose atom
+// is 4 K rows (SBO 512 B); the TMA map uses CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B to match.
+__device__ __forceinline__ unsigned long long make_mn_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes,
+                                                           unsigned layout_type) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
+  d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (unsigned long long)(sbo_bytes >> 4) << 32;
+  d |= (unsigned long long)1 << 46;
+  d |= (unsigned long long)layout_type << 61;
+  return d;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c, const CtParams p,
+                   float* __restrict__ out, const int* __restrict__ tap_off) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
+  __shared__ unsigned tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.y;
+  const int mb_idx = blockIdx.z / p.n_blocks, nb_idx = blockIdx.z % p.n_blocks;
+  if (p.upper_only && nb_idx * p.bn + p.bn <= mb_idx * 128) return;   // block strictly below the diagonal
+  int img_fixed = -1;
+  long long cbeg, cend;
+  if (p.per_img) {
+    img_fixed = blockIdx.x / p.ksplit;
+    const int kx = blockIdx.x % p.ksplit;
+    cbeg = (long long)kx * p.chunks_per_cta;
+  } else {
+    cbeg = (long long)blockIdx.x * p.chunks_per_cta;
+  }
+  cend = cbeg + p.chunks_per_cta;
+  if (cend > p.chunks_total) cend = p.chunks_total;
+  if (cbeg >= cend) return;                          // uniform across the CTA: nothing to do
+
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const unsigned tmem_cols = p.bn <= 32 ? 32 : p.bn <= 64 ? 64 : p.bn <= 128 ? 128 : 256;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_r) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+  const int m0 = mb_idx * 128, n0 = nb_idx * p.bn;
+  const int r_bytes = p.m_boxes * p.box_bytes;
+
+  if (warp == 0) {
+    int s = 0; unsigned ph = 0;
+    const int per_img_chunks = p.tiles_i * p.tiles_j;
+    for (long long c = cbeg; c < cend; ++c) {
+      int img, rem;
+      if (p.per_img) { img = img_fixed; rem = (int)c; }
+      else { img = (int)(c / per_img_chunks); rem = (int)(c % per_img_chunks); }
+      const int ti = rem / p.tiles_j, tj = rem % p.tiles_j;
+      const int i0 = ti * p.th, j0 = tj * p.tw;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (lane == 0) {
+        unsigned char* sr = smem + (size_t)s * p.stage_bytes;
+        mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
+        for (int b = 0; b < p.m_boxes; ++b)
+          tma_load_4d(sr + b * p.box_bytes, &tm_r, &full_bar[s], m0 + b * p.cb, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
+        for (int b = 0; b < p.n_boxes; ++b)
+          tma_load_4d(sr + r_bytes + b * p.box_bytes, &tm_c, &full_bar[s], n0 + b * p.cb, p.c_s * j0 + p.dx[t],
+                      p.c_s * i0 + p.dy[t], img);
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    int s = 0; unsigned ph = 0;
+    bool first = true;
+    for (long long c = cbeg; c < cend; ++c) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const unsigned b_addr = a_addr + r_bytes;
+        for (int k = 0; k < p.kmma; ++k) {
+          const unsigned long long ad = make_mn_desc(a_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
+          const unsigned long long bd = make_mn_desc(b_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
+          tc_mma<KIND>(tmem_base, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+        }
+        tc_commit(&empty_bar[s]);
+        if (c == cend - 1) tc_commit(&tfull_bar);
+      }
+      first = false;
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    float* o = out + (p.per_img ? (long long)img_fixed * p.out_img_stride : 0) + (tap_off ? tap_off[t] : 0);
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      float v[32];
+      tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+      if (m < p.m_valid) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = n0 + c0 + e;
+          if (n < p.n_valid && !(p.upper_only && n < m)) atomicAdd(o + (long long)m * p.s_m + (long long)n * p.s_n, v[e] * p.scale);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// fills the strict lower triangle of each C x C matrix from the upper one
+__global__ void mirror_upper_kernel(float* __restrict__ g, int c, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % c);
+    const int i = (int)((idx / c) % c);
+    if (j < i) g[idx] = g[idx - (long long)i * c - j + (long long)j * c + i];
+  }
+}
+
+static int encode_operand(EncodeTiledFn encode, CUtensorMap* tm, const ast_image* im, int cb, int tw, int th, int s) {
+  const int esz = im->dtype == AST_F32 ? 4 : 2;
+  const CUtensorMapDataType dt = im->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t dims[4] = {(cuuint64_t)im->c, (cuuint64_t)im->w, (cuuint64_t)im->h, (cuuint64_t)im->n};
+  cuuint64_t strides[3] = {(cuuint64_t)im->sw * esz, (cuuint64_t)im->sh * esz, (cuuint64_t)im->sn * esz};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(tw * s), (cuuint32_t)(th * s), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+  CUresult r = encode(tm, dt, 4, im->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      im->dtype == AST_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("contract_tc: cuTensorMapEncodeTiled failed: %d", (int)r); return (int)r; }
+  return 0;
+}
+
+static int check_operand(const char* who, const ast_image* im) {
+  const int esz = im->dtype == AST_F32 ? 4 : 2;
+  AST_CHECK_ARG(im->sc == 1, "%s: NHWC operand required", who);
+  AST_CHECK_ARG(((uintptr_t)im->ptr & 15) == 0 && (im->sw * esz) % 16 == 0 && (im->sh * esz) % 16 == 0 && (im->sn * esz) % 16 == 0,
+                "%s: pointer/strides must be 16-byte aligned (c=%d)", who, im->c);
+  return 0;
+}
+
+// rows = operand that provides the M (<=128 per block) dimension, cols = the N dimension.
+int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols, int c_s, const short* dy,
+                const short* dx, int ntaps, int mi, int mj, float* out, const int* tap_off, long long s_m,
+                long long s_n, long long out_img_stride, float scale, int upper_only, cudaStream_t stream) {
+  AST_CHECK_ARG(rows->dtype == cols->dtype, "contract_tc: operands must share a dtype");
+  AST_CHECK_ARG(rows->n == cols->n, "contract_tc: batch mismatch");
+  if (int e = check_operand("contract_tc(rows)", rows)) return e;
+  if (int e = check_operand("contract_tc(cols)", cols)) return e;
+  AST_CHECK_ARG(r_s >= 1 && r_s <= 2 && c_s >= 1 && c_s <= 2, "contract_tc: coordinate multipliers must be 1 or 2");
+  if (rows->n == 0) return 0;
+  EncodeTiledFn encode = get_encode();
+  AST_CHECK_ARG(encode, "contract_tc: cuTensorMapEncodeTiled entry point not available");
+  const int esz = rows->dtype == AST_F32 ? 4 : 2;
+
+  CtParams p;
+  memset(&p, 0, sizeof(p));
+  p.mi = mi; p.mj = mj; p.n_img = rows->n; p.ntaps = ntaps;
+  p.r_s = r_s; p.r_oy = r_oy; p.r_ox = r_ox; p.c_s = c_s;
+  for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy ? dy[t] : 0; p.dx[t] = dx ? dx[t] : 0; }
+  p.cb = 128 / esz;
+  p.m_valid = rows->c; p.n_valid = cols->c;
+  p.m_boxes = 128 / p.cb;
+  const int n_pad = (cols->c + p.cb - 1) / p.cb * p.cb;
+  p.bn = n_pad <= 256 ? n_pad : (n_pad % 256 == 0 ? 256 : (n_pad % 128 == 0 ? 128 : p.cb));
+  p.n_boxes = p.bn / p.cb;
+  p.m_blocks = (rows->c + 127) / 128;
+  p.n_blocks = (n_pad + p.bn - 1) / p.bn;
+  p.kp = 64;
+  pick_tile(mi, mj, p.kp, &p.tw, &p.th);
+  p.tiles_i = (mi + p.th - 1) / p.th; p.tiles_j = (mj + p.tw - 1) / p.tw;
+  p.per_img = out_img_stride != 0;
+  p.chunks_total = (long long)p.tiles_i * p.tiles_j * (p.per_img ? 1 : p.n_img);
+  p.out_img_stride = out_img_stride; p.s_m = s_m; p.s_n = s_n; p.scale = scale; p.upper_only = upper_only;
+  p.box_bytes = p.kp * 128;
+  p.stage_bytes = (p.m_boxes + p.n_boxes) * p.box_bytes;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
+  AST_CHECK_ARG(p.stages >= 2, "contract_tc: tile does not fit shared memory");
+  p.umma_k_bytes = (32 / esz) * 128;                 // UMMA_K pixel rows (16 bf16 / 8 tf32) x 128 B
+  p.kmma = p.kp / (32 / esz);
+  p.layout_type = esz == 4 ? 1u : 2u;
+  p.sbo = esz == 4 ? 512u : 1024u;
+  const unsigned fmt = rows->dtype == AST_F32 ? 2u : 1u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+  const long long fixed = (long long)ntaps * p.m_blocks * p.n_blocks * (p.per_img ? p.n_img : 1);
+  long long ks = (2LL * num_sms() + fixed - 1) / fixed;
+  if (ks < 1) ks = 1;
+  if (ks > p.chunks_total) ks = p.chunks_total;
+  p.chunks_per_cta = (int)((p.chunks_total + ks - 1) / ks);
+  p.ksplit = (int)((p.chunks_total + p.chunks_per_cta - 1) / p.chunks_per_cta);
+
+  alignas(64) CUtensorMap tm_r, tm_c;
+  if (int e = encode_operand(encode, &tm_r, rows, p.cb, p.tw, p.th, r_s)) return e;
+  if (int e = encode_operand(encode, &tm_c, cols, p.cb, p.tw, p.th, c_s)) return e;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  dim3 grid((unsigned)(p.ksplit * (p.per_img ? p.n_img : 1)), ntaps, p.m_blocks * p.n_blocks);
+  cudaError_t e;
+  if (rows->dtype == AST_BF16) {
+    e = cudaFuncSetAttribute(contract_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) contract_tc_kernel<0><<<grid, CT_THREADS, smem, stream>>>(tm_r, tm_c, p, out, tap_off);
+  } else {
+    e = cudaFuncSetAttribute(contract_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) contract_tc_kernel<1><<<grid, CT_THREADS, smem, stream>>>(tm_r, tm_c, p, out, tap_off);
+  }
+  if (e != cudaSuccess) { set_error("contract_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+int gram_tc(const ast_image* x, float* g, float scale, cudaStream_t s) {
+  cudaMemsetAsync(g, 0, sizeof(float) * (size_t)x->n * x->c * x->c, s);
+  int rc = contract_tc(x, 1, 0, 0, x, 1, nullptr, nullptr, 1, x->h, x->w, g, nullptr, x->c, 1, (long long)x->c * x->c,
+                       scale, 1, s);
+  if (rc) return rc;
+  const long long total = (long long)x->n * x->c * x->c;
+  long long blocks = (total + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  mirror_upper_kernel<<<(int)blocks, 256, 0, s>>>(g, x->c, total);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ast

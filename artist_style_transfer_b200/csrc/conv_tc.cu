@@ -10,9 +10,7 @@
 //   warps 2-5   epilogue: tcgen05.ld 32x32b -> bias / tap-gradient add / ReLU / ReLU-mask / tf32 rounding ->
 //               16-byte vector stores straight to the NHWC output (double-buffered accumulator in TMEM)
 // Replaces cuDNN/oneDNN convolution forward / backward-data at the call sites listed in include/ast.h.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ast {
 
@@ -31,94 +29,6 @@ struct TcParams {
   short dy[AST_MAX_TAPS];
   short dx[AST_MAX_TAPS];
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = smem_u32(bar);
-  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
-    unsigned ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
-                                       unsigned idesc, unsigned accumulate) {
-  if (KIND == 0)
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  else
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(unsigned taddr, float* v) {
-  unsigned r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO | SBO | version=1 | swizzle
-__device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, unsigned sbo_bytes, unsigned layout_type) {
-  unsigned long long d = 0;
-  d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
-  d |= (unsigned long long)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-  d |= (unsigned long long)(sbo_bytes >> 4) << 32;        // stride byte offset: 8 rows of one swizzle atom
-  d |= (unsigned long long)1 << 46;                       // descriptor version 1 (Blackwell)
-  d |= (unsigned long long)layout_type << 61;
-  return d;
-}
-__device__ __forceinline__ float round_tf32(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // ------------------------------------------------------------------ kernel
 template <int KIND>
@@ -286,34 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-static bool pick_tile(int mi, int mj, int* tw, int* th) {
-  double best = -1;
-  for (int w = 128; w >= 8; w >>= 1) {
-    const int h = 128 / w;
-    const double cover = (double)((mi + h - 1) / h * h) * ((mj + w - 1) / w * w);
-    const double eff = (double)mi * mj / cover;
-    if (eff > best + 1e-9) { best = eff; *tw = w; *th = h; }
-  }
-  return best > 0;
-}
-
-int tc_capabilities() { return 1; }
+int tc_capabilities() { return 3; }   // 1 = conv_tc.cu, 2 = contract_tc.cu (both are always built together)
 
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
                    const ast_image* add, const ast_image* mask, const ast_image* out, const ast_gather_geom* g,
@@ -341,7 +224,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   p.mi = g->mi; p.mj = g->mj; p.si = g->si; p.so = g->so; p.oy0 = g->oy0; p.ox0 = g->ox0;
   p.ntaps = g->ntaps; p.flags = g->flags; p.cout = out->c; p.n_img = in->n;
   for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = g->dy[t]; p.dx[t] = g->dx[t]; }
-  pick_tile(p.mi, p.mj, &p.tw, &p.th);
+  pick_tile(p.mi, p.mj, 128, &p.tw, &p.th);
   p.tiles_i = (p.mi + p.th - 1) / p.th;
   p.tiles_j = (p.mj + p.tw - 1) / p.tw;
   p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
@@ -403,11 +286,6 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
-}
-
-int gram_tc(const ast_image*, float*, float, cudaStream_t) {
-  set_error("tcgen05 gram kernel not built into this library");
-  return -2;
 }
 
 }  // namespace ast

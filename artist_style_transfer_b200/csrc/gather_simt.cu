@@ -288,6 +288,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
                    const ast_image* add, const ast_image* mask, const ast_image* out,
                    const ast_gather_geom* geom, cudaStream_t stream);  // conv_tc.cu
+int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols, int c_s, const short* dy,
+                const short* dx, int ntaps, int mi, int mj, float* out, const int* tap_off, long long s_m,
+                long long s_n, long long out_img_stride, float scale, int upper_only, cudaStream_t stream);  // contract_tc.cu
 
 }  // namespace ast
 
@@ -355,6 +358,9 @@ extern "C" int ast_wgrad_gather(const ast_image* x, const ast_image* gout, float
   AST_CHECK_ARG(geom->ntaps >= 1 && geom->ntaps <= AST_MAX_TAPS, "ast_wgrad_gather: ntaps %d out of range", geom->ntaps);
   AST_CHECK_ARG(x->n == gout->n, "ast_wgrad_gather: batch mismatch");
   if (x->n == 0) return 0;
+  if (geom->flags & AST_CONV_TENSOR)
+    return contract_tc(gout, geom->so, geom->oy0, geom->ox0, x, geom->si, geom->dy, geom->dx, geom->ntaps, geom->mi,
+                       geom->mj, dw, tap_off, s_co, s_ci, 0, 1.f, 0, (cudaStream_t)stream);
   return launch_wgrad_simt(x, gout, dw, tap_off, s_co, s_ci, geom, 0, 1.f, (cudaStream_t)stream);
 }
 

@@ -110,10 +110,18 @@ def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=N
     return out
 
 
-def _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False):
+def tc_contract_eligible(a, b):
+    """Operands the tcgen05 contraction kernel accepts (contract_tc.cu): NHWC, same dtype, 16-byte pixel stride."""
+    ok = _lib.has_tc_gram() and a.dtype == b.dtype
+    for t in (a, b):
+        ok = ok and t.stride(3) == 1 and all((s * t.element_size()) % 16 == 0 for s in t.stride()[:3])
+    return ok
+
+
+def _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False, tensor=False):
     """dw (fp32, pre-zeroed) += filter gradient for every launch of the op."""
     lib = _lib.load()
-    flags = CONV_REFLECT if reflect else 0
+    flags = (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
     xi, gi = image(x), image(gout)
     for l in launches:
         offs = tap_offsets(l.wtaps, s_u, s_v, dw.device)
@@ -229,9 +237,9 @@ def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, m
                                  reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32)
 
 
-def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False):
-    with _timed("wgrad_gather"):
-        return _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=reflect)
+def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False, tensor=False):
+    with _timed("wgrad_tc" if tensor else "wgrad_simt"):
+        return _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=reflect, tensor=tensor)
 
 
 def instnorm_stats(x, eps=1e-5):

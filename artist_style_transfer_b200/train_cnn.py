@@ -222,7 +222,8 @@ class _GramFunction(torch.autograd.Function):
             fv = fv.float()
         ctx.save_for_backward(fv)
         ctx.fast = fast
-        return ops.gram(fv.permute(0, 2, 3, 1), 1.0 / (c * h * w), tensor=fast and _lib.has_tc_gram())
+        xv = fv.permute(0, 2, 3, 1)
+        return ops.gram(xv, 1.0 / (c * h * w), tensor=fast and b > 0 and ops.tc_contract_eligible(xv, xv))
 
     @staticmethod
     def backward(ctx, dg):

@@ -132,3 +132,59 @@ def test_conv_tc_rejects_unsupported(env):
     y = torch.empty((1, 8, 8, 64), device="cuda")
     with pytest.raises(RuntimeError, match="conv_tc"):
         ops.conv_gather(x, wp, cg.conv_fwd(3, 1, 1, 8, 8), y, tensor=True)
+
+
+WG_CASES = [
+    # dtype, cin, cout, k, stride, n, h, w  (input is the physically padded buffer, like the transform net)
+    (torch.bfloat16, 128, 128, 3, 1, 2, 18, 18),
+    (torch.bfloat16, 64, 128, 3, 2, 2, 18, 18),
+    (torch.bfloat16, 32, 64, 3, 2, 1, 34, 34),
+    (torch.bfloat16, 128, 128, 1, 1, 2, 16, 16),
+    (torch.bfloat16, 128, 128, 3, 1, 1, 13, 11),
+]
+
+
+@pytest.mark.parametrize("dtype,cin,cout,k,s,n,h,w", WG_CASES)
+def test_wgrad_tc(env, dtype, cin, cout, k, s, n, h, w):
+    cg, ops = env
+    torch.manual_seed(cin + cout + k + s + h)
+    x = torch.randn(n, h, w, cin, device="cuda").to(dtype)
+    launches = cg.conv_fwd(k, s, 0, h, w)
+    ho, wo = launches[0].mi, launches[0].mj
+    gy = torch.randn(n, ho, wo, cout, device="cuda").to(dtype)
+    dw_tc = torch.zeros(cout, cin, k, k, device="cuda")
+    dw_simt = torch.zeros_like(dw_tc)
+    ops.wgrad_gather(x, gy, launches, dw_tc, cin * k * k, k * k, k, 1, tensor=True)
+    ops.wgrad_gather(x, gy, launches, dw_simt, cin * k * k, k * k, k, 1)
+    xr = x.double().cpu().permute(0, 3, 1, 2).requires_grad_(False)
+    wr = torch.zeros(cout, cin, k, k, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xr, wr, stride=s).backward(gy.double().cpu().permute(0, 3, 1, 2))
+    assert rel(dw_simt, wr.grad) < 1e-5
+    assert rel(dw_tc, wr.grad) < 1e-5, rel(dw_tc, wr.grad)
+
+
+def test_wgrad_tc_convT_phases(env):
+    cg, ops = env
+    torch.manual_seed(9)
+    n, h, w, cin, cout = 2, 8, 8, 128, 64
+    x = torch.randn(n, h, w, cin, device="cuda").bfloat16()
+    launches = cg.convT_fwd(3, 2, 1, 1, h, w)
+    gy = torch.randn(n, 16, 16, cout, device="cuda").bfloat16()
+    dw_tc = torch.zeros(cin, cout, 3, 3, device="cuda")
+    ops.wgrad_gather(x, gy, launches, dw_tc, 9, cout * 9, 3, 1, tensor=True)
+    wr = torch.zeros(cin, cout, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv_transpose2d(x.double().cpu().permute(0, 3, 1, 2), wr, stride=2, padding=1, output_padding=1).backward(
+        gy.double().cpu().permute(0, 3, 1, 2))
+    assert rel(dw_tc, wr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("c,h,w,n", [(64, 32, 32, 2), (128, 16, 16, 3), (256, 8, 8, 2), (512, 4, 4, 2), (64, 13, 9, 1)])
+def test_gram_tc(env, c, h, w, n):
+    cg, ops = env
+    from oracle import port
+    torch.manual_seed(c + h)
+    f = tf32_round(torch.randn(n, h, w, c, device="cuda") * 3)
+    g_tc = ops.gram(f, 1.0 / (c * h * w), tensor=True)
+    ref = port.gram(f.double().cpu().permute(0, 3, 1, 2))
+    assert rel(g_tc, ref) < 1e-5, rel(g_tc, ref)
+    assert float((g_tc - g_tc.transpose(1, 2)).abs().max()) == 0.0
