@@ -40,6 +40,10 @@ _SIGNATURES = {
     "ast_wgrad_gather": [_P(Image), _P(Image), _vp, _vp, ctypes.c_int64, ctypes.c_int64, _P(GatherGeom), _vp],
     "ast_pack_weights": [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
                          _vp, ctypes.c_int32, _vp],
+    "ast_pack_weights_ex": [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                            ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int32, _vp],
+    "ast_row_im2col": [_P(Image), _P(Image), _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                       ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_stats": [_P(Image), _vp, _vp, ctypes.c_float, _vp, _vp],
     "ast_instnorm_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_bwd_stats": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
@@ -112,11 +116,12 @@ def ref(img):
 
 
 def has_tc_conv():
-    return bool(load().ast_capabilities() & 1)
+    """tcgen05 conv kernel built in (AST_DISABLE_TC=1 is a debugging knob that routes fast mode to the SIMT kernels)."""
+    return bool(load().ast_capabilities() & 1) and os.environ.get("AST_DISABLE_TC") != "1"
 
 
 def has_tc_gram():
-    return bool(load().ast_capabilities() & 2)
+    return bool(load().ast_capabilities() & 2) and os.environ.get("AST_DISABLE_TC") != "1"
 
 
 def launch_count():

@@ -35,6 +35,11 @@ def get_default_precision():
     return _default_mode
 
 
+def _grad_fp32():
+    import os
+    return os.environ.get("AST_GRAD_FP32", "0") == "1"
+
+
 class _ConvParams(nn.Module):
     """Parameter holder laid out like nn.Conv2d / nn.ConvTranspose2d (weight, bias) with PyTorch's default init."""
 
@@ -96,6 +101,44 @@ def _pack_dgrad(st, w, launches, dtype):
     return ops.pack_weights(w, launches, st.cin, st.cout, st.cout * k2, k2, st.k, 1, dtype)
 
 
+# ---- 3-channel ends on the tensor cores (fast mode): the kw horizontal taps of the 9x9 filters are folded into
+# channels by ops.row_im2col so that TMA/tcgen05 see 32-channel NHWC tensors (csrc/im2col.cu explains the layouts).
+def _thin_in(st):
+    return st.kind == "conv" and st.stride == 1 and st.k > 1 and st.cin * st.k <= 32 and st.cout % 32 == 0 and st.norm
+
+
+def _thin_out(st):
+    return st.kind == "conv" and st.stride == 1 and st.k > 1 and st.cout * st.k <= 32 and st.cin % 32 == 0 and not st.norm
+
+
+def _vtaps(k, sign=1):
+    taps = [(sign * dy, 0) for dy in range(k)]
+    return taps, [(dy, 0) for dy in range(k)]
+
+
+def _thin_in_launch(st, h, w):
+    taps, wt = _vtaps(st.k)
+    return [cg.Launch(h, w, 1, 1, 0, 0, taps, wt, 0)]
+
+
+def _thin_in_pack(st, w, dtype):        # [dy][co][dx*cin + c] = W[co][c][dy][dx]
+    k, k2 = st.k, st.k * st.k
+    return ops.pack_weights_ex(w, [dy * k for dy in range(k)], st.cout, st.cout, 32, k * st.cin, st.cin,
+                               st.cin * k2, 1, k2, dtype)
+
+
+def _thin_out_pack_fwd(st, w, launches, dtype):   # [t][co (3 of 32)][c] = W[co][c][u][v]
+    k2 = st.k * st.k
+    offs = [u * st.k + v for u, v in cg.all_wtaps(launches)]
+    return ops.pack_weights_ex(w, offs, 32, st.cout, st.cin, st.cin, 1, st.cin * k2, k2, 0, dtype)
+
+
+def _thin_out_pack_dgrad(st, w, dtype):   # [dy][c][dx*cout + co] = W[co][c][dy][dx]
+    k, k2 = st.k, st.k * st.k
+    return ops.pack_weights_ex(w, [dy * k for dy in range(k)], st.cin, st.cin, 32, k * st.cout, st.cout,
+                               k2, 1, st.cin * k2, dtype)
+
+
 class _StageFunction(torch.autograd.Function):
     """Forward/backward of a list of stages as ONE autograd node (x: NCHW fp32 in, NCHW fp32 out)."""
 
@@ -114,20 +157,32 @@ class _StageFunction(torch.autograd.Function):
             cw, cb = next(pit), next(pit)
             P.append((cw, cb, next(pit), next(pit)) if st.norm else (cw, cb, None, None))
         p0 = stages[0].in_pad
-        node = torch.empty((n, h + 2 * p0, w + 2 * p0, stages[0].cin), dtype=adt, device=dev)
-        ops.copy_image(x.permute(0, 2, 3, 1), node, pad=p0)
+        thin_in = mode == "fast" and _thin_in(stages[0]) and ops.tc_eligible(torch.empty(0, 1, 1, 32, dtype=adt, device=dev), stages[0].cout)
+        if thin_in:     # row-im2col of the reflect-padded image: [N, H+2p, W, 32] (k*cin channels used)
+            node = torch.empty((n, h + 2 * p0, w, 32), dtype=adt, device=dev)
+            ops.row_im2col(x.permute(0, 2, 3, 1), node, stages[0].k, 1, p0, p0, True)
+        else:
+            node = torch.empty((n, h + 2 * p0, w + 2 * p0, stages[0].cin), dtype=adt, device=dev)
+            ops.copy_image(x.permute(0, 2, 3, 1), node, pad=p0)
         nodes, node_pad, saved = [node], [p0], []
         out = None
         for i, st in enumerate(stages):
             cw, cb, gam, bet = P[i]
             xin = nodes[-1]
-            launches, ho, wo = _fwd_geometry(st, xin.shape[1], xin.shape[2])
-            wp = _pack_fwd(st, cw.detach(), launches, adt)
             last = i == len(stages) - 1
+            thin_out = mode == "fast" and _thin_out(st) and ops.tc_eligible(xin, 32)
+            if i == 0 and thin_in:
+                launches, ho, wo = _thin_in_launch(st, h, w), h, w
+                wp = _thin_in_pack(st, cw.detach(), adt)
+            else:
+                launches, ho, wo = _fwd_geometry(st, xin.shape[1], xin.shape[2])
+                wp = (_thin_out_pack_fwd(st, cw.detach(), launches, adt) if thin_out
+                      else _pack_fwd(st, cw.detach(), launches, adt))
             if not st.norm:
                 assert last, "a stage without norm must be the last one"
                 out = torch.empty((n, st.cout, ho, wo), dtype=torch.float32, device=dev)
-                ops.conv_gather(xin, wp, launches, out.permute(0, 2, 3, 1), bias=cb.detach(), relu=st.relu)
+                ops.conv_gather(xin, wp, launches, out.permute(0, 2, 3, 1), bias=cb.detach(), relu=st.relu,
+                                tensor=thin_out)
                 saved.append((launches, None, None, None))
             else:
                 raw = torch.empty((n, ho, wo, st.cout), dtype=adt, device=dev)
@@ -149,7 +204,7 @@ class _StageFunction(torch.autograd.Function):
                     ops.copy_image(post, out.permute(0, 2, 3, 1))
         ctx.stages, ctx.mode, ctx.P = stages, mode, P
         ctx.nodes, ctx.node_pad, ctx.saved = nodes, node_pad, saved
-        ctx.x_needs_grad = x.requires_grad
+        ctx.thin_in = thin_in
         return out
 
     @staticmethod
@@ -159,6 +214,10 @@ class _StageFunction(torch.autograd.Function):
             raise NotImplementedError("gradient w.r.t. the input image is not part of the training path "
                                       "(train_cnn.py:298-299 feeds data that does not require grad)")
         adt = nodes[0].dtype
+        # dtype of the gradients entering an InstanceNorm backward (dgrad outputs, residual skip gradients).  The
+        # g - mean(g) - xhat*mean(g*xhat) cancellation amplifies their rounding error, so they can be kept in fp32
+        # (AST_GRAD_FP32=1) at the cost of 2x traffic on those tensors; see DESIGN.md "gradient noise".
+        gdt = torch.float32 if (adt == torch.float32 or _grad_fp32()) else adt
         gout = gout.to(torch.float32)
         L = len(stages)
         gpad = [None] * (L + 1)
@@ -169,10 +228,16 @@ class _StageFunction(torch.autograd.Function):
             cw, cb, gam, bet = P[i]
             launches, raw, mean, rstd = saved[i]
             xin = nodes[i]
+            thin_out = ctx.mode == "fast" and _thin_out(st) and ops.tc_eligible(xin, 32)
             if not st.norm:
                 d_raw = gout.permute(0, 2, 3, 1)
                 g_cb = gout.sum(dim=(0, 2, 3))
                 g_gam = g_bet = None
+                if thin_out:   # Dr[n,y,x',dx*cout+co] = dOut[n,y,x'-dx,co]: shared by the wgrad and the dgrad
+                    pk = st.k // 2
+                    nb, hb, wb = gout.shape[0], gout.shape[2], gout.shape[3]
+                    d_raw = torch.empty((nb, hb, wb + 2 * pk, 32), dtype=adt, device=gout.device)
+                    ops.row_im2col(gout.permute(0, 2, 3, 1), d_raw, st.k, -1, 0, 0, False)
             else:
                 j = i + 1
                 n, ho, wo, c = raw.shape
@@ -181,7 +246,7 @@ class _StageFunction(torch.autograd.Function):
                     ops.copy_image(gout.permute(0, 2, 3, 1), ge)
                     gextra[j] = ge
                 d_raw = torch.empty_like(raw)
-                gtotal = torch.empty_like(raw) if st.res_from is not None else None
+                gtotal = torch.empty(raw.shape, dtype=gdt, device=raw.device) if st.res_from is not None else None
                 s1, s2 = ops.instnorm_bwd(raw, mean, rstd, gam.detach(), bet.detach(), gpad[j], node_pad[j],
                                           gextra[j], st.relu, d_raw, gtotal)
                 g_bet = s1.view(n, c).sum(0)
@@ -192,19 +257,38 @@ class _StageFunction(torch.autograd.Function):
                     gextra[st.res_from + 1] = gtotal
                 gpad[j] = gextra[j] = None           # free
             k2 = st.k * st.k
-            g_cw = torch.zeros_like(cw, dtype=torch.float32)
             wtc = ctx.mode == "fast" and ops.tc_contract_eligible(xin, d_raw)
-            if st.kind == "conv":
-                ops.wgrad_gather(xin, d_raw, launches, g_cw, st.cin * k2, k2, st.k, 1, tensor=wtc)
+            if i == 0 and ctx.thin_in:
+                # tmp[dy][co][dx*cin+c] += sum_p dY[p][co] * Xr[p + dy rows][dx*cin+c]
+                tmp = torch.zeros((st.k, st.cout, 32), dtype=torch.float32, device=xin.device)
+                ops.wgrad_gather(xin, d_raw, launches, tmp, 32, 1, st.cout * 32, 0, tensor=wtc)
+                g_cw = tmp[:, :, :st.k * st.cin].reshape(st.k, st.cout, st.k, st.cin).permute(1, 3, 0, 2).contiguous()
+            elif not st.norm and thin_out:
+                # tmp[dy][dx*cout+co][c] += sum_{y,x'} Dr[y][x'][dx*cout+co] * xin[y+dy][x'][c]
+                taps, wt = _vtaps(st.k)
+                lw = [cg.Launch(d_raw.shape[1], d_raw.shape[2], 1, 1, 0, 0, taps, wt, 0)]
+                tmp = torch.zeros((st.k, 32, st.cin), dtype=torch.float32, device=xin.device)
+                ops.wgrad_gather(xin, d_raw, lw, tmp, st.cin, 1, 32 * st.cin, 0, tensor=True)
+                g_cw = tmp[:, :st.k * st.cout, :].reshape(st.k, st.k, st.cout, st.cin).permute(2, 3, 0, 1).contiguous()
             else:
-                ops.wgrad_gather(xin, d_raw, launches, g_cw, k2, st.cout * k2, st.k, 1, tensor=wtc)
-            if i > 0:
+                g_cw = torch.zeros_like(cw, dtype=torch.float32)
+                if st.kind == "conv":
+                    ops.wgrad_gather(xin, d_raw, launches, g_cw, st.cin * k2, k2, st.k, 1, tensor=wtc)
+                else:
+                    ops.wgrad_gather(xin, d_raw, launches, g_cw, k2, st.cout * k2, st.k, 1, tensor=wtc)
+            if i > 0 and not st.norm and thin_out:
+                taps, wt = _vtaps(st.k, -1)
+                dl = [cg.Launch(xin.shape[1], xin.shape[2], 1, 1, 0, 0, taps, wt, 0)]
+                g_in = torch.empty(xin.shape, dtype=gdt, device=xin.device)
+                ops.conv_gather(d_raw, _thin_out_pack_dgrad(st, cw.detach(), adt), dl, g_in, tensor=True)
+                gpad[i] = g_in
+            elif i > 0:
                 if st.kind == "conv":
                     dl = cg.conv_dgrad(st.k, st.stride, 0, xin.shape[1], xin.shape[2])
                 else:
                     dl = cg.convT_dgrad(st.k, st.stride, st.k // 2, d_raw.shape[1], d_raw.shape[2])
                 wpd = _pack_dgrad(st, cw.detach(), dl, adt)
-                g_in = torch.empty(xin.shape, dtype=adt, device=xin.device)
+                g_in = torch.empty(xin.shape, dtype=gdt, device=xin.device)
                 src = d_raw
                 if src.dtype != adt:               # fp32 NCHW grad of the last conv feeding a bf16 dgrad
                     src = torch.empty(d_raw.shape, dtype=adt, device=xin.device)

@@ -21,7 +21,7 @@ struct TcParams {
   int mi, mj, tw, th, tiles_i, tiles_j, n_img, n_tiles_n, bn;
   int ntaps, kchunks, kc;
   int si, so, oy0, ox0;
-  int cout, flags;
+  int cout, cout_valid, thin, flags;   // cout = weight rows per tap (multiple of 32); thin: cout_valid < cout or strided out
   int w_rows_per_img;
   int stages, a_bytes, stage_bytes, rowb;
   unsigned idesc, layout_type, sbo;
@@ -136,7 +136,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         float v[32];
         tc_ld32(taddr0 + c0, v);
         const int co = nt * p.bn + c0;
-        if (valid && co < p.cout) {
+        if (valid && p.thin) {
+          // thin / strided output (e.g. 3-channel NCHW image): scalar epilogue on the valid channels only
+          for (int e = 0; e < 32 && co + e < p.cout_valid; ++e) {
+            float x = v[e];
+            if (bias) x += __ldg(bias + co + e);
+            if (add.ptr) x += ld_elem(add, img_off(add, img, oy, ox, co + e));
+            if (p.flags & AST_CONV_RELU) x = fmaxf(x, 0.f);
+            if (mask.ptr) x = ld_elem(mask, img_off(mask, img, oy, ox, co + e)) > 0.f ? x : 0.f;
+            if (p.flags & AST_CONV_ROUND_TF32) x = round_tf32(x);
+            st_elem(out, img_off(out, img, oy, ox, co + e), x);
+          }
+        } else if (valid && co < p.cout) {
           if (bias) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] += __ldg(bias + co + e);
@@ -204,17 +215,18 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   const int esz = in->dtype == AST_F32 ? 4 : 2;
   AST_CHECK_ARG(!in_shift, "conv_tc: in_shift is only supported by the SIMT kernel");
   AST_CHECK_ARG(!(g->flags & AST_CONV_REFLECT), "conv_tc: reflect addressing needs a physically padded input");
-  AST_CHECK_ARG(in->sc == 1 && out->sc == 1, "conv_tc: NHWC tensors required");
+  const int cpad = (out->c + 31) / 32 * 32;        // weight rows per tap the caller packed (zero rows beyond out->c)
+  const bool thin = cpad != out->c || out->sc != 1;
+  AST_CHECK_ARG(in->sc == 1, "conv_tc: NHWC input required");
   AST_CHECK_ARG((in->c * esz) % 64 == 0, "conv_tc: cin*elemsize must be a multiple of 64 bytes (cin=%d)", in->c);
-  AST_CHECK_ARG(out->c % 32 == 0, "conv_tc: cout must be a multiple of 32 (cout=%d)", out->c);
   AST_CHECK_ARG(g->si >= 1 && g->si <= 2, "conv_tc: input stride must be 1 or 2");
-  AST_CHECK_ARG(((uintptr_t)in->ptr & 15) == 0 && ((uintptr_t)weights & 15) == 0 && ((uintptr_t)out->ptr & 15) == 0,
+  AST_CHECK_ARG(((uintptr_t)in->ptr & 15) == 0 && ((uintptr_t)weights & 15) == 0 && (thin || ((uintptr_t)out->ptr & 15) == 0),
                 "conv_tc: pointers must be 16-byte aligned");
   AST_CHECK_ARG((in->sw * esz) % 16 == 0 && (in->sh * esz) % 16 == 0 && (in->sn * esz) % 16 == 0,
                 "conv_tc: input strides must be multiples of 16 bytes");
-  AST_CHECK_ARG(out->sw % 4 == 0 && out->sh % 4 == 0 && out->sn % 4 == 0, "conv_tc: output strides must be multiples of 4 elements");
-  AST_CHECK_ARG(!add || (add->sc == 1 && add->sw % 4 == 0 && add->sh % 4 == 0 && add->sn % 4 == 0), "conv_tc: add layout");
-  AST_CHECK_ARG(!mask || (mask->sc == 1 && mask->sw % 4 == 0 && mask->sh % 4 == 0 && mask->sn % 4 == 0), "conv_tc: mask layout");
+  AST_CHECK_ARG(thin || (out->sw % 4 == 0 && out->sh % 4 == 0 && out->sn % 4 == 0), "conv_tc: output strides must be multiples of 4 elements");
+  AST_CHECK_ARG(thin || !add || (add->sc == 1 && add->sw % 4 == 0 && add->sh % 4 == 0 && add->sn % 4 == 0), "conv_tc: add layout");
+  AST_CHECK_ARG(thin || !mask || (mask->sc == 1 && mask->sw % 4 == 0 && mask->sh % 4 == 0 && mask->sn % 4 == 0), "conv_tc: mask layout");
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
@@ -222,7 +234,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.mi = g->mi; p.mj = g->mj; p.si = g->si; p.so = g->so; p.oy0 = g->oy0; p.ox0 = g->ox0;
-  p.ntaps = g->ntaps; p.flags = g->flags; p.cout = out->c; p.n_img = in->n;
+  p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.cout_valid = out->c; p.thin = thin; p.n_img = in->n;
   for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = g->dy[t]; p.dx[t] = g->dx[t]; }
   pick_tile(p.mi, p.mj, 128, &p.tw, &p.th);
   p.tiles_i = (p.mi + p.th - 1) / p.th;
@@ -230,13 +242,13 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
   p.kc = p.rowb / esz;
   p.kchunks = in->c / p.kc;
-  p.bn = out->c % 256 == 0 ? 256 : (out->c <= 256 ? out->c : (out->c % 128 == 0 ? 128 : (out->c % 64 == 0 ? 64 : 32)));
+  p.bn = cpad % 256 == 0 ? 256 : (cpad <= 256 ? cpad : (cpad % 128 == 0 ? 128 : (cpad % 64 == 0 ? 64 : 32)));
   AST_CHECK_ARG(p.bn == 32 || p.bn == 64 || p.bn == 128 || p.bn == 256, "conv_tc: unsupported cout %d", out->c);
-  p.n_tiles_n = out->c / p.bn;
+  p.n_tiles_n = cpad / p.bn;
   p.w_rows_per_img = 0;
   if (g->w_img_stride) {
-    AST_CHECK_ARG(g->w_img_stride == (int64_t)g->ntaps * out->c * in->c, "conv_tc: per-image weights must be densely packed");
-    p.w_rows_per_img = g->ntaps * out->c;
+    AST_CHECK_ARG(g->w_img_stride == (int64_t)g->ntaps * cpad * in->c, "conv_tc: per-image weights must be densely packed");
+    p.w_rows_per_img = g->ntaps * cpad;
   }
   p.a_bytes = 128 * p.rowb;
   p.stage_bytes = p.a_bytes + p.bn * p.rowb;
@@ -262,7 +274,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return (int)r; }
   }
   {
-    const long long rows = (long long)g->ntaps * out->c * (g->w_img_stride ? in->n : 1);
+    const long long rows = (long long)g->ntaps * cpad * (g->w_img_stride ? in->n : 1);
     cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
     cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.bn};

@@ -1,0 +1,99 @@
+// Helpers that let the 3-channel ends of both networks run on the tcgen05 kernels:
+//
+//  * ast_row_im2col: "row im2col" of a thin image.  out[n, y, x, d*C + c] = src[n, Y(y), X(x + sign*d - px), c]
+//    for d in [0, kw): the kw horizontal taps of a k x k filter become channels, so a 9x9 (or 3x3) convolution over
+//    a 3-channel image turns into a kw-tap (vertical only) convolution over a 32/16-channel NHWC tensor that
+//    conv_tc.cu / contract_tc.cu can consume with TMA (3 channels = 6/12 bytes per pixel cannot be a TMA row).
+//    Used for: StyleTransfer first conv 9x9 3->32 (cnn.py:16) fwd + wgrad, last conv 9x9 32->3 (cnn.py:39) dgrad +
+//    wgrad, VGG conv1_1 3->64 (train_cnn.py:54) fwd with the Caffe mean shift (train_cnn.py:300-301) fused in.
+//  * ast_pack_weights_ex: weight re-packing with a two-level inner index and zero padding, for those layouts.
+#include "common.cuh"
+
+namespace ast {
+
+__global__ void __launch_bounds__(256)
+row_im2col_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int sign, int px, int py, int reflect,
+                  int round_tf32) {
+  const int C = src.c;
+  const long long total = (long long)out.n * out.h * out.w * out.c;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int ch = (int)(idx % out.c);
+    long long r = idx / out.c;
+    const int x = (int)(r % out.w); r /= out.w;
+    const int y = (int)(r % out.h);
+    const int n = (int)(r / out.h);
+    float v = 0.f;
+    const int d = ch / C, c = ch - d * C;
+    if (d < kw) {
+      int sy = y - py, sx = x + sign * d - px;
+      bool ok = true;
+      if (reflect) { sy = reflect_idx(sy, src.h); sx = reflect_idx(sx, src.w); }
+      else ok = sy >= 0 && sy < src.h && sx >= 0 && sx < src.w;
+      if (ok) {
+        v = ld_elem(src, img_off(src, n, sy, sx, c));
+        if (shift) v += shift[c];
+      }
+    }
+    if (round_tf32) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); v = __uint_as_float(u); }
+    st_elem(out, img_off(out, n, y, x, ch), v);
+  }
+}
+
+template <typename TO, bool ROUND_TF32>
+__global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps, int a,
+                                       int a_valid, int b, int b_valid, int b0, long long s_a, long long s_b1,
+                                       long long s_b0, TO* __restrict__ dst) {
+  const long long total = (long long)ntaps * a * b;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ib = (int)(idx % b);
+    const int ia = (int)((idx / b) % a);
+    const int t = (int)(idx / ((long long)a * b));
+    float v = 0.f;
+    if (ia < a_valid && ib < b_valid) v = src[tap_off[t] + ia * s_a + (ib / b0) * s_b1 + (ib % b0) * s_b0];
+    if (ROUND_TF32) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); v = __uint_as_float(u); }
+    DT<TO>::st(dst + idx, v);
+  }
+}
+
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shift, int32_t kw, int32_t sign,
+                              int32_t px, int32_t py, int32_t reflect, int32_t round_tf32, void* stream) {
+  AST_CHECK_ARG(src && out, "ast_row_im2col: null argument");
+  AST_CHECK_ARG(out->n == src->n && kw >= 1 && out->c >= kw * src->c && (sign == 1 || sign == -1),
+                "ast_row_im2col: out.c (%d) must hold kw*C (%d) channels", out->c, kw * src->c);
+  AST_CHECK_ARG(!reflect || (src->h > 1 && src->w > 1), "ast_row_im2col: image too small to reflect");
+  const long long total = (long long)out->n * out->h * out->w * out->c;
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  row_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py,
+                                                                   reflect, round_tf32);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ast_pack_weights_ex(const float* src, const int32_t* tap_off, int32_t ntaps, int32_t a, int32_t a_valid,
+                                   int32_t b, int32_t b_valid, int32_t b0, int64_t s_a, int64_t s_b1, int64_t s_b0,
+                                   void* dst, int32_t dst_dtype, void* stream) {
+  AST_CHECK_ARG(src && tap_off && dst, "ast_pack_weights_ex: null argument");
+  AST_CHECK_ARG(ntaps >= 1 && ntaps <= AST_MAX_TAPS && a > 0 && b > 0 && b0 > 0 && a_valid <= a && b_valid <= b,
+                "ast_pack_weights_ex: bad sizes");
+  const long long total = (long long)ntaps * a * b;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  cudaStream_t s = (cudaStream_t)stream;
+#define PK(T, R) pack_weights_ex_kernel<T, R><<<(int)blocks, 256, 0, s>>>(src, tap_off, ntaps, a, a_valid, b, b_valid, b0, s_a, s_b1, s_b0, (T*)dst)
+  if (dst_dtype == AST_F32) PK(float, false);
+  else if (dst_dtype == AST_TF32) PK(float, true);
+  else if (dst_dtype == AST_BF16) PK(__nv_bfloat16, false);
+  else AST_CHECK_ARG(false, "ast_pack_weights_ex: bad dtype %d", dst_dtype);
+#undef PK
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}

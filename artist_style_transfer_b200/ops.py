@@ -18,6 +18,7 @@ _DT = {torch.float32: _lib.AST_F32, torch.bfloat16: _lib.AST_BF16}
 
 # ---- optional per-family CUDA-event timing (bench.py roofline leg); off by default, zero cost when off
 _prof = None
+PROFILE_DETAIL = False   # per-shape labels (scratch/layer_times.py)
 
 
 class _timed:
@@ -85,6 +86,26 @@ def _pack_weights_impl(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
     check(_lib.load().ast_pack_weights(ptr(w), ptr(offs), len(wt), a, b, s_a, s_b, ptr(out), code,
                                        stream_ptr()), "ast_pack_weights")
     return out
+
+
+def pack_weights_ex(w, tap_offs, a, a_valid, b, b_valid, b0, s_a, s_b1, s_b0, dtype):
+    """dst[t][ia][ib] = w.flat[tap_offs[t] + ia*s_a + (ib//b0)*s_b1 + (ib%b0)*s_b0], zero outside the valid box."""
+    with _timed("pack"):
+        offs = _tap_offsets_cached(tuple(tap_offs), w.device.index or 0)
+        out = torch.empty((len(tap_offs), a, b), dtype=torch.float32 if dtype == TF32 else dtype, device=w.device)
+        code = 2 if dtype == TF32 else _DT[dtype]
+        check(_lib.load().ast_pack_weights_ex(ptr(w), ptr(offs), len(tap_offs), a, a_valid, b, b_valid, b0, s_a, s_b1,
+                                              s_b0, ptr(out), code, stream_ptr()), "ast_pack_weights_ex")
+        return out
+
+
+def row_im2col(src, out, kw, sign, px, py, reflect, shift=None, round_tf32=False):
+    """out[n,y,x,d*C+c] = src[n, y-py, x+sign*d-px, c] (+shift); see include/ast.h ast_row_im2col."""
+    with _timed("pointwise"):
+        si, oi = image(src), image(out)
+        check(_lib.load().ast_row_im2col(ref(si), ref(oi), ptr(shift), kw, sign, px, py, int(reflect), int(round_tf32),
+                                         stream_ptr()), "ast_row_im2col")
+        return out
 
 
 def tc_eligible(x, cout):
@@ -232,28 +253,34 @@ def pack_weights(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
 
 def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False, reflect=False,
                 tensor=False, w_img_stride=0, round_tf32=False):
-    with _timed("conv_gather_tc" if tensor else "conv_gather_simt"):
+    label = "conv_gather_tc" if tensor else "conv_gather_simt"
+    if PROFILE_DETAIL and _prof is not None:
+        label += f"|{tuple(x.shape)}->{tuple(out.shape)} taps={sum(len(l.taps) for l in launches)} {str(x.dtype)[6:]}"
+    with _timed(label):
         return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu,
                                  reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32)
 
 
 def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False, tensor=False):
-    with _timed("wgrad_tc" if tensor else "wgrad_simt"):
+    label = "wgrad_tc" if tensor else "wgrad_simt"
+    if PROFILE_DETAIL and _prof is not None:
+        label += f"|x{tuple(x.shape)} g{tuple(gout.shape)} taps={sum(len(l.taps) for l in launches)}"
+    with _timed(label):
         return _wgrad_gather_impl(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=reflect, tensor=tensor)
 
 
 def instnorm_stats(x, eps=1e-5):
-    with _timed("instnorm"):
+    with _timed("instnorm" + (f"|stats{tuple(x.shape)}" if PROFILE_DETAIL and _prof is not None else "")):
         return _instnorm_stats_impl(x, eps=eps)
 
 
 def instnorm_apply(x, mean, rstd, gamma, beta, out, pad, relu, residual=None):
-    with _timed("instnorm"):
+    with _timed("instnorm" + (f"|apply{tuple(x.shape)}" if PROFILE_DETAIL and _prof is not None else "")):
         return _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=residual)
 
 
 def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None):
-    with _timed("instnorm"):
+    with _timed("instnorm" + (f"|bwd{tuple(x.shape)}" if PROFILE_DETAIL and _prof is not None else "")):
         return _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=gtotal)
 
 

@@ -60,7 +60,18 @@ class _VGGFunction(torch.autograd.Function):
         for idx, kind, cin, cout in module._layout:
             if idx > upto:
                 break
-            if kind == "conv":
+            if kind == "conv" and idx == 0 and tensor:
+                # conv1_1 on the tensor cores: fold the 3 horizontal taps (and the mean shift, applied before the
+                # zero padding like train_cnn.py:300-301) into a 16-channel TF32 tensor, then a 3-tap vertical conv
+                xr = torch.empty((n, h, w, 16), dtype=torch.float32, device=dev)
+                ops.row_im2col(cur, xr, 3, 1, 1, 0, False, shift=shift, round_tf32=True)
+                launches = [cg.Launch(h, w, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]
+                out = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev)
+                wp, bias = packed[idx]
+                ops.conv_gather(xr, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True)
+                plan.append((idx, "conv", cur, out))
+                cur = out
+            elif kind == "conv":
                 launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
                 out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
                 wp, bias = packed[idx]
@@ -115,7 +126,7 @@ class _VGGFunction(torch.autograd.Function):
             if idx == 0:
                 gx = torch.empty((out.shape[0], 3, out.shape[1], out.shape[2]), dtype=torch.float32, device=g.device)
                 launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
-                ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1))
+                ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1), tensor=tensor)
                 break
             launches = cg.conv_dgrad(3, 1, 1, xin.shape[1], xin.shape[2])
             gin = torch.empty(xin.shape, dtype=torch.float32, device=g.device)
@@ -179,6 +190,10 @@ class VGG16(nn.Module, _cnn._Precision):
                 if kind == "conv" and idx <= 21:
                     m = self.features[idx]
                     w = m.weight.detach().float()
+                    if idx == 0 and tensor:     # [dy][co][dx*3+c (9 of 16)] for the row-im2col'd conv1_1
+                        out[idx] = (ops.pack_weights_ex(w, [0, 3, 6], cout, cout, 16, 9, 3, 27, 1, 9, ops.TF32),
+                                    m.bias.detach().float())
+                        continue
                     out[idx] = (ops.pack_weights(w, launches, cout, cin, cin * 9, 9, 3, 1,
                                                  ops.TF32 if tensor else torch.float32), m.bias.detach().float())
             self._pack_cache["fwd_key"], self._pack_cache["fwd"] = key, out
@@ -192,6 +207,10 @@ class VGG16(nn.Module, _cnn._Precision):
             for idx, kind, cin, cout in self._layout:
                 if kind == "conv" and idx <= 21:
                     w = self.features[idx].weight.detach().float()
+                    if idx == 0 and tensor:     # [t][ci (3 of 32)][co]: thin-output dgrad on the tensor cores
+                        offs = [u * 3 + v for u, v in cg.all_wtaps(launches)]
+                        out[idx] = ops.pack_weights_ex(w, offs, 32, cin, cout, cout, 1, 9, 27, 0, ops.TF32)
+                        continue
                     out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1,
                                                 ops.TF32 if tensor else torch.float32)
             self._pack_cache["dgrad_key"], self._pack_cache["dgrad"] = key, out

@@ -84,6 +84,20 @@ int ast_wgrad_gather(const ast_image* x, const ast_image* gout, float* dw, const
 int ast_pack_weights(const float* src, const int32_t* tap_off, int32_t ntaps, int32_t a, int32_t b,
                      int64_t s_a, int64_t s_b, void* dst, int32_t dst_dtype, void* stream);
 
+/* Same with a two-level inner index and zero padding (layouts of the 3-channel layers, see ast_row_im2col):
+ *   dst[t][ia][ib] = (ia < a_valid && ib < b_valid) ? src[tap_off[t] + ia*s_a + (ib / b0)*s_b1 + (ib % b0)*s_b0] : 0 */
+int ast_pack_weights_ex(const float* src, const int32_t* tap_off, int32_t ntaps, int32_t a, int32_t a_valid,
+                        int32_t b, int32_t b_valid, int32_t b0, int64_t s_a, int64_t s_b1, int64_t s_b0,
+                        void* dst, int32_t dst_dtype, void* stream);
+
+/* "Row im2col" of a thin (3-channel) image so that its k x k convolution becomes a k-tap vertical convolution over
+ * kw*C (zero-padded to out.c) channels that TMA / tcgen05 can consume:
+ *   out[n, y, x, d*C + c] = src[n, Y(y - py), X(x + sign*d - px), c] (+ shift[c]),  d in [0, kw)
+ * Out-of-range source coordinates are mirrored (reflect != 0: nn.ReflectionPad2d, cnn.py:58) or read as 0 (zero padding
+ * of VGG conv1_1 applied AFTER the mean shift, train_cnn.py:300-301).  round_tf32 rounds fp32 outputs to TF32. */
+int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shift, int32_t kw, int32_t sign,
+                   int32_t px, int32_t py, int32_t reflect, int32_t round_tf32, void* stream);
+
 /* nn.InstanceNorm2d(affine=True), eps 1e-5, biased variance (cnn.py:68,114).
  * stats: mean[n*c], rstd[n*c] (fp32).  workspace: ast_instnorm_workspace_bytes(). */
 int64_t ast_instnorm_workspace_bytes(int32_t n, int32_t c);

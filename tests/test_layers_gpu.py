@@ -146,3 +146,23 @@ def test_gram_edge_shapes(ast, shape):
     assert g.shape == (shape[0], shape[1], shape[1])
     if shape[0]:
         assert rel(g, port.gram(f.double().cpu())) < 1e-6
+
+
+@pytest.mark.parametrize("cin,cout,k,norm,h,w", [(3, 32, 9, "instance", 24, 28), (32, 3, 9, "None", 20, 24)])
+def test_thin_layers_fast_mode(ast, cin, cout, k, norm, h, w):
+    """The 3-channel 9x9 ends in bf16 on the tcgen05 kernels (row-im2col path) against torch fp64."""
+    torch.manual_seed(21)
+    layer = ast.ConvLayer(cin, cout, k, 1, norm=norm).cuda()
+    layer.precision = "fast"
+    x = torch.randint(0, 256, (2, cin, h, w)).float().cuda() if cin == 3 else torch.randn(2, cin, h, w).cuda()
+    y = layer(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    P = {n: p.detach().double().cpu().requires_grad_(True) for n, p in layer.named_parameters()}
+    yr = _ref_conv_layer(x.double().cpu(), P["conv_layer.weight"], P["conv_layer.bias"],
+                         P.get("norm_layer.weight"), P.get("norm_layer.bias"), k, 1, norm == "instance")
+    yr.backward(gy.double().cpu())
+    assert rel(y, yr) < 1e-2
+    assert rel(layer.conv_layer.weight.grad, P["conv_layer.weight"].grad) < 2e-2
+    if norm == "None":
+        assert rel(layer.conv_layer.bias.grad, P["conv_layer.bias"].grad) < 1e-4

@@ -192,3 +192,40 @@ def test_launch_counter(ast):
     before = _lib.launch_count()
     ast.gram(torch.randn(1, 64, 8, 8, device="cuda"))
     assert _lib.launch_count() > before
+
+
+def test_fast_mode_runs_on_tensor_kernels_only(ast):
+    """In fast mode every conv / wgrad / Gram launch of a step is a tcgen05 kernel (no SIMT conv left)."""
+    from artist_style_transfer_b200 import ops
+    net, vgg = build(ast, "fast")
+    content = weights.content_batch(2, 64, 2).cuda()
+    style = ast.style_grams_single(vgg, weights.style_image(64, 2).cuda(), 2)
+    ast.perceptual_step(net, vgg, content, style)
+    net.zero_grad()
+    ops.profile_begin()
+    ast.perceptual_step(net, vgg, content, style)
+    fam = ops.profile_end()
+    assert "conv_gather_tc" in fam and "wgrad_tc" in fam
+    assert "conv_gather_simt" not in fam and "wgrad_simt" not in fam, fam
+
+
+def test_fast_vs_strict_gradients(ast):
+    """bf16/TF32 tensor-core step against the strict fp32 step on identical inputs: losses 1e-2, gradient direction."""
+    content = weights.content_batch(2, 64, 2).cuda()
+    out = {}
+    for mode in ("fp32", "fast"):
+        net, vgg = build(ast, mode)
+        style = ast.style_grams_single(vgg, weights.style_image(64, 2).cuda(), 2)
+        net.zero_grad()
+        c, s, t = ast.perceptual_step(net, vgg, content, style)
+        out[mode] = (float(t), {n: p.grad.clone() for n, p in net.named_parameters()})
+    assert abs(out["fast"][0] - out["fp32"][0]) < 1e-2 * abs(out["fp32"][0])
+    for name, g in out["fp32"][1].items():
+        if float(g.norm()) < 1e-9 or name.endswith("conv2.norm_layer.bias"):   # loss-invariant parameters: |g| ~ 0
+            continue
+        gf = out["fast"][1][name]
+        cos = float((g * gf).sum() / (g.norm() * gf.norm() + 1e-30))
+        # bf16 activations perturb the forward point; the deviation accumulates towards the input side (measured
+        # 0.945..1.0, and 0.97 between two bf16 runs that differ only in summation order): see DESIGN.md
+        assert cos > 0.9, (name, cos)
+        assert abs(float(gf.norm()) / float(g.norm()) - 1) < 0.15, name
