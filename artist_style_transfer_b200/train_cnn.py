@@ -19,6 +19,7 @@ import torch.nn as nn
 from . import _lib
 from . import cnn as _cnn
 from . import conv_geometry as cg
+from . import dp
 from . import ops
 from .cnn import _ConvParams
 
@@ -291,7 +292,6 @@ def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group
     wording).  With `group` (torch.distributed), each rank passes ITS shard of the paintings and the sums are
     all-reduced (NCCL) before the division; `paintings` is a list of (3,H,W) tensors or a [P,3,H,W] tensor.
     """
-    import torch.distributed as dist
     acc, count = None, 0
     shift = None
     with torch.no_grad():
@@ -310,10 +310,7 @@ def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group
                     ops.accumulate(v.unsqueeze(0), acc[k].unsqueeze(0))
             count += 1
         total = torch.tensor([float(count)], device=next(iter(acc.values())).device)
-        if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            for k in acc:
-                dist.all_reduce(acc[k], op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        dp.allreduce_sums(list(acc.values()) + [total], group)      # C2: one exchange per artist
         length = float(total.item())
         out = {}
         for k, v in acc.items():
@@ -395,17 +392,9 @@ class PerceptualTrainer:
         self._flat = None
 
     def _allreduce_grads(self):
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
-            return
-        grads = [p.grad for p in self.params]
         if self._flat is None:
-            self._flat = torch.empty(sum(g.numel() for g in grads), dtype=torch.float32, device=grads[0].device)
-        torch._foreach_copy_(list(self._flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
-        dist.all_reduce(self._flat, op=dist.ReduceOp.AVG if grads[0].is_cuda else dist.ReduceOp.SUM, group=self.group)
-        if not grads[0].is_cuda:
-            self._flat /= dist.get_world_size(self.group)
-        torch._foreach_copy_([g.reshape(-1) for g in grads], list(self._flat.split([g.numel() for g in grads])))
+            self._flat = dp.GradBucket()
+        self._flat.allreduce_mean(self.params, self.group)
 
     def step(self, content_batch):
         self.optimizer.zero_grad(set_to_none=True)                                                 # :295
