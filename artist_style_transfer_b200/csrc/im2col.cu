@@ -39,6 +39,53 @@ row_im2col_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int
   }
 }
 
+// One thread per output pixel: gathers the kw*C source values (coalesced along x: consecutive threads read
+// consecutive columns of each source plane) and writes the whole OUTC-channel row with 16-byte stores.
+template <int OUTC>
+__global__ void __launch_bounds__(256)
+row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int sign, int px, int py, int reflect,
+                      int round_tf32) {
+  const int C = src.c;
+  const long long total = (long long)out.n * out.h * out.w;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int x = (int)(idx % out.w);
+    long long r = idx / out.w;
+    const int y = (int)(r % out.h);
+    const int n = (int)(r / out.h);
+    float v[OUTC];
+#pragma unroll
+    for (int e = 0; e < OUTC; ++e) v[e] = 0.f;
+    int sy = y - py;
+    bool oky = true;
+    if (reflect) sy = reflect_idx(sy, src.h);
+    else oky = sy >= 0 && sy < src.h;
+    if (oky) {
+      int ch = 0;
+      for (int d = 0; d < kw; ++d) {
+        int sx = x + sign * d - px;
+        bool ok = true;
+        if (reflect) sx = reflect_idx(sx, src.w);
+        else ok = sx >= 0 && sx < src.w;
+        for (int c = 0; c < C; ++c, ++ch) {
+          float t = 0.f;
+          if (ok) { t = ld_elem(src, img_off(src, n, sy, sx, c)); if (shift) t += shift[c]; }
+          if (round_tf32) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t)); t = __uint_as_float(u); }
+#pragma unroll
+          for (int e = 0; e < OUTC; ++e) if (e == ch) v[e] = t;   // keeps v[] in registers
+        }
+      }
+    }
+    const long long oo = img_off(out, n, y, x, 0);
+    if (out.dtype == AST_F32) {
+#pragma unroll
+      for (int e = 0; e < OUTC; e += 4) st4((float*)out.ptr + oo + e, v + e);
+    } else {
+#pragma unroll
+      for (int e = 0; e < OUTC; e += 8) Vec16<__nv_bfloat16>::store((__nv_bfloat16*)out.ptr + oo + e, v + e);
+    }
+  }
+}
+
 template <typename TO, bool ROUND_TF32>
 __global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps, int a,
                                        int a_valid, int b, int b_valid, int b0, long long s_a, long long s_b1,
@@ -68,6 +115,21 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
   AST_CHECK_ARG(!reflect || (src->h > 1 && src->w > 1), "ast_row_im2col: image too small to reflect");
   const long long total = (long long)out->n * out->h * out->w * out->c;
   if (total == 0) return 0;
+  const int ev = out->dtype == AST_F32 ? 4 : 8;
+  const bool vec_ok = out->sc == 1 && out->sw % ev == 0 && out->sh % ev == 0 && out->sn % ev == 0 &&
+                      ((uintptr_t)out->ptr & 15) == 0 && (out->c == 16 || out->c == 32);
+  if (vec_ok) {
+    const long long pixels = total / out->c;
+    long long pb = (pixels + 255) / 256;
+    if (pb > (long long)num_sms() * 32) pb = (long long)num_sms() * 32;
+    if (out->c == 32)
+      row_im2col_pix_kernel<32><<<(int)pb, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32);
+    else
+      row_im2col_pix_kernel<16><<<(int)pb, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32);
+    count_launch();
+    AST_CUDA_LAUNCH_CHECK();
+    return 0;
+  }
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
   row_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py,

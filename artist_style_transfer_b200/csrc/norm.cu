@@ -267,6 +267,18 @@ static bool nhwc_ok(const ast_image* x, int vec) {
 
 }  // namespace ast
 
+namespace ast {   // norm_fast.cu: return 1 = launched, 0 = not applicable (use the generic kernel), other = error
+int instnorm_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                        const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s);
+int instnorm_bwd_stats_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                            float* s1, float* s2, cudaStream_t s);
+int instnorm_bwd_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                            const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
+                            cudaStream_t s);
+}  // namespace ast
+
 using namespace ast;
 
 extern "C" int64_t ast_instnorm_workspace_bytes(int32_t n, int32_t c) {
@@ -304,6 +316,8 @@ extern "C" int ast_instnorm_apply(const ast_image* x, const float* mean, const f
   AST_CHECK_ARG(pad < x->h && pad < x->w, "ast_instnorm_apply: pad too large for reflection");
   AST_CHECK_ARG(!residual || (same_shape(residual, x) && residual->sc == 1), "ast_instnorm_apply: residual shape");
   if (x->n == 0) return 0;
+  if (int fr = instnorm_apply_fast(x, mean, rstd, gamma, beta, residual, out, pad, relu, (cudaStream_t)stream))
+    return fr == 1 ? 0 : fr;
   const long long total = (long long)out->n * out->h * out->w * (x->c / 4);
   const int blocks = (int)min((total + NT - 1) / NT, (long long)num_sms() * 16);
   Img r = residual ? to_img(residual) : null_img();
@@ -338,6 +352,8 @@ extern "C" int ast_instnorm_bwd_stats(const ast_image* x, const float* mean, con
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(s1, 0, sizeof(float) * x->n * x->c, s);
   cudaMemsetAsync(s2, 0, sizeof(float) * x->n * x->c, s);
+  if (int fr = instnorm_bwd_stats_fast(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, s))
+    return fr == 1 ? 0 : fr;
   const int lanes = x->c / 4, slots = NT / lanes, hw = x->h * x->w;
   const int nblk = stats_blocks(x->n, hw, slots);
   const int chunk = (hw + nblk - 1) / nblk;
@@ -362,6 +378,9 @@ extern "C" int ast_instnorm_bwd_apply(const ast_image* x, const float* mean, con
   AST_CHECK_ARG(same_shape(dx, x) && dx->sc == 1, "ast_instnorm_bwd_apply: dx shape");
   AST_CHECK_ARG(!gtotal || (same_shape(gtotal, x) && gtotal->sc == 1), "ast_instnorm_bwd_apply: gtotal shape");
   if (x->n == 0) return 0;
+  if (int fr = instnorm_bwd_apply_fast(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, dx, gtotal,
+                                       (cudaStream_t)stream))
+    return fr == 1 ? 0 : fr;
   const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
   const int blocks = (int)min((total + NT - 1) / NT, (long long)num_sms() * 16);
   Img gp = gpad ? to_img(gpad) : null_img(), ge = gextra ? to_img(gextra) : null_img();

@@ -1,0 +1,274 @@
+// Vectorised InstanceNorm apply / backward kernels (the HBM-roofline kernels of the path).
+//
+// Thread mapping: a thread owns ONE 16-byte channel group (8 bf16 / 4 fp32 channels) for the whole kernel, so the
+// per-(n,c) constants (gamma*rstd, mean, beta, s1/HW, s2/HW) live in registers; consecutive threads cover consecutive
+// channel groups of a pixel, then consecutive pixels -> every warp access is a run of full 128-byte lines.
+// One pixel costs one integer division (amortised over 8 channels); reflection folding is only evaluated on the
+// border ring.  These replace the generic kernels of norm.cu whenever x / out / dx share one dtype and the tensors
+// are NHWC with 16-byte-aligned pixel strides (always true inside the engine).
+#include "common.cuh"
+
+namespace ast {
+
+constexpr int NF_THREADS = 256;
+
+template <int VEC>
+__device__ __forceinline__ void ldv_img(const Img& im, long long off, float* v) {
+  if (im.dtype == AST_F32) {
+#pragma unroll
+    for (int e = 0; e < VEC; e += 4) ld4((const float*)im.ptr + off + e, v + e);
+  } else {
+    if (VEC == 8) Vec16<__nv_bfloat16>::load((const __nv_bfloat16*)im.ptr + off, v);
+    else ld4((const __nv_bfloat16*)im.ptr + off, v);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv_img(const Img& im, long long off, const float* v) {
+  if (im.dtype == AST_F32) {
+#pragma unroll
+    for (int e = 0; e < VEC; e += 4) st4((float*)im.ptr + off + e, v + e);
+  } else {
+    if (VEC == 8) Vec16<__nv_bfloat16>::store((__nv_bfloat16*)im.ptr + off, v);
+    else st4((__nv_bfloat16*)im.ptr + off, v);
+  }
+}
+
+// ---------------------------------------------------------------- forward apply
+template <typename T>
+__global__ void __launch_bounds__(NF_THREADS)
+in_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, Img res, Img out, int pad,
+                     int relu, int chunk) {
+  constexpr int VEC = Vec16<T>::N;
+  const int C = x.c, lanes = C / VEC, slots = NF_THREADS / lanes;
+  const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+  const int n = blockIdx.y, c = lane * VEC;
+  float a[VEC], mu[VEC], be[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    mu[e] = mean[n * C + c + e];
+    a[e] = gamma[c + e] * rstd[n * C + c + e];
+    be[e] = beta[c + e];
+  }
+  const int npix = out.h * out.w;
+  const int pbeg = blockIdx.x * chunk, pend = min(npix, pbeg + chunk);
+  const T* xb = (const T*)x.ptr + (long long)n * x.sn + c;
+  T* ob = (T*)out.ptr + (long long)n * out.sn + c;
+  for (int p = pbeg + slot; p < pend; p += slots) {
+    const int oy = p / out.w, ox = p - oy * out.w;
+    const int i = reflect_idx(oy - pad, x.h), j = reflect_idx(ox - pad, x.w);
+    float v[VEC];
+    Vec16<T>::load(xb + (long long)i * x.sh + (long long)j * x.sw, v);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = fmaf(a[e], v[e] - mu[e], be[e]);
+    if (res.ptr) {
+      float r[VEC];
+      ldv_img<VEC>(res, img_off(res, n, i, j, c), r);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] += r[e];
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    Vec16<T>::store(ob + (long long)oy * out.sh + (long long)ox * out.sw, v);
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// g' = (fold_reflect(gpad) + gextra) * relu_mask ; interior pixels need one gpad read, the border ring up to 9
+template <int VEC>
+__device__ __forceinline__ void gprime_fast(const Img& gpad, int pad, const Img& gextra, int H, int W, int n, int i,
+                                            int j, int c, float* g) {
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) g[e] = 0.f;
+  if (gpad.ptr) {
+    ldv_img<VEC>(gpad, img_off(gpad, n, i + pad, j + pad, c), g);
+    const bool by = pad > 0 && (i <= pad || i >= H - 1 - pad), bx = pad > 0 && (j <= pad || j >= W - 1 - pad);
+    if (by || bx) {
+      int rr[3], cc[3], nr = 1, nc = 1;
+      rr[0] = i + pad; cc[0] = j + pad;
+      if (i >= 1 && i <= pad) rr[nr++] = pad - i;
+      if (i <= H - 2 && i >= H - 1 - pad) rr[nr++] = pad + 2 * (H - 1) - i;
+      if (j >= 1 && j <= pad) cc[nc++] = pad - j;
+      if (j <= W - 2 && j >= W - 1 - pad) cc[nc++] = pad + 2 * (W - 1) - j;
+      for (int a_ = 0; a_ < nr; ++a_)
+        for (int b_ = 0; b_ < nc; ++b_) {
+          if (a_ == 0 && b_ == 0) continue;
+          float t[VEC];
+          ldv_img<VEC>(gpad, img_off(gpad, n, rr[a_], cc[b_], c), t);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) g[e] += t[e];
+        }
+    }
+  }
+  if (gextra.ptr) {
+    float t[VEC];
+    ldv_img<VEC>(gextra, img_off(gextra, n, i, j, c), t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) g[e] += t[e];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NF_THREADS)
+in_bwd_stats_fast_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
+                         int relu, float* __restrict__ s1o, float* __restrict__ s2o, int chunk) {
+  constexpr int VEC = Vec16<T>::N;
+  extern __shared__ float sm[];
+  const int C = x.c, lanes = C / VEC, slots = NF_THREADS / lanes;
+  const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+  const int n = blockIdx.y, c = lane * VEC;
+  float a[VEC], mu[VEC], rs[VEC], be[VEC], t1[VEC], t2[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    mu[e] = mean[n * C + c + e]; rs[e] = rstd[n * C + c + e];
+    a[e] = gamma[c + e] * rs[e]; be[e] = beta[c + e];
+    t1[e] = 0.f; t2[e] = 0.f;
+  }
+  const int npix = x.h * x.w;
+  const int pbeg = blockIdx.x * chunk, pend = min(npix, pbeg + chunk);
+  const T* xb = (const T*)x.ptr + (long long)n * x.sn + c;
+  for (int p = pbeg + slot; p < pend; p += slots) {
+    const int i = p / x.w, j = p - i * x.w;
+    float xv[VEC], g[VEC];
+    Vec16<T>::load(xb + (long long)i * x.sh + (long long)j * x.sw, xv);
+    gprime_fast<VEC>(gpad, pad, gextra, x.h, x.w, n, i, j, c, g);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float d = xv[e] - mu[e];
+      if (relu && !(fmaf(a[e], d, be[e]) > 0.f)) g[e] = 0.f;      // same expression as the forward apply
+      t1[e] += g[e];
+      t2[e] = fmaf(g[e], d * rs[e], t2[e]);
+    }
+  }
+  float* r1 = sm;
+  float* r2 = sm + slots * C;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { r1[slot * C + c + e] = t1[e]; r2[slot * C + c + e] = t2[e]; }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += NF_THREADS) {
+    float u1 = 0.f, u2 = 0.f;
+    for (int s = 0; s < slots; ++s) { u1 += r1[s * C + cc]; u2 += r2[s * C + cc]; }
+    atomicAdd(s1o + n * C + cc, u1);
+    atomicAdd(s2o + n * C + cc, u2);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NF_THREADS)
+in_bwd_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
+                         int relu, const float* __restrict__ s1, const float* __restrict__ s2, Img dx, Img gtotal,
+                         int chunk) {
+  constexpr int VEC = Vec16<T>::N;
+  const int C = x.c, lanes = C / VEC, slots = NF_THREADS / lanes;
+  const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+  const int n = blockIdx.y, c = lane * VEC;
+  const float inv_hw = 1.f / (float)(x.h * x.w);
+  float a[VEC], mu[VEC], rs[VEC], be[VEC], m1[VEC], m2[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    mu[e] = mean[n * C + c + e]; rs[e] = rstd[n * C + c + e];
+    a[e] = gamma[c + e] * rs[e]; be[e] = beta[c + e];
+    m1[e] = s1[n * C + c + e] * inv_hw; m2[e] = s2[n * C + c + e] * inv_hw;
+  }
+  const int npix = x.h * x.w;
+  const int pbeg = blockIdx.x * chunk, pend = min(npix, pbeg + chunk);
+  const T* xb = (const T*)x.ptr + (long long)n * x.sn + c;
+  T* db = (T*)dx.ptr + (long long)n * dx.sn + c;
+  for (int p = pbeg + slot; p < pend; p += slots) {
+    const int i = p / x.w, j = p - i * x.w;
+    float xv[VEC], g[VEC], d[VEC];
+    Vec16<T>::load(xb + (long long)i * x.sh + (long long)j * x.sw, xv);
+    gprime_fast<VEC>(gpad, pad, gextra, x.h, x.w, n, i, j, c, g);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float dd = xv[e] - mu[e];
+      if (relu && !(fmaf(a[e], dd, be[e]) > 0.f)) g[e] = 0.f;
+      d[e] = a[e] * (g[e] - m1[e] - dd * rs[e] * m2[e]);
+    }
+    Vec16<T>::store(db + (long long)i * dx.sh + (long long)j * dx.sw, d);
+    if (gtotal.ptr) stv_img<VEC>(gtotal, img_off(gtotal, n, i, j, c), g);
+  }
+}
+
+static bool fast_ok(const ast_image* im, int vec) {
+  return im->sc == 1 && im->c % vec == 0 && im->sw % vec == 0 && im->sh % vec == 0 && im->sn % vec == 0 &&
+         ((uintptr_t)im->ptr & 15) == 0;
+}
+
+static int grid_chunks(int n, int npix, int slots, int* chunk) {
+  int nblk = (8 * num_sms() + n - 1) / n;
+  const int maxb = (npix + slots - 1) / slots;
+  if (nblk > maxb) nblk = maxb;
+  if (nblk < 1) nblk = 1;
+  *chunk = (npix + nblk - 1) / nblk;
+  return (npix + *chunk - 1) / *chunk;
+}
+
+// Returns 1 if the fast kernel was launched, 0 if the shapes/dtypes need the generic kernel, <0 / >0 on error.
+int instnorm_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                        const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s) {
+  const int vec = x->dtype == AST_F32 ? 4 : 8;
+  if (x->dtype != out->dtype || !fast_ok(x, vec) || !fast_ok(out, vec) || NF_THREADS % (x->c / vec) != 0) return 0;
+  if (residual && !fast_ok(residual, vec)) return 0;
+  const int slots = NF_THREADS / (x->c / vec);
+  int chunk;
+  const int nblk = grid_chunks(x->n, out->h * out->w, slots, &chunk);
+  dim3 grid(nblk, x->n);
+  Img r = residual ? to_img(residual) : null_img();
+  if (x->dtype == AST_F32)
+    in_apply_fast_kernel<float><<<grid, NF_THREADS, 0, s>>>(to_img(x), mean, rstd, gamma, beta, r, to_img(out), pad, relu, chunk);
+  else
+    in_apply_fast_kernel<__nv_bfloat16><<<grid, NF_THREADS, 0, s>>>(to_img(x), mean, rstd, gamma, beta, r, to_img(out), pad, relu, chunk);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
+int instnorm_bwd_stats_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                            float* s1, float* s2, cudaStream_t s) {
+  const int vec = x->dtype == AST_F32 ? 4 : 8;
+  if (!fast_ok(x, vec) || NF_THREADS % (x->c / vec) != 0) return 0;
+  if ((gpad && !fast_ok(gpad, vec)) || (gextra && !fast_ok(gextra, vec))) return 0;
+  const int slots = NF_THREADS / (x->c / vec);
+  int chunk;
+  const int nblk = grid_chunks(x->n, x->h * x->w, slots, &chunk);
+  dim3 grid(nblk, x->n);
+  const size_t smem = 2 * (size_t)slots * x->c * sizeof(float);
+  Img gp = gpad ? to_img(gpad) : null_img(), ge = gextra ? to_img(gextra) : null_img();
+  if (x->dtype == AST_F32)
+    in_bwd_stats_fast_kernel<float><<<grid, NF_THREADS, smem, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
+  else
+    in_bwd_stats_fast_kernel<__nv_bfloat16><<<grid, NF_THREADS, smem, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
+int instnorm_bwd_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                            const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
+                            cudaStream_t s) {
+  const int vec = x->dtype == AST_F32 ? 4 : 8;
+  if (x->dtype != dx->dtype || !fast_ok(x, vec) || !fast_ok(dx, vec) || NF_THREADS % (x->c / vec) != 0) return 0;
+  if ((gpad && !fast_ok(gpad, vec)) || (gextra && !fast_ok(gextra, vec)) || (gtotal && !fast_ok(gtotal, vec))) return 0;
+  const int slots = NF_THREADS / (x->c / vec);
+  int chunk;
+  const int nblk = grid_chunks(x->n, x->h * x->w, slots, &chunk);
+  dim3 grid(nblk, x->n);
+  Img gp = gpad ? to_img(gpad) : null_img(), ge = gextra ? to_img(gextra) : null_img();
+  Img gt = gtotal ? to_img(gtotal) : null_img();
+  if (x->dtype == AST_F32)
+    in_bwd_apply_fast_kernel<float><<<grid, NF_THREADS, 0, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, to_img(dx), gt, chunk);
+  else
+    in_bwd_apply_fast_kernel<__nv_bfloat16><<<grid, NF_THREADS, 0, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, to_img(dx), gt, chunk);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
+}  // namespace ast
