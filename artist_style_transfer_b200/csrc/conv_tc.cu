@@ -14,7 +14,7 @@
 
 namespace ast {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
 constexpr int MAX_STAGES = 8;
 
 struct TcParams {
@@ -48,7 +48,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -91,6 +91,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // ============================ MMA issuer ============================
     int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
     const int kmma = p.rowb / 32;   // UMMA_K spans 32 bytes for both bf16 (16 elems) and tf32 (8 elems)
+    const unsigned desc_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
@@ -99,12 +100,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
+          // descriptor hi word is constant; lo word = (addr >> 4) | LBO, advanced by 32 B (= 2) per UMMA_K step
           const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const unsigned b_addr = a_addr + p.a_bytes;
-          for (int k = 0; k < kmma; ++k) {
-            const unsigned long long ad = make_smem_desc(a_addr + k * 32, p.sbo, p.layout_type);
-            const unsigned long long bd = make_smem_desc(b_addr + k * 32, p.sbo, p.layout_type);
-            tc_mma<KIND>(d_tmem, ad, bd, p.idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          const unsigned a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
+          const unsigned b_lo = (((a_addr + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          tc_mma<KIND>(d_tmem, pack_desc64(a_lo, desc_hi), pack_desc64(b_lo, desc_hi), p.idesc, ks > 0 ? 1u : 0u);
+          tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 2, desc_hi), pack_desc64(b_lo + 2, desc_hi), p.idesc, 1u);
+          if (kmma == 4) {
+            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 4, desc_hi), pack_desc64(b_lo + 4, desc_hi), p.idesc, 1u);
+            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 6, desc_hi), pack_desc64(b_lo + 6, desc_hi), p.idesc, 1u);
           }
           tc_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
           if (ks == ksteps - 1) tc_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
@@ -117,6 +121,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   } else {
     // ============================ epilogue (warps 2..5) ============================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int cpar = (warp - 2) >> 2;              // which half of the 32-column chunks this warp drains
+    unsigned char* stage = smem + (size_t)p.stages * p.stage_bytes + (warp - 2) * 1024;
     const int row = q * 32 + lane;
     const int ty = row / p.tw, tx = row % p.tw;
     int as = 0; unsigned aph = 0;
@@ -132,64 +138,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      EpiRows rows;
+      if (!p.thin) tc_epi_row_offsets(valid ? img_off(out, img, oy, ox, 0) : -1, lane, out.dtype == AST_F32, rows);
+      for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
         float v[32];
         tc_ld32(taddr0 + c0, v);
         const int co = nt * p.bn + c0;
-        if (valid && p.thin) {
-          // thin / strided output (e.g. 3-channel NCHW image): scalar epilogue on the valid channels only
-          for (int e = 0; e < 32 && co + e < p.cout_valid; ++e) {
-            float x = v[e];
-            if (bias) x += __ldg(bias + co + e);
-            if (add.ptr) x += ld_elem(add, img_off(add, img, oy, ox, co + e));
-            if (p.flags & AST_CONV_RELU) x = fmaxf(x, 0.f);
-            if (mask.ptr) x = ld_elem(mask, img_off(mask, img, oy, ox, co + e)) > 0.f ? x : 0.f;
-            if (p.flags & AST_CONV_ROUND_TF32) x = round_tf32(x);
-            st_elem(out, img_off(out, img, oy, ox, co + e), x);
-          }
-        } else if (valid && co < p.cout) {
-          if (bias) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] += __ldg(bias + co + e);
-          }
-          if (add.ptr) {
-            const long long o = img_off(add, img, oy, ox, co);
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) { float t[4]; ld4_img(add, o + e, t); v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3]; }
-          }
-          if (p.flags & AST_CONV_RELU) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (mask.ptr) {
-            const long long o = img_off(mask, img, oy, ox, co);
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              float t[4]; ld4_img(mask, o + e, t);
-              v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f;
-              v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;
-            }
-          }
-          if (p.flags & AST_CONV_ROUND_TF32) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
-          }
-          const long long oo = img_off(out, img, oy, ox, co);
-          if (out.dtype == AST_F32) {
-            float* op = (float*)out.ptr + oo;
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          } else {
-            __nv_bfloat16* op = (__nv_bfloat16*)out.ptr + oo;
-#pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-              h[0] = __floats2bfloat162_rn(v[e], v[e + 1]); h[1] = __floats2bfloat162_rn(v[e + 2], v[e + 3]);
-              h[2] = __floats2bfloat162_rn(v[e + 4], v[e + 5]); h[3] = __floats2bfloat162_rn(v[e + 6], v[e + 7]);
-              *reinterpret_cast<uint4*>(op + e) = u;
-            }
-          }
+        if (p.thin) {
+          if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
+        } else {
+          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
         }
       }
       tc_fence_before();
@@ -207,6 +165,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ host side
+int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
+                   cudaStream_t stream);   // conv_ws.cu: 1 = launched, 0 = not applicable
 int tc_capabilities() { return 3; }   // 1 = conv_tc.cu, 2 = contract_tc.cu (both are always built together)
 
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
@@ -230,6 +191,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  if (int wr = conv_gather_ws(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return wr == 1 ? 0 : wr;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -283,7 +245,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 8192;   // + per-warp store-transpose stage
   const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   cudaError_t e;

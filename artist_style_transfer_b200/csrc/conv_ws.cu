@@ -1,0 +1,285 @@
+// Weight-stationary, halo-reusing variant of the tcgen05 gather convolution (stride-1 input, small filters).
+//
+// conv_tc.cu re-loads the 128-pixel A tile for every tap (9x / 81x read amplification out of L2) and re-streams the
+// weights for every tile.  For layers whose whole packed filter fits in shared memory this kernel instead
+//   * loads ALL taps' weights once per CTA (they stay resident for every tile the persistent CTA processes), and
+//   * loads ONE halo patch (16+kh-1) x 16 pixels per cin-chunk and tile; each tap's A operand is the same patch
+//     addressed through a shifted shared-memory descriptor: tile = 16 rows x 8 pixels, one 8-pixel row = one
+//     swizzle atom, atoms are SBO = 16 pixels apart, the tap shift (dy*16 + dx) pixels moves the start address
+//     (the hardware swizzles on absolute smem address bits, so unaligned starts need no base_offset - measured).
+// Used for: VGG conv1_2-class 64->64 layers, the row-im2col'd 3-channel ends, the 81-tap 9x9 32->3 convolution.
+#include "tc_common.cuh"
+
+namespace ast {
+
+constexpr int WS_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int WS_MAX_PBUF = 4;
+constexpr int WS_TH = 16, WS_TW = 8;
+
+struct WsParams {
+  int mi, mj, tiles_i, tiles_j, n_img;
+  int bn, cout, cout_valid, thin, flags;
+  int ntaps, kchunks, kc, rowb;
+  int so, oy0, ox0;
+  int dy_min, dx_min, ph, pw;
+  int patch_bytes, patch_tx, n_pbuf, w_tile_bytes, w_total_bytes;
+  unsigned idesc, layout_type, sbo, base_mode;
+  long long total_tiles;
+  short tdy[AST_MAX_TAPS];
+  short tdx[AST_MAX_TAPS];
+};
+
+__device__ __forceinline__ unsigned long long make_ws_desc(unsigned saddr, unsigned sbo_bytes, unsigned layout_type,
+                                                           unsigned base_mode) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
+  d |= (unsigned long long)1 << 16;
+  d |= (unsigned long long)(sbo_bytes >> 4) << 32;
+  d |= (unsigned long long)1 << 46;
+  if (base_mode) d |= (unsigned long long)((saddr >> 7) & 7u) << 49;   // swizzle phase of an unaligned start
+  d |= (unsigned long long)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ unsigned long long pack_desc(unsigned lo, unsigned hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
+               const float* __restrict__ bias, const Img add, const Img mask, const Img out) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
+  __shared__ unsigned tmem_slot;
+  __shared__ unsigned s_tapoff[AST_MAX_TAPS];    // per-tap A start offset inside the patch, in 16-byte units
+
+  unsigned char* smem_w = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_p = smem_w + ((p.w_total_bytes + 1023) & ~1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned tmem_cols = (2 * p.bn <= 32) ? 32 : (2 * p.bn <= 64) ? 64 : (2 * p.bn <= 128) ? 128 : (2 * p.bn <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    for (int s = 0; s < p.n_pbuf; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
+    mbar_init(&wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < p.ntaps) {
+    const int t = threadIdx.x - 64;
+    s_tapoff[t] = (unsigned)((p.tdy[t] * p.pw + p.tdx[t]) * p.rowb) >> 4;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {       // the whole filter, once
+      mbar_expect_tx(&wbar, (unsigned)p.w_total_bytes);
+      for (int t = 0; t < p.ntaps; ++t)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(smem_w + (size_t)(t * p.kchunks + kc) * p.w_tile_bytes, &tm_w, &wbar, kc * p.kc, t * p.cout);
+    }
+    __syncwarp();
+    int s = 0; unsigned ph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long r = tile;
+      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
+      const int ti = (int)(r % p.tiles_i);
+      const int img = (int)(r / p.tiles_i);
+      const int x0 = tj * WS_TW + p.dx_min, y0 = ti * WS_TH + p.dy_min;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&pempty[s], ph ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&pfull[s], (unsigned)p.patch_tx);
+          tma_load_4d(smem_p + (size_t)s * p.patch_bytes, &tm_in, &pfull[s], kc * p.kc, x0, y0, img);
+        }
+        __syncwarp();
+        if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
+    const int kmma = p.rowb / 32;
+    mbar_wait(&wbar, 0);
+    tc_fence_after();
+    const unsigned w_addr0 = smem_u32(smem_w);
+    const unsigned hi_a = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
+    const unsigned hi_b = ((8u * p.rowb) >> 4) | (1u << 14) | (p.layout_type << 29);
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const unsigned d_tmem = tmem_base + (unsigned)(as * p.bn);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&pfull[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          // descriptors: hi word is constant, lo word = (addr >> 4) | LBO; one 32-bit add per MMA
+          const unsigned p_lo = ((smem_u32(smem_p + (size_t)s * p.patch_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
+          const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
+          unsigned acc = kc > 0 ? 1u : 0u;
+#pragma unroll 1
+          for (int t = 0; t < p.ntaps; ++t) {
+            const unsigned a_lo = p_lo + s_tapoff[t];
+            const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
+            tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
+            tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
+            if (kmma == 4) {
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
+            }
+            acc = 1u;
+          }
+          tc_commit(&pempty[s]);
+          if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int q = warp & 3;                        // TMEM lane quarter of this warp
+    const int cpar = (warp - 2) >> 2;              // which half of the 32-column chunks this warp drains
+    const int row = q * 32 + lane;
+    const int ty = row / WS_TW, tx = row % WS_TW;
+    unsigned char* stage = smem_p + (size_t)p.n_pbuf * p.patch_bytes + (warp - 2) * 1024;
+    int as = 0; unsigned aph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long r = tile;
+      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
+      const int ti = (int)(r % p.tiles_i);
+      const int img = (int)(r / p.tiles_i);
+      const int i = ti * WS_TH + ty, j = tj * WS_TW + tx;
+      const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
+      const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
+      EpiRows rows;
+      if (!p.thin) tc_epi_row_offsets(valid ? img_off(out, img, oy, ox, 0) : -1, lane, out.dtype == AST_F32, rows);
+      for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
+        float v[32];
+        tc_ld32(taddr0 + c0, v);
+        if (p.thin) {
+          if (valid) tc_epilogue32(v, c0, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
+        } else {
+          tc_epilogue32_coalesced(v, c0, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// Returns 1 = launched, 0 = not applicable (caller uses conv_tc), other = error.
+int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
+                   cudaStream_t stream) {
+  const char* env = getenv("AST_CONV_WS");
+  const int mode = env ? atoi(env) : 1;            // 0 = off (A/B against conv_tc), 1 = on, 9 = experiment: base_offset
+  if (mode == 0) return 0;
+  if (g->si != 1 || g->w_img_stride != 0 || cpad > 256) return 0;
+  const int esz = in->dtype == AST_F32 ? 4 : 2;
+  int dy_min = 1 << 30, dy_max = -(1 << 30), dx_min = 1 << 30, dx_max = -(1 << 30);
+  for (int t = 0; t < g->ntaps; ++t) {
+    dy_min = g->dy[t] < dy_min ? g->dy[t] : dy_min; dy_max = g->dy[t] > dy_max ? g->dy[t] : dy_max;
+    dx_min = g->dx[t] < dx_min ? g->dx[t] : dx_min; dx_max = g->dx[t] > dx_max ? g->dx[t] : dx_max;
+  }
+  if (dx_max - dx_min > 8 || dy_max - dy_min > 15) return 0;
+  WsParams p;
+  memset(&p, 0, sizeof(p));
+  p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
+  p.kc = p.rowb / esz;
+  p.kchunks = in->c / p.kc;
+  p.bn = cpad;
+  p.w_tile_bytes = p.bn * p.rowb;
+  p.w_total_bytes = g->ntaps * p.kchunks * p.w_tile_bytes;
+  p.pw = (dx_max == dx_min) ? WS_TW : 16;
+  p.ph = WS_TH + (dy_max - dy_min);
+  p.patch_tx = p.pw * p.ph * p.rowb;
+  p.patch_bytes = (p.patch_tx + 1023) & ~1023;
+  const int budget = 232448 - 1024 - 1024 - 8192 - ((p.w_total_bytes + 1023) & ~1023);   // align slack, static, store stage
+  if (budget < 2 * p.patch_bytes) return 0;
+  p.n_pbuf = budget / p.patch_bytes;
+  if (p.n_pbuf > WS_MAX_PBUF) p.n_pbuf = WS_MAX_PBUF;
+  EncodeTiledFn encode = get_encode();
+  AST_CHECK_ARG(encode, "conv_ws: cuTensorMapEncodeTiled entry point not available");
+
+  p.mi = g->mi; p.mj = g->mj; p.so = g->so; p.oy0 = g->oy0; p.ox0 = g->ox0;
+  p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.cout_valid = out->c; p.thin = thin; p.n_img = in->n;
+  p.dy_min = dy_min; p.dx_min = dx_min;
+  for (int t = 0; t < g->ntaps; ++t) { p.tdy[t] = g->dy[t] - dy_min; p.tdx[t] = g->dx[t] - dx_min; }
+  p.tiles_i = (p.mi + WS_TH - 1) / WS_TH;
+  p.tiles_j = (p.mj + WS_TW - 1) / WS_TW;
+  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j;
+  p.layout_type = p.rowb == 128 ? 2u : 4u;
+  p.sbo = (unsigned)(p.pw * p.rowb);
+  // Measured on B200: the tensor core applies the 128B/64B swizzle XOR on ABSOLUTE shared-memory address bits, so a
+  // start address shifted by whole pixels needs base_offset = 0 (setting it to (addr>>7)&7 gives wrong results).
+  p.base_mode = mode == 9 ? 1u : 0u;
+  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+
+  alignas(64) CUtensorMap tm_in, tm_w;
+  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {(cuuint64_t)in->sw * esz, (cuuint64_t)in->sh * esz, (cuuint64_t)in->sn * esz};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)p.pw, (cuuint32_t)p.ph, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tm_in, dt, 4, in->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_ws: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return (int)r; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)((long long)g->ntaps * cpad)};
+    cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_ws: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
+  }
+  const size_t smem = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)p.n_pbuf * p.patch_bytes + 8192;
+  const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
+  cudaError_t e;
+  if (in->dtype == AST_BF16) {
+    e = cudaFuncSetAttribute(conv_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_ws_kernel<0><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+  } else {
+    e = cudaFuncSetAttribute(conv_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_ws_kernel<1><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+  }
+  if (e != cudaSuccess) { set_error("conv_ws: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
+}  // namespace ast

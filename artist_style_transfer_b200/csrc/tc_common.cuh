@@ -88,12 +88,190 @@ __device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, uns
   d |= (unsigned long long)layout_type << 61;
   return d;
 }
+__device__ __forceinline__ unsigned long long pack_desc64(unsigned lo, unsigned hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 __device__ __forceinline__ float round_tf32(float x) {
   unsigned r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
 
+
+// Fused epilogue for 32 consecutive output channels of one pixel held in registers (conv_ws.cu):
+// bias -> tap-gradient add -> ReLU -> ReLU mask -> TF32 rounding -> 16-byte stores (or scalar "thin" stores).
+__device__ __forceinline__ void tc_epilogue32(float* v, int co, int img, int oy, int ox, bool thin, int cout,
+                                              int cout_valid, int flags, const float* __restrict__ bias, const Img& add,
+                                              const Img& mask, const Img& out) {
+  if (thin) {
+    // fully unrolled with a predicate: a dynamic index would force v[] (the accumulator registers) into local memory
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (co + e >= cout_valid) continue;
+      float x = v[e];
+      if (bias) x += __ldg(bias + co + e);
+      if (add.ptr) x += ld_elem(add, img_off(add, img, oy, ox, co + e));
+      if (flags & AST_CONV_RELU) x = fmaxf(x, 0.f);
+      if (mask.ptr) x = ld_elem(mask, img_off(mask, img, oy, ox, co + e)) > 0.f ? x : 0.f;
+      if (flags & AST_CONV_ROUND_TF32) x = round_tf32(x);
+      st_elem(out, img_off(out, img, oy, ox, co + e), x);
+    }
+    return;
+  }
+  if (co >= cout) return;
+  if (bias) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] += __ldg(bias + co + e);
+  }
+  if (add.ptr) {
+    const long long o = img_off(add, img, oy, ox, co);
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) { float t[4]; ld4_img(add, o + e, t); v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3]; }
+  }
+  if (flags & AST_CONV_RELU) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  if (mask.ptr) {
+    const long long o = img_off(mask, img, oy, ox, co);
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float t[4]; ld4_img(mask, o + e, t);
+      v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f;
+      v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;
+    }
+  }
+  if (flags & AST_CONV_ROUND_TF32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+  }
+  const long long oo = img_off(out, img, oy, ox, co);
+  if (out.dtype == AST_F32) {
+    float* op = (float*)out.ptr + oo;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+  } else {
+    __nv_bfloat16* op = (__nv_bfloat16*)out.ptr + oo;
+#pragma unroll
+    for (int e = 0; e < 32; e += 8) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+      h[0] = __floats2bfloat162_rn(v[e], v[e + 1]); h[1] = __floats2bfloat162_rn(v[e + 2], v[e + 3]);
+      h[2] = __floats2bfloat162_rn(v[e + 4], v[e + 5]); h[3] = __floats2bfloat162_rn(v[e + 6], v[e + 7]);
+      *reinterpret_cast<uint4*>(op + e) = u;
+    }
+  }
+}
+
+// Coalesced epilogue.  The 32 x 32 block (this warp's 32 pixel rows x 32 channels) is transposed through a 1 KB
+// per-warp shared-memory stage, 8 rows per pass, XOR-swizzled 16-byte chunks (conflict-free), so every global store
+// instruction writes whole 128-byte (fp32) / 64-byte (bf16) row segments.  Row offsets are exchanged ONCE per tile
+// (tc_epi_row_offsets) and reused for every 32-channel chunk.  All 32 lanes must call both functions.
+struct EpiRows { long long off[8]; };
+
+__device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void tc_epi_row_offsets(long long my_off, int lane, bool f32, EpiRows& r) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // fp32: pass p = k>>1, iteration i = k&1, row = 8p + 4i + lane/8 ; bf16: pass p = k (k < 4), row = 8p + lane/4
+    const int src = f32 ? (8 * (k >> 1) + 4 * (k & 1) + (lane >> 3)) : (8 * (k & 3) + (lane >> 2));
+    r.off[k] = __shfl_sync(0xffffffffu, my_off, src);
+  }
+}
+
+__device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int img, int oy, int ox, bool valid, int cout,
+                                                        int flags, const float* __restrict__ bias, const Img& add,
+                                                        const Img& mask, const Img& out, const EpiRows& rows,
+                                                        unsigned char* stage, int lane) {
+  if (co >= cout) return;                                   // uniform
+  if (valid) {
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + e));
+        v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+      }
+    }
+    if (add.ptr) {
+      const long long o = img_off(add, img, oy, ox, co);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) { float t[4]; ld4_img(add, o + e, t); v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3]; }
+    }
+    if (flags & AST_CONV_RELU) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    if (mask.ptr) {
+      const long long o = img_off(mask, img, oy, ox, co);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        float t[4]; ld4_img(mask, o + e, t);
+        v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f;
+        v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;
+      }
+    }
+    if (flags & AST_CONV_ROUND_TF32) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+    }
+  }
+  const unsigned st = smem_u32(stage);                      // explicit shared-space accesses (16-byte slots)
+  const int r8 = lane & 7;
+  if (out.dtype == AST_F32) {                               // stage: [8 rows][8 chunks of 16 B]
+    float* base = (float*)out.ptr + co + 4 * (lane & 7);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if ((lane >> 3) == p) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts128(st + 16u * (r8 * 8 + (c ^ r8)), make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                                             __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = (lane >> 3) + 4 * i;
+        const uint4 val = lds128(st + 16u * (row * 8 + ((lane & 7) ^ row)));
+        const long long off = rows.off[2 * p + i];
+        if (off >= 0) *reinterpret_cast<uint4*>(base + off) = val;
+      }
+      __syncwarp();
+    }
+  } else {                                                  // stage: [8 rows][4 chunks of 16 B]
+    __nv_bfloat16* base = (__nv_bfloat16*)out.ptr + co + 8 * (lane & 3);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if ((lane >> 3) == p) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          h[0] = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]); h[1] = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+          h[2] = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]); h[3] = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+          sts128(st + 16u * (r8 * 4 + (c ^ (r8 & 3))), u);
+        }
+      }
+      __syncwarp();
+      {
+        const int row = lane >> 2;
+        const uint4 val = lds128(st + 16u * (row * 4 + ((lane & 3) ^ (row & 3))));
+        const long long off = rows.off[p];
+        if (off >= 0) *reinterpret_cast<uint4*>(base + off) = val;
+      }
+      __syncwarp();
+    }
+  }
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
