@@ -44,6 +44,7 @@ _SIGNATURES = {
                             ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int32, _vp],
     "ast_row_im2col": [_P(Image), _P(Image), _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                        ctypes.c_int32, ctypes.c_int32, _vp],
+    "ast_unfold_rows": [_P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_stats": [_P(Image), _vp, _vp, ctypes.c_float, _vp, _vp],
     "ast_instnorm_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_bwd_stats": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,

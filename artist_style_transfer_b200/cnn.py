@@ -258,18 +258,31 @@ class _StageFunction(torch.autograd.Function):
                 gpad[j] = gextra[j] = None           # free
             k2 = st.k * st.k
             wtc = ctx.mode == "fast" and ops.tc_contract_eligible(xin, d_raw)
+            one_tap = [cg.Launch(1, 1, 1, 1, 0, 0, [(0, 0)], [(0, 0)], 0)]
             if i == 0 and ctx.thin_in:
-                # tmp[dy][co][dx*cin+c] += sum_p dY[p][co] * Xr[p + dy rows][dx*cin+c]
-                tmp = torch.zeros((st.k, st.cout, 32), dtype=torch.float32, device=xin.device)
-                ops.wgrad_gather(xin, d_raw, launches, tmp, 32, 1, st.cout * 32, 0, tensor=wtc)
-                g_cw = tmp[:, :, :st.k * st.cin].reshape(st.k, st.cout, st.k, st.cin).permute(1, 3, 0, 2).contiguous()
+                # fold the k vertical taps into channels too (X[y][x][dy*32 + dx*cin+c] = Xr[y+dy][x][dx*cin+c], 16-byte
+                # copies), then ONE single-tap contraction: tmp[co][dy*32 + dx*cin+c] = sum_p dY[p][co] * X[p][...]
+                n_, h_, w_ = d_raw.shape[0], d_raw.shape[1], d_raw.shape[2]
+                xf = torch.empty((n_, h_, w_, st.k * 32), dtype=adt, device=xin.device)
+                ops.unfold_rows(xin, xf, st.k, 1)
+                one_tap[0].mi, one_tap[0].mj = h_, w_
+                # operands swapped (the 288-channel tensor provides the M rows): tmp[dy*32 + dx*cin+c][co]
+                tmp = torch.zeros((st.k * 32, st.cout), dtype=torch.float32, device=xin.device)
+                ops.wgrad_gather(d_raw, xf, one_tap, tmp, st.cout, 1, 0, 0, tensor=wtc)
+                g_cw = (tmp.view(st.k, 32, st.cout)[:, :st.k * st.cin, :].reshape(st.k, st.k, st.cin, st.cout)
+                        .permute(3, 2, 0, 1).contiguous())
+                del xf
             elif not st.norm and thin_out:
-                # tmp[dy][dx*cout+co][c] += sum_{y,x'} Dr[y][x'][dx*cout+co] * xin[y+dy][x'][c]
-                taps, wt = _vtaps(st.k)
-                lw = [cg.Launch(d_raw.shape[1], d_raw.shape[2], 1, 1, 0, 0, taps, wt, 0)]
-                tmp = torch.zeros((st.k, 32, st.cin), dtype=torch.float32, device=xin.device)
-                ops.wgrad_gather(xin, d_raw, lw, tmp, st.cin, 1, 32 * st.cin, 0, tensor=True)
-                g_cw = tmp[:, :st.k * st.cout, :].reshape(st.k, st.k, st.cout, st.cin).permute(2, 3, 0, 1).contiguous()
+                # D[y'][x'][dy*32 + dx*cout+co] = Dr[y'-dy][x'][dx*cout+co] (zero outside), then ONE single-tap
+                # contraction against the padded input: tmp[dy*32 + dx*cout+co][c] = sum_{y',x'} D[..] * xin[y'][x'][c]
+                df = torch.empty((xin.shape[0], xin.shape[1], xin.shape[2], st.k * 32), dtype=adt, device=xin.device)
+                ops.unfold_rows(d_raw, df, st.k, -1)
+                one_tap[0].mi, one_tap[0].mj = xin.shape[1], xin.shape[2]
+                tmp = torch.zeros((st.k * 32, st.cin), dtype=torch.float32, device=xin.device)
+                ops.wgrad_gather(xin, df, one_tap, tmp, st.cin, 1, 0, 0, tensor=True)
+                g_cw = (tmp.view(st.k, 32, st.cin)[:, :st.k * st.cout, :].reshape(st.k, st.k, st.cout, st.cin)
+                        .permute(2, 3, 0, 1).contiguous())
+                del df
             else:
                 g_cw = torch.zeros_like(cw, dtype=torch.float32)
                 if st.kind == "conv":

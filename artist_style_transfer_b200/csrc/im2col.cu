@@ -103,9 +103,49 @@ __global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int*
   }
 }
 
+// out[n, y, x, d*C + j] = src[n, y + sign*d - py, x, j]  (0 outside): folds kh vertical taps of an NHWC tensor into
+// channels with 16-byte copies, so a kh-tap filter-gradient contraction becomes ONE tap with kh*C channels.
+__global__ void __launch_bounds__(256) unfold_rows_kernel(Img src, Img out, int kh, int sign, int py, int esz) {
+  const int cpp = src.c * esz / 16;                 // 16-byte chunks per source pixel
+  const long long total = (long long)out.n * out.h * out.w * kh * cpp;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int ch = (int)(idx % cpp);
+    long long r = idx / cpp;
+    const int d = (int)(r % kh); r /= kh;
+    const int x = (int)(r % out.w); r /= out.w;
+    const int y = (int)(r % out.h);
+    const int n = (int)(r / out.h);
+    const int sy = y + sign * d - py;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (sy >= 0 && sy < src.h)
+      v = *reinterpret_cast<const uint4*>(src.ptr + (img_off(src, n, sy, x, 0) * esz + ch * 16));
+    *reinterpret_cast<uint4*>(out.ptr + ((img_off(out, n, y, x, 0) + (long long)d * src.c) * esz + ch * 16)) = v;
+  }
+}
+
 }  // namespace ast
 
 using namespace ast;
+
+extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32_t kh, int32_t sign, int32_t py,
+                               void* stream) {
+  AST_CHECK_ARG(src && out, "ast_unfold_rows: null argument");
+  const int esz = src->dtype == AST_F32 ? 4 : 2;
+  AST_CHECK_ARG(src->dtype == out->dtype && out->n == src->n && out->w == src->w && out->c == kh * src->c,
+                "ast_unfold_rows: out must be [n, *, w, kh*c] of the same dtype");
+  AST_CHECK_ARG(src->sc == 1 && out->sc == 1 && (src->c * esz) % 16 == 0 && (src->sw * esz) % 16 == 0 &&
+                (src->sh * esz) % 16 == 0 && (src->sn * esz) % 16 == 0 && (out->sw * esz) % 16 == 0 &&
+                (out->sh * esz) % 16 == 0 && (out->sn * esz) % 16 == 0 && (sign == 1 || sign == -1),
+                "ast_unfold_rows: NHWC tensors with 16-byte aligned pixels required");
+  const long long total = (long long)out->n * out->h * out->w * kh * (src->c * esz / 16);
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+  unfold_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), kh, sign, py, esz);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shift, int32_t kw, int32_t sign,
                               int32_t px, int32_t py, int32_t reflect, int32_t round_tf32, void* stream) {

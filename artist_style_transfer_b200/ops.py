@@ -108,6 +108,14 @@ def row_im2col(src, out, kw, sign, px, py, reflect, shift=None, round_tf32=False
         return out
 
 
+def unfold_rows(src, out, kh, sign, py=0):
+    """out[n,y,x,d*C+j] = src[n, y+sign*d-py, x, j] (0 outside); see include/ast.h ast_unfold_rows."""
+    with _timed("pointwise"):
+        si, oi = image(src), image(out)
+        check(_lib.load().ast_unfold_rows(ref(si), ref(oi), kh, sign, py, stream_ptr()), "ast_unfold_rows")
+        return out
+
+
 def tc_eligible(x, cout):
     """Shapes the tcgen05 kernel accepts (conv_tc.cu): cin*elemsize % 64 == 0, cout % 32 == 0, NHWC."""
     return (_lib.has_tc_conv() and x.stride(3) == 1 and (x.shape[3] * x.element_size()) % 64 == 0

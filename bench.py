@@ -120,6 +120,10 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # keep stdout clean for the ONE JSON line: libraries (e.g. "NCCL version ...") write to fd 1 during init
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import artist_style_transfer_b200 as ast
@@ -240,7 +244,7 @@ def run_ours(args):
         "gflop_per_image": GF_PER_IMG["total"] * scale,
         "tensor_frac_whole_step": GF_PER_IMG["total"] * scale * B * K / ms / peak_tf,
     }
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

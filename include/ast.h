@@ -98,6 +98,10 @@ int ast_pack_weights_ex(const float* src, const int32_t* tap_off, int32_t ntaps,
 int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shift, int32_t kw, int32_t sign,
                    int32_t px, int32_t py, int32_t reflect, int32_t round_tf32, void* stream);
 
+/* out[n, y, x, d*C + j] = src[n, y + sign*d - py, x, j] (0 outside), d in [0, kh): folds the kh vertical taps of an NHWC
+ * tensor into channels so that a kh-tap ast_wgrad_gather becomes one tap over kh*C channels (thin 9x9 layers). */
+int ast_unfold_rows(const ast_image* src, const ast_image* out, int32_t kh, int32_t sign, int32_t py, void* stream);
+
 /* nn.InstanceNorm2d(affine=True), eps 1e-5, biased variance (cnn.py:68,114).
  * stats: mean[n*c], rstd[n*c] (fp32).  workspace: ast_instnorm_workspace_bytes(). */
 int64_t ast_instnorm_workspace_bytes(int32_t n, int32_t c);
