@@ -239,7 +239,8 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   const unsigned fmt = rows->dtype == AST_F32 ? 2u : 1u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
   const long long fixed = (long long)ntaps * p.m_blocks * p.n_blocks * (p.per_img ? p.n_img : 1);
-  long long ks = (2LL * num_sms() + fixed - 1) / fixed;
+  // one CTA per SM (200 KB of smem each): size the split-K so the whole grid is a single wave without a tail
+  long long ks = num_sms() / fixed;
   if (ks < 1) ks = 1;
   if (ks > p.chunks_total) ks = p.chunks_total;
   p.chunks_per_cta = (int)((p.chunks_total + ks - 1) / ks);

@@ -1,8 +1,12 @@
 // Vectorised InstanceNorm apply / backward kernels (the HBM-roofline kernels of the path).
 //
 // Thread mapping: a thread owns ONE 16-byte channel group (8 bf16 / 4 fp32 channels) for the whole kernel, so the
-// per-(n,c) constants (gamma*rstd, mean, beta, s1/HW, s2/HW) live in registers; consecutive threads cover consecutive
-// channel groups of a pixel, then consecutive pixels -> every warp access is a run of full 128-byte lines.
+// per-(n,c) constants live in registers; consecutive threads cover consecutive channel groups of a pixel, then
+// consecutive pixels -> every warp access is a run of full 128-byte lines.  To keep the register count low enough
+// for 4 blocks/SM (memory-level parallelism is what these kernels live on), the per-channel math is folded into few
+// constants:   y  = A*x + D                      (A = gamma*rstd, D = beta - A*mean; same expression fwd and bwd)
+//              dx = A*g + B*x + C                (B = -A*rstd*s2/HW, C = -A*s1/HW - B*mean)
+//              s1 = sum g',  s2 = rstd*(sum g'*x - mean*sum g')
 // One pixel costs one integer division (amortised over 8 channels); reflection folding is only evaluated on the
 // border ring.  These replace the generic kernels of norm.cu whenever x / out / dx share one dtype and the tensors
 // are NHWC with 16-byte-aligned pixel strides (always true inside the engine).
@@ -35,7 +39,7 @@ __device__ __forceinline__ void stv_img(const Img& im, long long off, const floa
 
 // ---------------------------------------------------------------- forward apply
 template <typename T>
-__global__ void __launch_bounds__(NF_THREADS)
+__global__ void __launch_bounds__(NF_THREADS, 4)
 in_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, Img res, Img out, int pad,
                      int relu, int chunk) {
@@ -43,12 +47,11 @@ in_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __restr
   const int C = x.c, lanes = C / VEC, slots = NF_THREADS / lanes;
   const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
   const int n = blockIdx.y, c = lane * VEC;
-  float a[VEC], mu[VEC], be[VEC];
+  float A[VEC], D[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    mu[e] = mean[n * C + c + e];
-    a[e] = gamma[c + e] * rstd[n * C + c + e];
-    be[e] = beta[c + e];
+    A[e] = gamma[c + e] * rstd[n * C + c + e];
+    D[e] = beta[c + e] - A[e] * mean[n * C + c + e];
   }
   const int npix = out.h * out.w;
   const int pbeg = blockIdx.x * chunk, pend = min(npix, pbeg + chunk);
@@ -60,7 +63,7 @@ in_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __restr
     float v[VEC];
     Vec16<T>::load(xb + (long long)i * x.sh + (long long)j * x.sw, v);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) v[e] = fmaf(a[e], v[e] - mu[e], be[e]);
+    for (int e = 0; e < VEC; ++e) v[e] = fmaf(A[e], v[e], D[e]);
     if (res.ptr) {
       float r[VEC];
       ldv_img<VEC>(res, img_off(res, n, i, j, c), r);
@@ -111,7 +114,7 @@ __device__ __forceinline__ void gprime_fast(const Img& gpad, int pad, const Img&
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NF_THREADS)
+__global__ void __launch_bounds__(NF_THREADS, 4)
 in_bwd_stats_fast_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
                          int relu, float* __restrict__ s1o, float* __restrict__ s2o, int chunk) {
@@ -120,11 +123,11 @@ in_bwd_stats_fast_kernel(Img x, const float* __restrict__ mean, const float* __r
   const int C = x.c, lanes = C / VEC, slots = NF_THREADS / lanes;
   const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
   const int n = blockIdx.y, c = lane * VEC;
-  float a[VEC], mu[VEC], rs[VEC], be[VEC], t1[VEC], t2[VEC];
+  float A[VEC], D[VEC], t1[VEC], t2[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    mu[e] = mean[n * C + c + e]; rs[e] = rstd[n * C + c + e];
-    a[e] = gamma[c + e] * rs[e]; be[e] = beta[c + e];
+    A[e] = gamma[c + e] * rstd[n * C + c + e];
+    D[e] = beta[c + e] - A[e] * mean[n * C + c + e];
     t1[e] = 0.f; t2[e] = 0.f;
   }
   const int npix = x.h * x.w;
@@ -137,10 +140,9 @@ in_bwd_stats_fast_kernel(Img x, const float* __restrict__ mean, const float* __r
     gprime_fast<VEC>(gpad, pad, gextra, x.h, x.w, n, i, j, c, g);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const float d = xv[e] - mu[e];
-      if (relu && !(fmaf(a[e], d, be[e]) > 0.f)) g[e] = 0.f;      // same expression as the forward apply
+      if (relu && !(fmaf(A[e], xv[e], D[e]) > 0.f)) g[e] = 0.f;      // same expression as the forward apply
       t1[e] += g[e];
-      t2[e] = fmaf(g[e], d * rs[e], t2[e]);
+      t2[e] = fmaf(g[e], xv[e], t2[e]);
     }
   }
   float* r1 = sm;
@@ -151,13 +153,14 @@ in_bwd_stats_fast_kernel(Img x, const float* __restrict__ mean, const float* __r
   for (int cc = threadIdx.x; cc < C; cc += NF_THREADS) {
     float u1 = 0.f, u2 = 0.f;
     for (int s = 0; s < slots; ++s) { u1 += r1[s * C + cc]; u2 += r2[s * C + cc]; }
+    // s2 = sum g*xhat = rstd * (sum g*x - mean * sum g)
     atomicAdd(s1o + n * C + cc, u1);
-    atomicAdd(s2o + n * C + cc, u2);
+    atomicAdd(s2o + n * C + cc, rstd[n * C + cc] * (u2 - mean[n * C + cc] * u1));
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NF_THREADS)
+__global__ void __launch_bounds__(NF_THREADS, 4)
 in_bwd_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
                          int relu, const float* __restrict__ s1, const float* __restrict__ s2, Img dx, Img gtotal,
@@ -167,12 +170,14 @@ in_bwd_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __r
   const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
   const int n = blockIdx.y, c = lane * VEC;
   const float inv_hw = 1.f / (float)(x.h * x.w);
-  float a[VEC], mu[VEC], rs[VEC], be[VEC], m1[VEC], m2[VEC];
+  float A[VEC], B[VEC], Cc[VEC], D[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    mu[e] = mean[n * C + c + e]; rs[e] = rstd[n * C + c + e];
-    a[e] = gamma[c + e] * rs[e]; be[e] = beta[c + e];
-    m1[e] = s1[n * C + c + e] * inv_hw; m2[e] = s2[n * C + c + e] * inv_hw;
+    const float mu = mean[n * C + c + e], rs = rstd[n * C + c + e];
+    A[e] = gamma[c + e] * rs;
+    D[e] = beta[c + e] - A[e] * mu;
+    B[e] = -A[e] * rs * s2[n * C + c + e] * inv_hw;
+    Cc[e] = -A[e] * s1[n * C + c + e] * inv_hw - B[e] * mu;
   }
   const int npix = x.h * x.w;
   const int pbeg = blockIdx.x * chunk, pend = min(npix, pbeg + chunk);
@@ -180,17 +185,16 @@ in_bwd_apply_fast_kernel(Img x, const float* __restrict__ mean, const float* __r
   T* db = (T*)dx.ptr + (long long)n * dx.sn + c;
   for (int p = pbeg + slot; p < pend; p += slots) {
     const int i = p / x.w, j = p - i * x.w;
-    float xv[VEC], g[VEC], d[VEC];
+    float xv[VEC], g[VEC];
     Vec16<T>::load(xb + (long long)i * x.sh + (long long)j * x.sw, xv);
     gprime_fast<VEC>(gpad, pad, gextra, x.h, x.w, n, i, j, c, g);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const float dd = xv[e] - mu[e];
-      if (relu && !(fmaf(a[e], dd, be[e]) > 0.f)) g[e] = 0.f;
-      d[e] = a[e] * (g[e] - m1[e] - dd * rs[e] * m2[e]);
-    }
-    Vec16<T>::store(db + (long long)i * dx.sh + (long long)j * dx.sw, d);
+    for (int e = 0; e < VEC; ++e)
+      if (relu && !(fmaf(A[e], xv[e], D[e]) > 0.f)) g[e] = 0.f;
     if (gtotal.ptr) stv_img<VEC>(gtotal, img_off(gtotal, n, i, j, c), g);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) xv[e] = fmaf(A[e], g[e], fmaf(B[e], xv[e], Cc[e]));
+    Vec16<T>::store(db + (long long)i * dx.sh + (long long)j * dx.sw, xv);
   }
 }
 
@@ -201,7 +205,7 @@ static bool fast_ok(const ast_image* im, int vec) {
 
 static int grid_chunks(int n, int npix, int slots, int* chunk) {
   int nblk = (8 * num_sms() + n - 1) / n;
-  const int maxb = (npix + slots - 1) / slots;
+  const int maxb = (npix + 4 * slots - 1) / (4 * slots);       // at least 4 pixels per thread
   if (nblk > maxb) nblk = maxb;
   if (nblk < 1) nblk = 1;
   *chunk = (npix + nblk - 1) / nblk;
