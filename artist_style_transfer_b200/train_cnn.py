@@ -268,8 +268,15 @@ def gram(f, precision=None):
     return _GramFunction.apply(f, mode == "fast")
 
 
+_neg_mean_cache = {}
+
+
 def neg_mean(device):
-    return torch.tensor(IMAGENET_NEG_MEAN, dtype=torch.float32, device=device)
+    """(-103.939, -116.779, -123.68) on `device`, created once (no host-to-device copy inside a captured step)."""
+    key = str(device)
+    if key not in _neg_mean_cache:
+        _neg_mean_cache[key] = torch.tensor(IMAGENET_NEG_MEAN, dtype=torch.float32, device=device)
+    return _neg_mean_cache[key]
 
 
 def style_grams_single(vgg, style_tensor, batch_size):
@@ -381,28 +388,55 @@ class PerceptualTrainer:
     """
 
     def __init__(self, transfer, vgg, style_gram, lr=LR, weight_decay=1e-4, num_epochs=200, num_steps=2,
-                 content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT, group=None):
+                 content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT, group=None, cuda_graph=False):
         self.transfer, self.vgg, self.style_gram = transfer, vgg, style_gram
         self.content_weight, self.style_weight = content_weight, style_weight
         self.params = [p for p in transfer.parameters()]
-        self.optimizer = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay)          # :247
+        on_cuda = self.params[0].is_cuda
+        self.optimizer = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay,
+                                          capturable=bool(cuda_graph and on_cuda))                 # :247
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=max(1, num_epochs // num_steps),
                                                          gamma=0.5)                                # :248
         self.group = group
         self._flat = None
+        # cuda_graph=True: after 3 eager warm-up steps the whole step (fwd, bwd, all-reduce, Adam: ~350 launches) is
+        # captured once per input shape and replayed, removing host launch overhead and inter-kernel gaps.
+        self.cuda_graph = bool(cuda_graph and on_cuda)
+        self._graph, self._static_in, self._static_losses, self._eager_steps = None, None, None, 0
 
     def _allreduce_grads(self):
         if self._flat is None:
             self._flat = dp.GradBucket()
         self._flat.allreduce_mean(self.params, self.group)
 
-    def step(self, content_batch):
+    def _eager_step(self, content_batch):
         self.optimizer.zero_grad(set_to_none=True)                                                 # :295
         losses = perceptual_step(self.transfer, self.vgg, content_batch, self.style_gram,
                                  self.content_weight, self.style_weight, backward=True)
         self._allreduce_grads()
         self.optimizer.step()                                                                      # :334
         return losses
+
+    def _capture(self, content_batch):
+        self._static_in = content_batch.clone()
+        self._graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self._graph):
+            self._static_losses = self._eager_step(self._static_in)
+
+    def step(self, content_batch):
+        if not self.cuda_graph:
+            return self._eager_step(content_batch)
+        if self._graph is not None and self._static_in.shape == content_batch.shape:
+            self._static_in.copy_(content_batch, non_blocking=True)
+            self._graph.replay()
+            return self._static_losses
+        if self._eager_steps < 3:                       # warm up caches (packed weights, tap tables, allocator)
+            self._eager_steps += 1
+            return self._eager_step(content_batch)
+        self._capture(content_batch)                    # capture does not execute: run the graph once for this batch
+        self._graph.replay()
+        return self._static_losses
 
     def end_epoch(self):
         self.scheduler.step()                                                                      # :375

@@ -146,7 +146,7 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(2 + 7919 * rank)
     style_img = torch.randint(0, 256, (3, S, S), device=dev, generator=torch.Generator(device=dev).manual_seed(2)).float()
     style = ast.style_grams_single(vgg, style_img, B)
-    trainer = ast.PerceptualTrainer(net, vgg, style)
+    trainer = ast.PerceptualTrainer(net, vgg, style, cuda_graph=not args.no_graph)
     nbuf = 4
     batches = [torch.randint(0, 256, (B, 3, S, S), device=dev, generator=gen).float() for _ in range(nbuf)]
 
@@ -155,7 +155,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(W):
+    for i in range(W + (4 if not args.no_graph else 0)):   # graph mode: 3 eager steps + capture happen before timing
         trainer.step(batches[i % nbuf])
     barrier()
     sampler = ClockSampler(local)
@@ -196,11 +196,14 @@ def run_ours(args):
     e2e_value = B * world * ke / (float(te.item()) / 1e3)
 
     # ---- per-kernel-family device time (CUDA events on the launching stream), 2 instrumented steps
+    lc0 = _lib.launch_count()
     ops.profile_begin()
     kp = 2
     for i in range(kp):
-        trainer.step(batches[i % nbuf])
+        trainer._eager_step(batches[i % nbuf])          # per-op events need eager launches (not a graph replay)
     prof = ops.profile_end()
+    if not args.no_graph:        # replays do not pass through the library's launch counter: use the eager count
+        launches = (_lib.launch_count() - lc0) // kp * K
     fam = {k: {"ms_per_step": v[0] / kp, "launches_per_step": v[1] / kp} for k, v in prof.items()}
     scale = (S / 256.0) ** 2
     peaks = read_peaks()
@@ -234,7 +237,7 @@ def run_ours(args):
         "dtype": "bf16" if args.precision == "fast" else "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: perceptual-loss training step, {S}x{S}, batch {B}/GPU, "
                                f"precision={args.precision}, random-init TransformerNet+VGG16, Adam",
-                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; inputs rotate over 4 buffers"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                 "d2h_bytes_per_step": 12, "steps": ke},
@@ -259,6 +262,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

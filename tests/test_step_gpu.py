@@ -229,3 +229,22 @@ def test_fast_vs_strict_gradients(ast):
         # 0.945..1.0, and 0.97 between two bf16 runs that differ only in summation order): see DESIGN.md
         assert cos > 0.9, (name, cos)
         assert abs(float(gf.norm()) / float(g.norm()) - 1) < 0.15, name
+
+
+def test_cuda_graph_step_matches_eager(ast):
+    """Capturing the whole step in a CUDA graph must not change the numbers (same kernels, same order)."""
+    content = [weights.content_batch(2, 64, 2, step=i).cuda() for i in range(6)]
+    res = {}
+    for graph in (False, True):
+        net, vgg = build(ast, "fast")
+        style = ast.style_grams_single(vgg, weights.style_image(64, 2).cuda(), 2)
+        tr = ast.PerceptualTrainer(net, vgg, style, lr=1e-3, cuda_graph=graph)
+        losses = [tuple(float(v) for v in tr.step(c)) for c in content]
+        res[graph] = (losses, [p.detach().clone() for p in net.parameters()])
+    for a, b in zip(res[False][0], res[True][0]):
+        np.testing.assert_allclose(np.array(a), np.array(b), rtol=2e-3)     # atomics order differs run to run
+    assert res[True][0][3] != res[True][0][4]                               # replays really consume new inputs
+    for pa, pb in zip(res[False][1], res[True][1]):
+        # Adam moves every weight by ~lr*sign(g) per step, so run-to-run atomics noise on near-zero gradients shows up
+        # as a few flipped steps: compare the mean displacement against the 6*lr a weight can travel
+        assert float((pa - pb).abs().mean()) < 0.2 * 6 * 1e-3
