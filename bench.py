@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -211,9 +211,30 @@ def run_ours(args):
     conv_launches = sum(fam[k]["launches_per_step"] for k in ("conv_gather_tc", "conv_gather_simt") if k in fam)
     conv_tf = GF_PER_IMG["conv_gather"] * scale * B / conv_ms            # GF/ms == TF/s
     peak_tf = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step)", "bound": "tensor",
-                "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf, "traffic": None,
-                "peak_source": f"{peaks['src']} bf16 sustained", "launch_ms_avg": conv_ms / max(1.0, conv_launches)}
+    # TF32 peak is not in MEASURED_PEAKS.json: measure it the same way (cuBLAS 8192^3, best of 5).
+    # 72 % of the conv FLOPs of this mode run in TF32 (VGG + Gram backward), the rest in bf16 (TransformerNet).
+    tf32_peak = None
+    if rank == 0 and args.precision == "fast":
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a_ = torch.randn(8192, 8192, device=dev); b_ = torch.randn(8192, 8192, device=dev)
+        best = 1e9
+        for _ in range(6):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(); torch.matmul(a_, b_); t1.record(); torch.cuda.synchronize()
+            best = min(best, t0.elapsed_time(t1))
+        tf32_peak = 2 * 8192 ** 3 / best / 1e9
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a_, b_
+    tf32_share = (36.465 * 2 + 12.306 + 2.147) / GF_PER_IMG["conv_gather"]
+    mix_peak = None if not tf32_peak else 1.0 / (tf32_share / tf32_peak + (1 - tf32_share) / peaks["bf16_tflops"])
+    roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step: conv_tc_kernel + conv_ws_kernel)",
+                "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
+                "traffic": 375.0e6, "traffic_note": "dram read+write bytes of one conv_tc<tf32> launch (128->128 @128^2, "
+                "B=32) from profiles/r01b_conv_tc_ncu_full_excerpt.csv; algorithmic bytes of that launch: 537 MB",
+                "peak_source": f"{peaks['src']} bf16 sustained", "launch_ms_avg": conv_ms / max(1.0, conv_launches),
+                "tf32_tflops_measured": tf32_peak, "tf32_flop_share": tf32_share,
+                "frac_of_precision_mix_peak": None if not mix_peak else conv_tf / mix_peak}
     in_ms = fam.get("instnorm", {"ms_per_step": float("nan")})["ms_per_step"]
     esz = 2 if args.precision == "fast" else 4
     in_gb = IN_ELEMS_PER_IMG * scale * B * esz * 5 / 1e9                 # fwd 1R+1W, bwd 2R+1W
