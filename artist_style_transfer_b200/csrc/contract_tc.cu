@@ -26,6 +26,7 @@ struct CtParams {
   long long out_img_stride, s_m, s_n;
   float scale;
   int stages, box_bytes, stage_bytes, umma_k_bytes, kmma, upper_only;
+  int tg, ngroups;                  // taps handled by one CTA (rows operand loaded once per stage for all of them)
   unsigned sbo, layout_type;
   unsigned idesc;
   short dy[AST_MAX_TAPS];
@@ -56,7 +57,8 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
   __shared__ unsigned tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.y;
+  const int t0 = blockIdx.y * p.tg;                                   // first tap of this CTA's tap group
+  const int nt = min(p.tg, p.ntaps - t0);
   const int mb_idx = blockIdx.z / p.n_blocks, nb_idx = blockIdx.z % p.n_blocks;
   if (p.upper_only && nb_idx * p.bn + p.bn <= mb_idx * 128) return;   // block strictly below the diagonal
   int img_fixed = -1;
@@ -73,7 +75,8 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
   if (cbeg >= cend) return;                          // uniform across the CTA: nothing to do
 
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const unsigned tmem_cols = p.bn <= 32 ? 32 : p.bn <= 64 ? 64 : p.bn <= 128 ? 128 : 256;
+  const int acc_cols = p.tg * p.bn;
+  const unsigned tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_r) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
@@ -105,12 +108,13 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (lane == 0) {
         unsigned char* sr = smem + (size_t)s * p.stage_bytes;
-        mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
+        mbar_expect_tx(&full_bar[s], (unsigned)((p.m_boxes + nt * p.n_boxes) * p.box_bytes));
         for (int b = 0; b < p.m_boxes; ++b)
           tma_load_4d(sr + b * p.box_bytes, &tm_r, &full_bar[s], m0 + b * p.cb, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
-        for (int b = 0; b < p.n_boxes; ++b)
-          tma_load_4d(sr + r_bytes + b * p.box_bytes, &tm_c, &full_bar[s], n0 + b * p.cb, p.c_s * j0 + p.dx[t],
-                      p.c_s * i0 + p.dy[t], img);
+        for (int u = 0; u < nt; ++u)
+          for (int b = 0; b < p.n_boxes; ++b)
+            tma_load_4d(sr + r_bytes + (u * p.n_boxes + b) * p.box_bytes, &tm_c, &full_bar[s], n0 + b * p.cb,
+                        p.c_s * j0 + p.dx[t0 + u], p.c_s * i0 + p.dy[t0 + u], img);
       }
       __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -123,11 +127,13 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
       tc_fence_after();
       if (lane == 0) {
         const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const unsigned b_addr = a_addr + r_bytes;
-        for (int k = 0; k < p.kmma; ++k) {
-          const unsigned long long ad = make_mn_desc(a_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
-          const unsigned long long bd = make_mn_desc(b_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
-          tc_mma<KIND>(tmem_base, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+        for (int u = 0; u < nt; ++u) {
+          const unsigned b_addr = a_addr + r_bytes + u * p.n_boxes * p.box_bytes;
+          for (int k = 0; k < p.kmma; ++k) {
+            const unsigned long long ad = make_mn_desc(a_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
+            const unsigned long long bd = make_mn_desc(b_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
+            tc_mma<KIND>(tmem_base + (unsigned)(u * p.bn), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+          }
         }
         tc_commit(&empty_bar[s]);
         if (c == cend - 1) tc_commit(&tfull_bar);
@@ -141,15 +147,17 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
     const int m = m0 + q * 32 + lane;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
-    float* o = out + (p.per_img ? (long long)img_fixed * p.out_img_stride : 0) + (tap_off ? tap_off[t] : 0);
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
-      float v[32];
-      tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
-      if (m < p.m_valid) {
+    for (int u = 0; u < nt; ++u) {
+      float* o = out + (p.per_img ? (long long)img_fixed * p.out_img_stride : 0) + (tap_off ? tap_off[t0 + u] : 0);
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        float v[32];
+        tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(u * p.bn + c0), v);
+        if (m < p.m_valid) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int n = n0 + c0 + e;
-          if (n < p.n_valid && !(p.upper_only && n < m)) atomicAdd(o + (long long)m * p.s_m + (long long)n * p.s_n, v[e] * p.scale);
+          for (int e = 0; e < 32; ++e) {
+            const int n = n0 + c0 + e;
+            if (n < p.n_valid && !(p.upper_only && n < m)) atomicAdd(o + (long long)m * p.s_m + (long long)n * p.s_n, v[e] * p.scale);
+          }
         }
       }
     }
@@ -228,7 +236,18 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   p.chunks_total = (long long)p.tiles_i * p.tiles_j * (p.per_img ? 1 : p.n_img);
   p.out_img_stride = out_img_stride; p.s_m = s_m; p.s_n = s_n; p.scale = scale; p.upper_only = upper_only;
   p.box_bytes = p.kp * 128;
-  p.stage_bytes = (p.m_boxes + p.n_boxes) * p.box_bytes;
+  // tap groups: one CTA accumulates `tg` taps (tg*bn TMEM columns) from ONE load of the rows operand per stage
+  {
+    const char* env = getenv("AST_WGRAD_TG");
+    int tg_max = 512 / p.bn;
+    if (env) tg_max = atoi(env) < tg_max ? atoi(env) : tg_max;
+    if (tg_max < 1) tg_max = 1;
+    if (tg_max > ntaps) tg_max = ntaps;
+    while (tg_max > 1 && 2 * (p.m_boxes + tg_max * p.n_boxes) * p.box_bytes > 200 * 1024) --tg_max;
+    p.ngroups = (ntaps + tg_max - 1) / tg_max;
+    p.tg = (ntaps + p.ngroups - 1) / p.ngroups;       // balance the groups
+  }
+  p.stage_bytes = (p.m_boxes + p.tg * p.n_boxes) * p.box_bytes;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
   AST_CHECK_ARG(p.stages >= 2, "contract_tc: tile does not fit shared memory");
@@ -238,7 +257,7 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   p.sbo = esz == 4 ? 512u : 1024u;
   const unsigned fmt = rows->dtype == AST_F32 ? 2u : 1u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
-  const long long fixed = (long long)ntaps * p.m_blocks * p.n_blocks * (p.per_img ? p.n_img : 1);
+  const long long fixed = (long long)p.ngroups * p.m_blocks * p.n_blocks * (p.per_img ? p.n_img : 1);
   // one CTA per SM (200 KB of smem each): size the split-K so the whole grid is a single wave without a tail
   long long ks = num_sms() / fixed;
   if (ks < 1) ks = 1;
@@ -250,7 +269,7 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   if (int e = encode_operand(encode, &tm_r, rows, p.cb, p.tw, p.th, r_s)) return e;
   if (int e = encode_operand(encode, &tm_c, cols, p.cb, p.tw, p.th, c_s)) return e;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  dim3 grid((unsigned)(p.ksplit * (p.per_img ? p.n_img : 1)), ntaps, p.m_blocks * p.n_blocks);
+  dim3 grid((unsigned)(p.ksplit * (p.per_img ? p.n_img : 1)), p.ngroups, p.m_blocks * p.n_blocks);
   cudaError_t e;
   if (rows->dtype == AST_BF16) {
     e = cudaFuncSetAttribute(contract_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -41,11 +41,13 @@ row_im2col_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int
 
 // One thread per output pixel: gathers the kw*C source values (coalesced along x: consecutive threads read
 // consecutive columns of each source plane) and writes the whole OUTC-channel row with 16-byte stores.
-template <int OUTC>
+// KW, C > 0: compile-time tap / channel counts (fully unrolled, every v[] index is static); 0 = runtime values.
+template <int OUTC, int KW, int CC>
 __global__ void __launch_bounds__(256)
-row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int sign, int px, int py, int reflect,
+row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw_rt, int sign, int px, int py, int reflect,
                       int round_tf32) {
-  const int C = src.c;
+  const int C = CC > 0 ? CC : src.c;
+  const int kw = KW > 0 ? KW : kw_rt;
   const long long total = (long long)out.n * out.h * out.w;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
     const int x = (int)(idx % out.w);
@@ -60,18 +62,35 @@ row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw,
     if (reflect) sy = reflect_idx(sy, src.h);
     else oky = sy >= 0 && sy < src.h;
     if (oky) {
-      int ch = 0;
-      for (int d = 0; d < kw; ++d) {
-        int sx = x + sign * d - px;
-        bool ok = true;
-        if (reflect) sx = reflect_idx(sx, src.w);
-        else ok = sx >= 0 && sx < src.w;
-        for (int c = 0; c < C; ++c, ++ch) {
-          float t = 0.f;
-          if (ok) { t = ld_elem(src, img_off(src, n, sy, sx, c)); if (shift) t += shift[c]; }
-          if (round_tf32) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t)); t = __uint_as_float(u); }
+      if (KW > 0 && CC > 0) {
 #pragma unroll
-          for (int e = 0; e < OUTC; ++e) if (e == ch) v[e] = t;   // keeps v[] in registers
+        for (int d = 0; d < (KW > 0 ? KW : 1); ++d) {
+          int sx = x + sign * d - px;
+          bool ok = true;
+          if (reflect) sx = reflect_idx(sx, src.w);
+          else ok = sx >= 0 && sx < src.w;
+#pragma unroll
+          for (int c = 0; c < (CC > 0 ? CC : 1); ++c) {
+            float t = 0.f;
+            if (ok) { t = ld_elem(src, img_off(src, n, sy, sx, c)); if (shift) t += shift[c]; }
+            if (round_tf32) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t)); t = __uint_as_float(u); }
+            if (d * CC + c < OUTC) v[d * CC + c] = t;
+          }
+        }
+      } else {
+        int ch = 0;
+        for (int d = 0; d < kw; ++d) {
+          int sx = x + sign * d - px;
+          bool ok = true;
+          if (reflect) sx = reflect_idx(sx, src.w);
+          else ok = sx >= 0 && sx < src.w;
+          for (int c = 0; c < C; ++c, ++ch) {
+            float t = 0.f;
+            if (ok) { t = ld_elem(src, img_off(src, n, sy, sx, c)); if (shift) t += shift[c]; }
+            if (round_tf32) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t)); t = __uint_as_float(u); }
+#pragma unroll
+            for (int e = 0; e < OUTC; ++e) if (e == ch) v[e] = t;   // keeps v[] in registers
+          }
         }
       }
     }
@@ -162,10 +181,12 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
     const long long pixels = total / out->c;
     long long pb = (pixels + 255) / 256;
     if (pb > (long long)num_sms() * 32) pb = (long long)num_sms() * 32;
-    if (out->c == 32)
-      row_im2col_pix_kernel<32><<<(int)pb, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32);
-    else
-      row_im2col_pix_kernel<16><<<(int)pb, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32);
+#define RIK(O, K, C) row_im2col_pix_kernel<O, K, C><<<(int)pb, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32)
+    if (out->c == 32 && kw == 9 && src->c == 3) RIK(32, 9, 3);
+    else if (out->c == 16 && kw == 3 && src->c == 3) RIK(16, 3, 3);
+    else if (out->c == 32) RIK(32, 0, 0);
+    else RIK(16, 0, 0);
+#undef RIK
     count_launch();
     AST_CUDA_LAUNCH_CHECK();
     return 0;
