@@ -14,6 +14,7 @@ namespace ast {
 
 constexpr int WS_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
 constexpr int WS_MAX_PBUF = 4;
+constexpr int WS_MAX_WBUF = 8;
 constexpr int WS_TH = 16, WS_TW = 8;
 
 struct WsParams {
@@ -23,6 +24,7 @@ struct WsParams {
   int so, oy0, ox0;
   int dy_min, dx_min, ph, pw;
   int patch_bytes, patch_tx, n_pbuf, w_tile_bytes, w_total_bytes;
+  int w_resident, n_wbuf, n_tiles_n;   // weights resident in smem, or streamed through an n_wbuf-deep ring
   unsigned idesc, layout_type, sbo, base_mode;
   long long total_tiles;
   short tdy[AST_MAX_TAPS];
@@ -53,6 +55,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                const float* __restrict__ bias, const Img add, const Img mask, const Img out) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
+  __shared__ __align__(8) unsigned long long wfull[WS_MAX_WBUF], wempty[WS_MAX_WBUF];
   __shared__ unsigned tmem_slot;
   __shared__ unsigned s_tapoff[AST_MAX_TAPS];    // per-tap A start offset inside the patch, in 16-byte units
 
@@ -67,6 +70,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     for (int s = 0; s < p.n_pbuf; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
     mbar_init(&wbar, 1);
+    for (int s = 0; s < p.n_wbuf; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -85,16 +89,17 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {       // the whole filter, once
+    if (lane == 0 && p.w_resident) {       // the whole filter, once
       mbar_expect_tx(&wbar, (unsigned)p.w_total_bytes);
       for (int t = 0; t < p.ntaps; ++t)
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d(smem_w + (size_t)(t * p.kchunks + kc) * p.w_tile_bytes, &tm_w, &wbar, kc * p.kc, t * p.cout);
     }
     __syncwarp();
-    int s = 0; unsigned ph = 0;
+    int s = 0; unsigned ph = 0; int ws = 0; unsigned wph = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
+      const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
       const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
@@ -107,13 +112,24 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
         __syncwarp();
         if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
+        if (!p.w_resident) {           // stream this chunk's weights tap by tap, in the order the MMA warp consumes them
+          for (int t = 0; t < p.ntaps; ++t) {
+            mbar_wait(&wempty[ws], wph ^ 1);
+            if (lane == 0) {
+              mbar_expect_tx(&wfull[ws], (unsigned)p.w_tile_bytes);
+              tma_load_2d(smem_w + (size_t)ws * p.w_tile_bytes, &tm_w, &wfull[ws], kc * p.kc, t * p.cout + nt * p.bn);
+            }
+            __syncwarp();
+            if (++ws == p.n_wbuf) { ws = 0; wph ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
+    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0; int ws = 0; unsigned wph = 0;
     const int kmma = p.rowb / 32;
-    mbar_wait(&wbar, 0);
+    if (p.w_resident) mbar_wait(&wbar, 0);
     tc_fence_after();
     const unsigned w_addr0 = smem_u32(smem_w);
     const unsigned hi_a = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
@@ -131,20 +147,49 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
           const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
           unsigned acc = kc > 0 ? 1u : 0u;
+          if (p.w_resident) {
 #pragma unroll 1
-          for (int t = 0; t < p.ntaps; ++t) {
-            const unsigned a_lo = p_lo + s_tapoff[t];
-            const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
-            tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
-            tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
-            if (kmma == 4) {
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
+            for (int t = 0; t < p.ntaps; ++t) {
+              const unsigned a_lo = p_lo + s_tapoff[t];
+              const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
+              if (kmma == 4) {
+                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
+                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
+              }
+              acc = 1u;
             }
-            acc = 1u;
+            tc_commit(&pempty[s]);
+            if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
           }
-          tc_commit(&pempty[s]);
-          if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
+        }
+        if (!p.w_resident) {
+          // streamed weights: one ring slot per tap; the whole warp waits, lane 0 issues
+          const unsigned p_lo = ((smem_u32(smem_p + (size_t)s * p.patch_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
+          const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
+          for (int t = 0; t < p.ntaps; ++t) {
+            mbar_wait(&wfull[ws], wph);
+            tc_fence_after();
+            if (lane == 0) {
+              const unsigned a_lo = p_lo + s_tapoff[t];
+              const unsigned b_lo = w_lo + (unsigned)ws * w16;
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, (kc > 0 || t > 0) ? 1u : 0u);
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
+              if (kmma == 4) {
+                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
+                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
+              }
+              tc_commit(&wempty[ws]);
+              if (t == p.ntaps - 1) {
+                tc_commit(&pempty[s]);
+                if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
+              }
+            }
+            __syncwarp();
+            if (++ws == p.n_wbuf) { ws = 0; wph ^= 1; }
+          }
         }
         __syncwarp();
         if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
@@ -161,6 +206,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     int as = 0; unsigned aph = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
+      const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
       const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
@@ -175,10 +221,11 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
         float v[32];
         tc_ld32(taddr0 + c0, v);
+        const int co = nt * p.bn + c0;
         if (p.thin) {
-          if (valid) tc_epilogue32(v, c0, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
+          if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
-          tc_epilogue32_coalesced(v, c0, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
+          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
         }
       }
       tc_fence_before();
@@ -200,9 +247,10 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
                    cudaStream_t stream) {
   const char* env = getenv("AST_CONV_WS");
-  const int mode = env ? atoi(env) : 1;            // 0 = off (A/B against conv_tc), 1 = on, 9 = experiment: base_offset
+  const int mode = env ? atoi(env) : 1;   // 0 = off (A/B against conv_tc), 1 = resident weights only (default),
+                                          // 3 = also stream weights for big layers, 9 = base_offset experiment
   if (mode == 0) return 0;
-  if (g->si != 1 || g->w_img_stride != 0 || cpad > 256) return 0;
+  if (g->si != 1 || g->w_img_stride != 0) return 0;
   const int esz = in->dtype == AST_F32 ? 4 : 2;
   int dy_min = 1 << 30, dy_max = -(1 << 30), dx_min = 1 << 30, dx_max = -(1 << 30);
   for (int t = 0; t < g->ntaps; ++t) {
@@ -215,17 +263,33 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
   p.kc = p.rowb / esz;
   p.kchunks = in->c / p.kc;
-  p.bn = cpad;
+  p.bn = cpad % 256 == 0 ? 256 : (cpad <= 256 ? cpad : (cpad % 128 == 0 ? 128 : (cpad % 64 == 0 ? 64 : 32)));
+  p.n_tiles_n = cpad / p.bn;
   p.w_tile_bytes = p.bn * p.rowb;
   p.w_total_bytes = g->ntaps * p.kchunks * p.w_tile_bytes;
   p.pw = (dx_max == dx_min) ? WS_TW : 16;
   p.ph = WS_TH + (dy_max - dy_min);
   p.patch_tx = p.pw * p.ph * p.rowb;
   p.patch_bytes = (p.patch_tx + 1023) & ~1023;
-  const int budget = 232448 - 1024 - 1024 - 8192 - ((p.w_total_bytes + 1023) & ~1023);   // align slack, static, store stage
-  if (budget < 2 * p.patch_bytes) return 0;
-  p.n_pbuf = budget / p.patch_bytes;
-  if (p.n_pbuf > WS_MAX_PBUF) p.n_pbuf = WS_MAX_PBUF;
+  const int avail = 232448 - 1024 - 1024 - 8192;        // align slack, static smem, store-transpose stage
+  int budget = avail - ((p.w_total_bytes + 1023) & ~1023);
+  p.w_resident = (p.n_tiles_n == 1 && budget >= 2 * p.patch_bytes) ? 1 : 0;
+  if (p.w_resident) {
+    p.n_pbuf = budget / p.patch_bytes;
+    if (p.n_pbuf > WS_MAX_PBUF) p.n_pbuf = WS_MAX_PBUF;
+    p.n_wbuf = 0;
+  } else {
+    // streamed weights: 2-3 patches + a ring of per-tap weight tiles; only worth it for multi-tap filters
+    // Measured on B200 (profiles/r01_summary.md): NOT faster than conv_tc's per-tap streaming for the 128..512-channel
+    // layers (they are bound by shared-memory operand bandwidth of cta_group::1 MMAs, not by L2), so it is opt-in.
+    if (mode != 3 || g->ntaps < 4 || p.rowb != 128) return 0;
+    p.n_pbuf = 2;
+    p.n_wbuf = (avail - p.n_pbuf * p.patch_bytes) / p.w_tile_bytes;
+    if (p.n_wbuf > WS_MAX_WBUF) p.n_wbuf = WS_MAX_WBUF;
+    if (p.n_wbuf < 3) return 0;
+    if (avail - p.n_pbuf * p.patch_bytes - p.n_wbuf * p.w_tile_bytes >= p.patch_bytes) p.n_pbuf = 3;
+    p.w_total_bytes = p.n_wbuf * p.w_tile_bytes;       // ring size (smem layout below uses this)
+  }
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_ws: cuTensorMapEncodeTiled entry point not available");
 
@@ -235,7 +299,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   for (int t = 0; t < g->ntaps; ++t) { p.tdy[t] = g->dy[t] - dy_min; p.tdx[t] = g->dx[t] - dx_min; }
   p.tiles_i = (p.mi + WS_TH - 1) / WS_TH;
   p.tiles_j = (p.mj + WS_TW - 1) / WS_TW;
-  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j;
+  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j * p.n_tiles_n;
   p.layout_type = p.rowb == 128 ? 2u : 4u;
   p.sbo = (unsigned)(p.pw * p.rowb);
   // Measured on B200: the tensor core applies the 128B/64B swizzle XOR on ABSOLUTE shared-memory address bits, so a
