@@ -28,7 +28,7 @@ class GatherGeom(ctypes.Structure):
                 ("oy0", ctypes.c_int32), ("ox0", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("flags", ctypes.c_int32),
                 ("dy", ctypes.c_int16 * AST_MAX_TAPS), ("dx", ctypes.c_int16 * AST_MAX_TAPS),
-                ("w_img_stride", ctypes.c_int64)]
+                ("w_img_stride", ctypes.c_int64), ("stats", ctypes.c_void_p)]
 
 
 _lib = None
@@ -46,6 +46,7 @@ _SIGNATURES = {
                        ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_unfold_rows": [_P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_stats": [_P(Image), _vp, _vp, ctypes.c_float, _vp, _vp],
+    "ast_instnorm_finalize": [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, _vp, _vp, _vp],
     "ast_instnorm_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_bwd_stats": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
                                _vp, _vp, _vp],

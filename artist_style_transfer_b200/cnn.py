@@ -42,6 +42,11 @@ def _thin_wgrad_mode():
     return os.environ.get("AST_THIN_WGRAD", "taps")
 
 
+def _fused_stats():
+    import os
+    return os.environ.get("AST_FUSED_STATS", "1") == "1"
+
+
 def _grad_fp32():
     import os
     return os.environ.get("AST_GRAD_FP32", "0") == "1"
@@ -194,8 +199,14 @@ class _StageFunction(torch.autograd.Function):
             else:
                 raw = torch.empty((n, ho, wo, st.cout), dtype=adt, device=dev)
                 # conv bias is dead under InstanceNorm and is not added
-                ops.conv_gather(xin, wp, launches, raw, tensor=mode == "fast" and ops.tc_eligible(xin, st.cout))
-                mean, rstd = ops.instnorm_stats(raw)
+                use_tc = mode == "fast" and ops.tc_eligible(xin, st.cout)
+                if use_tc and _fused_stats():      # sum x / sum x^2 accumulated by the conv epilogue: no stats pass
+                    sums = torch.zeros(n * st.cout * 2, dtype=torch.float32, device=dev)
+                    ops.conv_gather(xin, wp, launches, raw, tensor=True, stats=sums)
+                    mean, rstd = ops.instnorm_finalize(sums, n, st.cout, ho * wo)
+                else:
+                    ops.conv_gather(xin, wp, launches, raw, tensor=use_tc)
+                    mean, rstd = ops.instnorm_stats(raw)
                 pn = 0 if last else stages[i + 1].in_pad
                 post = torch.empty((n, ho + 2 * pn, wo + 2 * pn, st.cout), dtype=adt, device=dev)
                 res = None

@@ -34,7 +34,8 @@ struct TcParams {
 template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const TcParams p,
-               const float* __restrict__ bias, const Img add, const Img mask, const Img out) {
+               const float* __restrict__ bias, const Img add, const Img mask, const Img out,
+               float* __restrict__ stats) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ unsigned tmem_slot;
@@ -147,6 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (p.thin) {
           if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
+          if (stats) tc_epi_stats(v, valid, stats + ((long long)img * p.cout_valid + co) * 2, lane);
           tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
         }
       }
@@ -179,6 +181,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   const int cpad = (out->c + 31) / 32 * 32;        // weight rows per tap the caller packed (zero rows beyond out->c)
   const bool thin = cpad != out->c || out->sc != 1;
   AST_CHECK_ARG(in->sc == 1, "conv_tc: NHWC input required");
+  AST_CHECK_ARG(!g->stats || !thin, "conv_tc: fused statistics need a full NHWC output (cout %% 32 == 0)");
   AST_CHECK_ARG((in->c * esz) % 64 == 0, "conv_tc: cin*elemsize must be a multiple of 64 bytes (cin=%d)", in->c);
   AST_CHECK_ARG(g->si >= 1 && g->si <= 2, "conv_tc: input stride must be 1 or 2");
   AST_CHECK_ARG(((uintptr_t)in->ptr & 15) == 0 && ((uintptr_t)weights & 15) == 0 && (thin || ((uintptr_t)out->ptr & 15) == 0),
@@ -251,10 +254,10 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   cudaError_t e;
   if (in->dtype == AST_BF16) {
     e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<0><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+    if (e == cudaSuccess) conv_tc_kernel<0><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+    if (e == cudaSuccess) conv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   }
   if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();

@@ -52,7 +52,8 @@ __device__ __forceinline__ unsigned long long pack_desc(unsigned lo, unsigned hi
 template <int KIND>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
-               const float* __restrict__ bias, const Img add, const Img mask, const Img out) {
+               const float* __restrict__ bias, const Img add, const Img mask, const Img out,
+               float* __restrict__ stats) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ __align__(8) unsigned long long wfull[WS_MAX_WBUF], wempty[WS_MAX_WBUF];
@@ -225,6 +226,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (p.thin) {
           if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
+          if (stats) tc_epi_stats(v, valid, stats + ((long long)img * p.cout_valid + co) * 2, lane);
           tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
         }
       }
@@ -335,10 +337,10 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   cudaError_t e;
   if (in->dtype == AST_BF16) {
     e = cudaFuncSetAttribute(conv_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_ws_kernel<0><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+    if (e == cudaSuccess) conv_ws_kernel<0><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   } else {
     e = cudaFuncSetAttribute(conv_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_ws_kernel<1><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out));
+    if (e == cudaSuccess) conv_ws_kernel<1><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   }
   if (e != cudaSuccess) { set_error("conv_ws: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();

@@ -253,6 +253,16 @@ in_bwd_apply_kernel(Img x, const float* __restrict__ mean, const float* __restri
   }
 }
 
+__global__ void in_finalize_kernel(const float* __restrict__ sums, int total, float inv_hw, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = sums[2 * i] * inv_hw;
+  const float var = fmaxf(sums[2 * i + 1] * inv_hw - m * m, 0.f);
+  mean[i] = m;
+  rstd[i] = rsqrtf(var + eps);
+}
+
 static int stats_blocks(int n, int hw, int slots) {
   int nblk = (4 * num_sms() + n - 1) / n;
   const int maxb = (hw + slots * 4 - 1) / (slots * 4);
@@ -302,6 +312,17 @@ extern "C" int ast_instnorm_stats(const ast_image* x, float* mean, float* rstd, 
   else in_stats_partial_kernel<__nv_bfloat16><<<grid, NT, smem, s>>>(to_img(x), (float*)workspace, nblk, chunk);
   in_stats_final_kernel<<<x->n, 128, 0, s>>>((const float*)workspace, nblk, x->c, hw, eps, mean, rstd);
   count_launch(2);
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ast_instnorm_finalize(const float* sums, int32_t n, int32_t c, int32_t hw, float eps, float* mean,
+                                     float* rstd, void* stream) {
+  AST_CHECK_ARG(sums && mean && rstd && hw > 0, "ast_instnorm_finalize: bad argument");
+  const int total = n * c;
+  if (total == 0) return 0;
+  in_finalize_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, total, 1.f / (float)hw, eps, mean, rstd);
+  count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -171,6 +171,28 @@ __device__ __forceinline__ void tc_epilogue32(float* v, int co, int img, int oy,
 // (tc_epi_row_offsets) and reused for every 32-channel chunk.  All 32 lanes must call both functions.
 struct EpiRows { long long off[8]; };
 
+// InstanceNorm statistics fused into the conv epilogue: each lane holds 32 channels of one pixel row; a reduce-scatter
+// butterfly (16+8+4+2+1 shuffles per quantity) leaves lane L with the sum over the warp's 32 rows of channel co+L,
+// which is added to stats[(img*C + co+L)*2 + {0,1}] with one fire-and-forget atomic each.
+__device__ __forceinline__ void tc_epi_stats(const float* v, bool valid, float* __restrict__ stats_row, int lane) {
+  float a[32], b[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) { a[e] = valid ? v[e] : 0.f; b[e] = a[e] * a[e]; }
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = lane & half;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float sa = up ? a[j] : a[j + half], ka = up ? a[j + half] : a[j];
+      const float sb = up ? b[j] : b[j + half], kb = up ? b[j + half] : b[j];
+      a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, half);
+      b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, half);
+    }
+  }
+  atomicAdd(stats_row + 2 * lane, a[0]);
+  atomicAdd(stats_row + 2 * lane + 1, b[0]);
+}
+
 __device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

@@ -55,7 +55,7 @@ def profile_end():
     return out
 
 
-def _geom(launch, flags=0, w_img_stride=0):
+def _geom(launch, flags=0, w_img_stride=0, stats=None):
     g = GatherGeom()
     g.mi, g.mj, g.si, g.so, g.oy0, g.ox0 = launch.mi, launch.mj, launch.si, launch.so, launch.oy0, launch.ox0
     g.ntaps = len(launch.taps)
@@ -64,6 +64,7 @@ def _geom(launch, flags=0, w_img_stride=0):
         g.dy[t] = dy
         g.dx[t] = dx
     g.w_img_stride = w_img_stride
+    g.stats = None if stats is None else stats.data_ptr()
     return g
 
 
@@ -116,6 +117,16 @@ def unfold_rows(src, out, kh, sign, py=0):
         return out
 
 
+def instnorm_finalize(sums, n, c, hw, eps=1e-5):
+    """(sum x, sum x^2) pairs accumulated by a conv epilogue -> (mean, rstd)."""
+    with _timed("instnorm"):
+        mean = torch.empty(n * c, dtype=torch.float32, device=sums.device)
+        rstd = torch.empty_like(mean)
+        check(_lib.load().ast_instnorm_finalize(ptr(sums), n, c, hw, eps, ptr(mean), ptr(rstd), stream_ptr()),
+              "ast_instnorm_finalize")
+        return mean, rstd
+
+
 def tc_eligible(x, cout):
     """Shapes the tcgen05 kernel accepts (conv_tc.cu): cin*elemsize % 64 == 0, cout % 32 == 0, NHWC."""
     return (_lib.has_tc_conv() and x.stride(3) == 1 and (x.shape[3] * x.element_size()) % 64 == 0
@@ -123,7 +134,7 @@ def tc_eligible(x, cout):
 
 
 def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
-                reflect=False, tensor=False, w_img_stride=0, round_tf32=False):
+                reflect=False, tensor=False, w_img_stride=0, round_tf32=False, stats=None):
     """Run every launch of an op. x/out/add/mask: (N,H,W,C)-ordered tensors; wpacked: [taps][cout][cin]."""
     lib = _lib.load()
     flags = ((CONV_RELU if relu else 0) | (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
@@ -132,7 +143,7 @@ def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=N
     cout, cin = wpacked.shape[-2], wpacked.shape[-1]
     esz = wpacked.element_size()
     for l in launches:
-        g = _geom(l, flags, w_img_stride)
+        g = _geom(l, flags, w_img_stride, stats)
         wp = _lib.ctypes.c_void_p(wpacked.data_ptr() + l.woff * cout * cin * esz)
         check(lib.ast_conv_gather(ref(xi), wp, ptr(bias), ptr(in_shift), ref(ai), ref(mi), ref(oi), ref(g),
                                   stream_ptr()), "ast_conv_gather")
@@ -260,13 +271,14 @@ def pack_weights(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
 
 
 def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False, reflect=False,
-                tensor=False, w_img_stride=0, round_tf32=False):
+                tensor=False, w_img_stride=0, round_tf32=False, stats=None):
     label = "conv_gather_tc" if tensor else "conv_gather_simt"
     if PROFILE_DETAIL and _prof is not None:
         label += f"|{tuple(x.shape)}->{tuple(out.shape)} taps={sum(len(l.taps) for l in launches)} {str(x.dtype)[6:]}"
     with _timed(label):
         return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu,
-                                 reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32)
+                                 reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32,
+                                 stats=stats)
 
 
 def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False, tensor=False):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 1
+#define AST_ABI_VERSION 2
 
 typedef enum { AST_F32 = 0, AST_BF16 = 1, AST_TF32 = 2 /* fp32 storage rounded to TF32; pack_weights only */ } ast_dtype;
 
@@ -58,6 +58,9 @@ typedef struct {
   int16_t dy[AST_MAX_TAPS];
   int16_t dx[AST_MAX_TAPS];
   int64_t w_img_stride;    /* elements between per-image weight sets, 0 = shared weights */
+  float*  stats;           /* optional fp32 [n][cout][2] (sum x, sum x^2 of the fp32 results, BEFORE bias/activation),
+                              accumulated by the tensor-core epilogue: InstanceNorm statistics fused into the producing
+                              conv (cnn.py:63,68).  Zeroed by the caller; NULL = off; tensor-core launches only. */
 } ast_gather_geom;
 
 #define AST_CONV_RELU     1   /* epilogue max(v,0)                       (nn.ReLU, train_cnn.py VGG idx 1,3,...)   */
@@ -106,6 +109,9 @@ int ast_unfold_rows(const ast_image* src, const ast_image* out, int32_t kh, int3
  * stats: mean[n*c], rstd[n*c] (fp32).  workspace: ast_instnorm_workspace_bytes(). */
 int64_t ast_instnorm_workspace_bytes(int32_t n, int32_t c);
 int ast_instnorm_stats(const ast_image* x, float* mean, float* rstd, float eps, void* workspace, void* stream);
+/* mean/rstd from the (sum x, sum x^2) pairs a conv epilogue accumulated (ast_gather_geom.stats): [n*c][2] -> [n*c]. */
+int ast_instnorm_finalize(const float* sums, int32_t n, int32_t c, int32_t hw, float eps, float* mean, float* rstd,
+                          void* stream);
 /* y = gamma*(x-mean)*rstd + beta (+ residual) (ReLU if relu), written to the interior of `out`, which is an
  * (h+2*pad) x (w+2*pad) image whose border is filled by mirroring (the next layer's nn.ReflectionPad2d). */
 int ast_instnorm_apply(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
