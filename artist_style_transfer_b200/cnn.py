@@ -315,6 +315,14 @@ class _StageFunction(torch.autograd.Function):
                 g_cw = (tmp.view(st.k, 32, st.cin)[:, :st.k * st.cout, :].reshape(st.k, st.k, st.cout, st.cin)
                         .permute(2, 3, 0, 1).contiguous())
                 del df
+            elif wtc:
+                # tap-major scratch tmp[tap][co][ci]: ci contiguous, so the contraction epilogue reduces with 16-byte
+                # vector atomics; the permute to the parameter layout is one small copy
+                tmp = torch.zeros((k2, st.cout, st.cin), dtype=torch.float32, device=xin.device)
+                ops.wgrad_gather(xin, d_raw, launches, tmp, st.cin, 1, st.k * st.cout * st.cin, st.cout * st.cin,
+                                 tensor=True)
+                tmp = tmp.view(st.k, st.k, st.cout, st.cin)
+                g_cw = (tmp.permute(2, 3, 0, 1) if st.kind == "conv" else tmp.permute(3, 2, 0, 1)).contiguous()
             else:
                 g_cw = torch.zeros_like(cw, dtype=torch.float32)
                 if st.kind == "conv":

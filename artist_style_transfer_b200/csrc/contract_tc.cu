@@ -147,16 +147,40 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
     const int m = m0 + q * 32 + lane;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
-    for (int u = 0; u < nt; ++u) {
+    // the split-K CTAs of one output all finish together: rotate each CTA's walk over (tap, column block) so that they
+    // do not all hit the same addresses at the same moment
+    const int nblk = p.bn / 32;
+    const int rot = (int)(blockIdx.x % (unsigned)(nt * nblk));
+    for (int it = 0; it < nt * nblk; ++it) {
+      const int idx = (it + rot) % (nt * nblk);
+      const int u = idx / nblk;
       float* o = out + (p.per_img ? (long long)img_fixed * p.out_img_stride : 0) + (tap_off ? tap_off[t0 + u] : 0);
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      const bool vec_ok = p.s_n == 1 && (p.s_m & 3) == 0 && (((uintptr_t)o) & 15) == 0;
+      {
+        const int c0 = (idx - u * nblk) * 32;
         float v[32];
         tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(u * p.bn + c0), v);
         if (m < p.m_valid) {
+          float* orow = o + (long long)m * p.s_m;
+          if (vec_ok) {          // 16-byte vector reductions: 4x fewer L2 atomic operations than scalar atomicAdd
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int n = n0 + c0 + e;
-            if (n < p.n_valid && !(p.upper_only && n < m)) atomicAdd(o + (long long)m * p.s_m + (long long)n * p.s_n, v[e] * p.scale);
+            for (int e = 0; e < 32; e += 4) {
+              const int n = n0 + c0 + e;
+              if (n + 3 < p.n_valid && !(p.upper_only && n < m)) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + n), "f"(v[e] * p.scale),
+                             "f"(v[e + 1] * p.scale), "f"(v[e + 2] * p.scale), "f"(v[e + 3] * p.scale) : "memory");
+              } else {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                  if (n + q4 < p.n_valid && !(p.upper_only && n + q4 < m)) atomicAdd(orow + n + q4, v[e + q4] * p.scale);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int n = n0 + c0 + e;
+              if (n < p.n_valid && !(p.upper_only && n < m)) atomicAdd(orow + (long long)n * p.s_n, v[e] * p.scale);
+            }
           }
         }
       }
@@ -202,6 +226,185 @@ static int check_operand(const char* who, const ast_image* im) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Thin variant (both operands have <= 32 bf16 channels: the 9x9 first/last layers after the row unfold).  The generic
+// kernel pads such operands to 64-channel boxes and to M = 128, i.e. 8x wasted MMA work and 2.6x wasted smem fill.
+// Here a box is 64 pixels x 32 channels (64-byte rows, SWIZZLE_64B) and the M = 128 rows of one MMA are FOUR TAPS of the
+// shifted operand (four boxes, LBO apart), the N = 32 columns the fixed operand:
+//     D_g[(t - 4g)*32 + cc][rc] += sum_p C[p + tap_t][cc] * R[p][rc]            g = t / 4
+// One CTA handles all taps (ceil(ntaps/4) accumulators of 32 TMEM columns); split-K over pixel chunks, fp32 atomics.
+struct CtThinParams {
+  int mi, mj, tw, th, tiles_i, tiles_j, n_img;
+  int r_s, r_oy, r_ox, c_s;
+  int ntaps, ngrp, r_valid, c_valid, chunks_per_cta, stages, stage_bytes;
+  long long chunks_total, s_m, s_n;
+  float scale;
+  unsigned idesc;
+  short dy[AST_MAX_TAPS];
+  short dx[AST_MAX_TAPS];
+};
+constexpr int THIN_KP = 64;                    // pixels per stage
+constexpr int THIN_BOX = THIN_KP * 64;         // bytes per box
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c,
+                     const CtThinParams p, float* __restrict__ out, const int* __restrict__ tap_off) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
+  __shared__ unsigned tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cbeg = (long long)blockIdx.x * p.chunks_per_cta;
+  long long cend = cbeg + p.chunks_per_cta;
+  if (cend > p.chunks_total) cend = p.chunks_total;
+  if (cbeg >= cend) return;
+
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const unsigned tmem_cols = p.ngrp * 32 <= 32 ? 32 : p.ngrp * 32 <= 64 ? 64 : p.ngrp * 32 <= 128 ? 128 : p.ngrp * 32 <= 256 ? 256 : 512;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_r) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+  const int padded_taps = p.ngrp * 4;          // box slots of the shifted operand per stage (slots >= ntaps stay unwritten)
+
+  if (warp == 0) {
+    int s = 0; unsigned ph = 0;
+    const int per_img_chunks = p.tiles_i * p.tiles_j;
+    if (lane == 0) {       // unwritten tap slots feed only ignored accumulator rows, but keep them finite: zero once
+      for (int st = 0; st < p.stages; ++st)
+        for (int t = p.ntaps; t < padded_taps; ++t) {
+          uint4* z = (uint4*)(smem + (size_t)st * p.stage_bytes + (1 + t) * THIN_BOX);
+          for (int k = 0; k < THIN_BOX / 16; ++k) z[k] = make_uint4(0, 0, 0, 0);
+        }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    for (long long c = cbeg; c < cend; ++c) {
+      const int img = (int)(c / per_img_chunks), rem = (int)(c % per_img_chunks);
+      const int ti = rem / p.tiles_j, tj = rem % p.tiles_j;
+      const int i0 = ti * p.th, j0 = tj * p.tw;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (lane == 0) {
+        unsigned char* sr = smem + (size_t)s * p.stage_bytes;
+        mbar_expect_tx(&full_bar[s], (unsigned)((1 + p.ntaps) * THIN_BOX));
+        tma_load_4d(sr, &tm_r, &full_bar[s], 0, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
+        for (int t = 0; t < p.ntaps; ++t)
+          tma_load_4d(sr + (1 + t) * THIN_BOX, &tm_c, &full_bar[s], 0, p.c_s * j0 + p.dx[t], p.c_s * i0 + p.dy[t], img);
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    int s = 0; unsigned ph = 0;
+    bool first = true;
+    for (long long c = cbeg; c < cend; ++c) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const unsigned r_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        for (int g = 0; g < p.ngrp; ++g) {
+          const unsigned c_addr = r_addr + (1 + 4 * g) * THIN_BOX;
+          for (int k = 0; k < THIN_KP / 16; ++k) {           // UMMA_K = 16 pixel rows of 64 bytes
+            // A = four tap boxes (column blocks of 32 channels, LBO = one box apart); B = the fixed operand
+            const unsigned long long ad = make_mn_desc(c_addr + k * 1024, THIN_BOX, 512, 4u);
+            const unsigned long long bd = make_mn_desc(r_addr + k * 1024, THIN_BOX, 512, 4u);
+            tc_mma<0>(tmem_base + (unsigned)(g * 32), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(&empty_bar[s]);
+        if (c == cend - 1) tc_commit(&tfull_bar);
+      }
+      first = false;
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;                   // TMEM lane quarter = tap within the group; lane = channel of the shifted operand
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    for (int g = 0; g < p.ngrp; ++g) {
+      float v[32];
+      tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(g * 32), v);
+      const int t = 4 * g + q;
+      if (t < p.ntaps && lane < p.c_valid) {
+        float* o = out + (tap_off ? tap_off[t] : 0) + (long long)lane * p.s_n;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < p.r_valid) atomicAdd(o + (long long)e * p.s_m, v[e] * p.scale);   // lanes -> consecutive addresses when s_n == 1
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+static int encode_thin_operand(EncodeTiledFn encode, CUtensorMap* tm, const ast_image* im, int tw, int th, int s) {
+  cuuint64_t dims[4] = {(cuuint64_t)im->c, (cuuint64_t)im->w, (cuuint64_t)im->h, (cuuint64_t)im->n};
+  cuuint64_t strides[3] = {(cuuint64_t)im->sw * 2, (cuuint64_t)im->sh * 2, (cuuint64_t)im->sn * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)(tw * s), (cuuint32_t)(th * s), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, im->ptr, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("contract_thin: cuTensorMapEncodeTiled failed: %d", (int)r); return (int)r; }
+  return 0;
+}
+
+// returns 1 when the thin kernel took the job, 0 when not applicable, < 0 / CUDA error codes otherwise
+static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols,
+                         int c_s, const short* dy, const short* dx, int ntaps, int mi, int mj, float* out,
+                         const int* tap_off, long long s_m, long long s_n, float scale, cudaStream_t stream) {
+  static const int enabled = [] { const char* e = getenv("AST_WGRAD_THIN"); return e ? atoi(e) : 1; }();
+  if (!enabled || rows->dtype != AST_BF16 || rows->c > 32 || cols->c > 32 || ntaps < 2 || ntaps > 60) return 0;
+  CtThinParams p;
+  memset(&p, 0, sizeof(p));
+  p.mi = mi; p.mj = mj; p.n_img = rows->n; p.ntaps = ntaps; p.ngrp = (ntaps + 3) / 4;
+  p.r_s = r_s; p.r_oy = r_oy; p.r_ox = r_ox; p.c_s = c_s;
+  for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy ? dy[t] : 0; p.dx[t] = dx ? dx[t] : 0; }
+  p.r_valid = rows->c; p.c_valid = cols->c;
+  pick_tile(mi, mj, THIN_KP, &p.tw, &p.th);
+  p.tiles_i = (mi + p.th - 1) / p.th; p.tiles_j = (mj + p.tw - 1) / p.tw;
+  p.chunks_total = (long long)p.tiles_i * p.tiles_j * p.n_img;
+  p.s_m = s_m; p.s_n = s_n; p.scale = scale;
+  p.stage_bytes = (1 + 4 * p.ngrp) * THIN_BOX;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
+  if (p.stages < 2) return 0;
+  // bf16 A/B (1), both MN-major (bits 15, 16), N = 32, M = 128
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  long long ks = num_sms();
+  if (ks > p.chunks_total) ks = p.chunks_total;
+  p.chunks_per_cta = (int)((p.chunks_total + ks - 1) / ks);
+  const int grid = (int)((p.chunks_total + p.chunks_per_cta - 1) / p.chunks_per_cta);
+  alignas(64) CUtensorMap tm_r, tm_c;
+  if (int e = encode_thin_operand(encode, &tm_r, rows, p.tw, p.th, r_s)) return e;
+  if (int e = encode_thin_operand(encode, &tm_c, cols, p.tw, p.th, c_s)) return e;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(contract_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("contract_thin: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+  contract_thin_kernel<<<grid, CT_THREADS, smem, stream>>>(tm_r, tm_c, p, out, tap_off);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
 // rows = operand that provides the M (<=128 per block) dimension, cols = the N dimension.
 int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols, int c_s, const short* dy,
                 const short* dx, int ntaps, int mi, int mj, float* out, const int* tap_off, long long s_m,
@@ -215,6 +418,11 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "contract_tc: cuTensorMapEncodeTiled entry point not available");
   const int esz = rows->dtype == AST_F32 ? 4 : 2;
+  if (!upper_only && out_img_stride == 0) {
+    const int tr = contract_thin(encode, rows, r_s, r_oy, r_ox, cols, c_s, dy, dx, ntaps, mi, mj, out, tap_off, s_m, s_n,
+                                 scale, stream);
+    if (tr != 0) return tr == 1 ? 0 : tr;
+  }
 
   CtParams p;
   memset(&p, 0, sizeof(p));

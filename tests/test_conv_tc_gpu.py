@@ -141,6 +141,12 @@ WG_CASES = [
     (torch.bfloat16, 32, 64, 3, 2, 1, 34, 34),
     (torch.bfloat16, 128, 128, 1, 1, 2, 16, 16),
     (torch.bfloat16, 128, 128, 3, 1, 1, 13, 11),
+    # <= 32 channels on both sides: the thin kernel (four taps stacked in the M rows, 64-byte swizzle)
+    (torch.bfloat16, 32, 32, 3, 1, 2, 18, 18),
+    (torch.bfloat16, 32, 32, 5, 1, 2, 21, 19),
+    (torch.bfloat16, 32, 32, 3, 2, 1, 35, 33),
+    (torch.bfloat16, 16, 32, 3, 1, 3, 40, 70),
+    (torch.bfloat16, 32, 24, 2, 1, 1, 9, 9),
 ]
 
 
@@ -161,6 +167,10 @@ def test_wgrad_tc(env, dtype, cin, cout, k, s, n, h, w):
     F.conv2d(xr, wr, stride=s).backward(gy.double().cpu().permute(0, 3, 1, 2))
     assert rel(dw_simt, wr.grad) < 1e-5
     assert rel(dw_tc, wr.grad) < 1e-5, rel(dw_tc, wr.grad)
+    # tap-major scratch layout [ky][kx][co][ci] (ci contiguous -> 16-byte vector atomics in the epilogue)
+    dw_tm = torch.zeros(k, k, cout, cin, device="cuda")
+    ops.wgrad_gather(x, gy, launches, dw_tm, cin, 1, k * cout * cin, cout * cin, tensor=True)
+    assert rel(dw_tm.permute(2, 3, 0, 1), wr.grad) < 1e-5
 
 
 def test_wgrad_tc_convT_phases(env):
