@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libast_b200.so")
+# AST_B200_LIB points at another build of the same library (kernel A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get("AST_B200_LIB") or os.path.join(_HERE, "libast_b200.so")
 
 AST_F32, AST_BF16 = 0, 1
 AST_MAX_TAPS = 81
