@@ -371,9 +371,21 @@ static int grid_rows(int n, int rows_total, int* rows) {
   return (rows_total + *rows - 1) / *rows;
 }
 
+// norm_staged.cu: bulk-copy staged versions (tried first; 0 = shape not suited, use the register kernels below)
+int instnorm_apply_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s);
+int instnorm_bwd_stats_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                              float* s1, float* s2, cudaStream_t s);
+int instnorm_bwd_apply_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                              const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
+                              cudaStream_t s);
+
 // Returns 1 if the fast kernel was launched, 0 if the shapes/dtypes need the generic kernel, <0 / >0 on error.
 int instnorm_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                         const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s) {
+  if (int r = instnorm_apply_staged(x, mean, rstd, gamma, beta, residual, out, pad, relu, s)) return r;
   const int vec = x->dtype == AST_F32 ? 4 : 8;
   if (x->dtype != out->dtype || !fast_ok(x, vec) || !fast_ok(out, vec) || NF_THREADS % (x->c / vec) != 0) return 0;
   if (residual && (!fast_ok(residual, vec) || residual->dtype != x->dtype)) return 0;
@@ -401,6 +413,7 @@ static bool bwd_fast_ok(const ast_image* x, const ast_image* gpad, const ast_ima
 int instnorm_bwd_stats_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
                             const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
                             float* s1, float* s2, cudaStream_t s) {
+  if (int r = instnorm_bwd_stats_staged(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, s)) return r;
   const int vec = x->dtype == AST_F32 ? 4 : 8;
   if (!bwd_fast_ok(x, gpad, gextra, vec)) return 0;
   NfShape sh;
@@ -421,6 +434,7 @@ int instnorm_bwd_apply_fast(const ast_image* x, const float* mean, const float* 
                             const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
                             const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
                             cudaStream_t s) {
+  if (int r = instnorm_bwd_apply_staged(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, dx, gtotal, s)) return r;
   const int vec = x->dtype == AST_F32 ? 4 : 8;
   if (x->dtype != dx->dtype || !bwd_fast_ok(x, gpad, gextra, vec) || !fast_ok(dx, vec) || !lin_ok(dx)) return 0;
   if (gtotal && (!fast_ok(gtotal, vec) || gtotal->dtype != x->dtype || !lin_ok(gtotal))) return 0;

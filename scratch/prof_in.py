@@ -27,9 +27,17 @@ def bench(n, h, w, c, pad, relu, residual, sets=6, iters=30):
                              ("apply", run_apply, (x.numel() * (1 + (1 if residual else 0)) + out.numel()) * 2)):
         for i in range(5): fn(i)
         torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()                 # graph replay: no CPU launch overhead in the timing
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            fn(0)
+            with torch.cuda.graph(graph, stream=st):
+                for i in range(iters): fn(i)
+        torch.cuda.synchronize()
+        graph.replay(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters): fn(i)
+        graph.replay()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         print(f"{name:6s} ({n},{h},{w},{c}) pad={pad} res={residual}: {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s (all passes' bytes)")
