@@ -44,6 +44,10 @@ def _vgg_layout():
     return layers
 
 
+def _vgg_bwd_bf16():
+    return os.environ.get("AST_VGG_BWD", "bf16") != "tf32"
+
+
 class _VGGFunction(torch.autograd.Function):
     """conv3x3(pad 1)+ReLU / maxpool chain up to `upto`, returning the tapped activations (NCHW views)."""
 
@@ -103,7 +107,12 @@ class _VGGFunction(torch.autograd.Function):
                     ops.copy_image(g, gc)
                     g = gc
                 tapg[idx] = g
-        packed = module._packed_dgrad(tensor)
+        # fast mode: the gradient chain through the frozen VGG runs in bf16 (fp32 accumulation), like the transform
+        # net's backward; the forward taps, Grams and losses keep TF32 (parity is stated on those).  AST_VGG_BWD=tf32
+        # restores a TF32 backward.
+        bf16_bwd = tensor and _vgg_bwd_bf16()
+        gdt = torch.bfloat16 if bf16_bwd else torch.float32
+        packed = module._packed_dgrad(tensor, bf16_bwd)
         g = None            # gradient w.r.t. the OUTPUT of the current plan entry (already ReLU-masked for convs)
         gx = None
         for pos in reversed(range(len(plan))):
@@ -118,7 +127,7 @@ class _VGGFunction(torch.autograd.Function):
             relu_idx = idx + 1
             if relu_idx in tapg:   # tap gradient not yet folded in (only when no pool/conv consumer did it)
                 t = tapg.pop(relu_idx)
-                m = torch.empty_like(t)
+                m = torch.empty(t.shape, dtype=gdt, device=t.device)
                 ops.mask_add(t, g, out, m)       # (tap grad + downstream grad) * (relu out > 0)
                 g = m
             if g is None:
@@ -130,15 +139,15 @@ class _VGGFunction(torch.autograd.Function):
                 ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1), tensor=tensor)
                 break
             launches = cg.conv_dgrad(3, 1, 1, xin.shape[1], xin.shape[2])
-            gin = torch.empty(xin.shape, dtype=torch.float32, device=g.device)
+            gin = torch.empty(xin.shape, dtype=gdt, device=g.device)
             # the conv input is either a ReLU output (mask here, add its tap grad) or a pool output (no mask)
             prev_kind = plan[pos - 1][1]
             use_tc = tensor and ops.tc_eligible(g, xin.shape[3])
             if prev_kind == "conv":
                 ops.conv_gather(g, packed[idx], launches, gin, add=tapg.pop(idx - 1, None), mask=xin, tensor=use_tc,
-                                round_tf32=tensor)
+                                round_tf32=tensor and not bf16_bwd)
             else:
-                ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc, round_tf32=tensor)
+                ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc, round_tf32=tensor and not bf16_bwd)
             g = gin
         ctx.plan = None
         return (gx, None, None, None) + tuple(None for _ in module._weights())
@@ -200,20 +209,20 @@ class VGG16(nn.Module, _cnn._Precision):
             self._pack_cache["fwd_key"], self._pack_cache["fwd"] = key, out
         return self._pack_cache["fwd"]
 
-    def _packed_dgrad(self, tensor):
-        key = self._cache_key("dgrad", tensor)
+    def _packed_dgrad(self, tensor, bf16=False):
+        key = self._cache_key("dgrad", (tensor, bf16))
         if self._pack_cache.get("dgrad_key") != key:
             out = {}
             launches = cg.conv_dgrad(3, 1, 1, 8, 8)
+            wdt = torch.bfloat16 if bf16 else (ops.TF32 if tensor else torch.float32)
             for idx, kind, cin, cout in self._layout:
                 if kind == "conv" and idx <= 21:
                     w = self.features[idx].weight.detach().float()
                     if idx == 0 and tensor:     # [t][ci (3 of 32)][co]: thin-output dgrad on the tensor cores
                         offs = [u * 3 + v for u, v in cg.all_wtaps(launches)]
-                        out[idx] = ops.pack_weights_ex(w, offs, 32, cin, cout, cout, 1, 9, 27, 0, ops.TF32)
+                        out[idx] = ops.pack_weights_ex(w, offs, 32, cin, cout, cout, 1, 9, 27, 0, wdt)
                         continue
-                    out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1,
-                                                ops.TF32 if tensor else torch.float32)
+                    out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1, wdt)
             self._pack_cache["dgrad_key"], self._pack_cache["dgrad"] = key, out
         return self._pack_cache["dgrad"]
 
