@@ -46,6 +46,7 @@ _SIGNATURES = {
     "ast_row_im2col": [_P(Image), _P(Image), _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                        ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_unfold_rows": [_P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp],
+    "ast_fold_rows": [_P(Image), _P(Image), _vp, ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_stats": [_P(Image), _vp, _vp, ctypes.c_float, _vp, _vp],
     "ast_instnorm_finalize": [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, _vp, _vp, _vp],
     "ast_instnorm_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, _vp],

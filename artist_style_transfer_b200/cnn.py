@@ -11,6 +11,7 @@ Internal data flow: activations are NHWC; each stage is
 The backward pass runs the same stages in reverse inside one autograd.Function.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -145,6 +146,18 @@ def _thin_out_pack_fwd(st, w, launches, dtype):   # [t][co (3 of 32)][c] = W[co]
     return ops.pack_weights_ex(w, offs, 32, st.cout, st.cin, st.cin, 1, st.cin * k2, k2, 0, dtype)
 
 
+def _thin_out_pack_vfwd(st, w, dtype):   # [dy][dx*cout + co (k*cout of 32)][c] = W[co][c][dy][dx]
+    k = st.k
+    w2 = w.permute(2, 3, 0, 1).contiguous()            # (dy, dx, co, c): the row index dx*cout+co becomes linear
+    return ops.pack_weights_ex(w2, [dy * k * st.cout * st.cin for dy in range(k)], 32, k * st.cout, st.cin, st.cin,
+                               st.cin, st.cin, 0, 1, dtype)
+
+
+def _thin_out_fold():
+    """AST_THIN_OUT=taps: the last 9x9 layer as one 81-tap conv; default: 9 vertical taps + ast_fold_rows."""
+    return os.environ.get("AST_THIN_OUT", "fold") != "taps"
+
+
 def _thin_out_pack_dgrad(st, w, dtype):   # [dy][c][dx*cout + co] = W[co][c][dy][dx]
     k, k2 = st.k, st.k * st.k
     return ops.pack_weights_ex(w, [dy * k for dy in range(k)], st.cin, st.cin, 32, k * st.cout, st.cout,
@@ -188,13 +201,26 @@ class _StageFunction(torch.autograd.Function):
                 wp = _thin_in_pack(st, cw.detach(), adt)
             else:
                 launches, ho, wo = _fwd_geometry(st, xin.shape[1], xin.shape[2])
-                wp = (_thin_out_pack_fwd(st, cw.detach(), launches, adt) if thin_out
-                      else _pack_fwd(st, cw.detach(), launches, adt))
+                if thin_out and _thin_out_fold():
+                    wp = None                      # packed for the vertical-tap formulation below
+                else:
+                    wp = (_thin_out_pack_fwd(st, cw.detach(), launches, adt) if thin_out
+                          else _pack_fwd(st, cw.detach(), launches, adt))
             if not st.norm:
                 assert last, "a stage without norm must be the last one"
                 out = torch.empty((n, st.cout, ho, wo), dtype=torch.float32, device=dev)
-                ops.conv_gather(xin, wp, launches, out.permute(0, 2, 3, 1), bias=cb.detach(), relu=st.relu,
-                                tensor=thin_out)
+                if thin_out and _thin_out_fold():
+                    # k vertical taps on the tensor cores give, per pixel, the partial sums of all k horizontal taps
+                    # as k*cout (27 of 32) channels; ast_fold_rows adds the k shifted partials and the bias
+                    taps, wt = _vtaps(st.k)
+                    part = torch.empty((n, ho, xin.shape[2], 32), dtype=torch.float32, device=dev)
+                    ops.conv_gather(xin, _thin_out_pack_vfwd(st, cw.detach(), adt),
+                                    [cg.Launch(ho, xin.shape[2], 1, 1, 0, 0, taps, wt, 0)], part, tensor=True)
+                    ops.fold_rows(part, out.permute(0, 2, 3, 1), st.k, bias=cb.detach(), relu=st.relu)
+                    del part
+                else:
+                    ops.conv_gather(xin, wp, launches, out.permute(0, 2, 3, 1), bias=cb.detach(), relu=st.relu,
+                                    tensor=thin_out)
                 saved.append((launches, None, None, None))
             else:
                 raw = torch.empty((n, ho, wo, st.cout), dtype=adt, device=dev)

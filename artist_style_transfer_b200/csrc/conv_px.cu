@@ -1,0 +1,373 @@
+// "Pixels-as-N" orientation of the tcgen05 gather convolution, for layers with at most 128 output channels.
+//
+// Measured on B200 (scratch/mma_bench.cu, profiles/r01_summary.md): a tcgen05.mma of cta_group::1 costs
+// max(~64, N/2) cycles, and ~104 cycles as soon as tcgen05.commit is used to recycle pipeline stages - whatever M is.
+// conv_tc.cu maps output channels to N, so a 128-channel layer pays 104 cycles for a 128x128x(32 B) MMA and a
+// 64-channel layer the same for half the work.  Here the operands swap roles:
+//
+//     D^T[co][pixel] (fp32, TMEM: lane = output channel, column = pixel)  +=  W_t[co][k] * X[pixel + tap_t][k]
+//
+//   A operand = the packed weights of tap t (<= 128 rows, K-major),  B operand = 256 pixels (two 128-pixel tiles of the
+//   same image, K-major rows of the NHWC tensor), so every MMA is 128 x 256 x (32 B) and runs at the tensor peak.
+//
+// Warp roles as in conv_tc.cu (warp 0 TMA, warp 1 MMA, warps 2-9 epilogue).  In the epilogue a thread owns ONE output
+// channel and 32 consecutive pixels of a tcgen05.ld: the bias is a scalar, the InstanceNorm statistics (sum x, sum x^2)
+// are plain per-thread sums, and for a fixed pixel the 32 lanes of a warp touch 32 consecutive channels, so the NHWC
+// stores and the add / mask loads are coalesced without a shared-memory transpose.
+#include "tc_common.cuh"
+
+namespace ast {
+
+constexpr int PX_THREADS = 320;
+constexpr int PX_MAX_STAGES = 8;
+constexpr int PX_PRODUCERS = 4;    // producer lanes (one thread issues only ~1 TMA instruction per 150-200 cycles)
+
+struct PxParams {
+  int mi, mj, tw, th, tiles_i, tiles_j, n_img;
+  int ntaps, kchunks, kc;
+  int si, so, oy0, ox0;
+  int cout, flags;                 // cout = weight rows per tap (64 or 128)
+  int w_rows_per_img;
+  int stages, w_bytes, a_bytes, stage_bytes, rowb;
+  int pairs_per_img;
+  unsigned idesc, layout_type, sbo;
+  long long total_pairs;
+  short dy[AST_MAX_TAPS];
+  short dx[AST_MAX_TAPS];
+};
+
+struct Img32 {                     // 32-bit element strides (the host checks every tensor spans < 2^31 elements)
+  char* ptr;
+  int dtype, h, w, sn, sh, sw;
+};
+
+__device__ __forceinline__ float px_ld(const Img32& im, int off) {
+  return im.dtype == AST_F32 ? reinterpret_cast<const float*>(im.ptr)[off]
+                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(im.ptr)[off]);
+}
+__device__ __forceinline__ void px_st(const Img32& im, int off, float v) {
+  if (im.dtype == AST_F32) reinterpret_cast<float*>(im.ptr)[off] = v;
+  else reinterpret_cast<__nv_bfloat16*>(im.ptr)[off] = __float2bfloat16_rn(v);
+}
+
+// One 32-pixel x 32-channel accumulator chunk: v[e] = D^T[ch][pixel e].  FAST: the 32 pixels are consecutive in x inside
+// one tile row (tw % 32 == 0), so their offsets are affine in e (o = base + e*step, the first `nvalid` are in range);
+// otherwise lane e holds pixel e's offsets and they are broadcast with shuffles.
+struct PxOff { int out, add, mask; };      // FAST: offsets of pixel 0 (uniform); else of pixel `lane`; out < 0 = invalid
+template <bool FAST>
+__device__ __forceinline__ void px_chunk(float* v, const PxOff& off, int nvalid, int so, int ch, int lane, float b, int flags,
+                                         const Img32& add, const Img32& mask, const Img32& out, bool want_stats, float& s1,
+                                         float& s2) {
+#define PX_VALID(e) (FAST ? (e) < nvalid : __shfl_sync(0xffffffffu, off.out, (e)) >= 0)
+#define PX_OFF(field, sw, e) (FAST ? off.field + (e) * so * (sw) : __shfl_sync(0xffffffffu, off.field, (e)))
+  if (want_stats) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float x = PX_VALID(e) ? v[e] : 0.f;
+      s1 += x; s2 = fmaf(x, x, s2);
+    }
+  }
+  // the add / mask operands of all 32 pixels are loaded up front (independent loads in flight), never interleaved
+  // with the stores: the compiler must assume out may alias them
+  if (add.ptr) {
+    float t[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int oa = PX_OFF(add, add.sw, e);
+      t[e] = PX_VALID(e) ? px_ld(add, oa + ch) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] += t[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    v[e] += b;
+    if (flags & AST_CONV_RELU) v[e] = fmaxf(v[e], 0.f);
+  }
+  if (mask.ptr) {
+    float t[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int om = PX_OFF(mask, mask.sw, e);
+      t[e] = PX_VALID(e) ? px_ld(mask, om + ch) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = t[e] > 0.f ? v[e] : 0.f;
+  }
+  if (flags & AST_CONV_ROUND_TF32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+  }
+  if (out.dtype == AST_F32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int o = PX_OFF(out, out.sw, e);
+      if (PX_VALID(e)) reinterpret_cast<float*>(out.ptr)[o + ch] = v[e];
+    }
+  } else {
+    // bf16: neighbouring lanes trade values so that every lane stores TWO channels (4 bytes) of one pixel: even lanes
+    // serve pixel e, odd lanes pixel e+1 -> 16 store instructions of 2 x 64 B instead of 32 of 64 B
+    const int odd = lane & 1;
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      const float mine = odd ? v[e + 1] : v[e];          // my channel, the pixel I store
+      const float give = odd ? v[e] : v[e + 1];          // my channel, the pixel the neighbour stores
+      const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+      const int o = FAST ? off.out + (e + odd) * so * out.sw : __shfl_sync(0xffffffffu, off.out, e + odd);
+      const bool ok = FAST ? (e + odd) < nvalid : o >= 0;
+      const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine) : __floats2bfloat162_rn(mine, got);
+      if (ok) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + o + (ch & ~1)) = pk;
+    }
+  }
+#undef PX_VALID
+#undef PX_OFF
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PX_THREADS, 1)
+conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const PxParams p,
+               const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
+               float* __restrict__ stats) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[PX_MAX_STAGES], empty_bar[PX_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ unsigned tmem_slot;
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ksteps = p.ntaps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producers (lanes 0..PX_PRODUCERS-1 take the stages round-robin) ============
+    if (lane < PX_PRODUCERS) {
+      int s = 0, turn = 0; unsigned ph = 0;
+      for (long long pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+        const int img = (int)(pair / p.pairs_per_img);
+        const int sp0 = 2 * (int)(pair % p.pairs_per_img);
+        // two consecutive spatial tiles (row-major over ti, tj); a tile index past the end gives ti == tiles_i: the
+        // loads are fully out of bounds (zero fill) and the epilogue stores nothing
+        const int ti0 = sp0 / p.tiles_j, tj0 = sp0 - ti0 * p.tiles_j;
+        const int ti1 = (sp0 + 1) / p.tiles_j, tj1 = (sp0 + 1) - ti1 * p.tiles_j;
+        const int x0 = p.si * tj0 * p.tw, y0 = p.si * ti0 * p.th, x1 = p.si * tj1 * p.tw, y1 = p.si * ti1 * p.th;
+        const int wrow0 = img * p.w_rows_per_img;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            if (turn == lane) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              unsigned char* sw = smem + (size_t)s * p.stage_bytes;
+              mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
+              tma_load_2d(sw, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
+              tma_load_4d(sw + p.w_bytes, &tm_in, &full_bar[s], kc * p.kc, x0 + p.dx[t], y0 + p.dy[t], img);
+              tma_load_4d(sw + p.w_bytes + p.a_bytes, &tm_in, &full_bar[s], kc * p.kc, x1 + p.dx[t], y1 + p.dy[t], img);
+            }
+            if (++turn == PX_PRODUCERS) turn = 0;
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
+    const int kmma = p.rowb / 32;
+    const unsigned desc_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
+    for (long long pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const unsigned d_tmem = tmem_base + (unsigned)(as * 256);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const unsigned w_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const unsigned a_lo = ((w_addr & 0x3FFFFu) >> 4) | (1u << 16);                   // A operand: weights
+          const unsigned b_lo = (((w_addr + p.w_bytes) & 0x3FFFFu) >> 4) | (1u << 16);      // B operand: 256 pixels
+          tc_mma<KIND>(d_tmem, pack_desc64(a_lo, desc_hi), pack_desc64(b_lo, desc_hi), p.idesc, ks > 0 ? 1u : 0u);
+          tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 2, desc_hi), pack_desc64(b_lo + 2, desc_hi), p.idesc, 1u);
+          if (kmma == 4) {
+            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 4, desc_hi), pack_desc64(b_lo + 4, desc_hi), p.idesc, 1u);
+            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 6, desc_hi), pack_desc64(b_lo + 6, desc_hi), p.idesc, 1u);
+          }
+          tc_commit(&empty_bar[s]);
+          if (ks == ksteps - 1) tc_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else {
+    // ============================ epilogue (warps 2..9) ============================
+    const int q = warp & 3;                        // TMEM lane quarter -> output channels q*32 .. q*32+31
+    const int half = (warp - 2) >> 2;              // which 128-pixel tile of the pair (TMEM columns half*128 ..)
+    const int ch = q * 32 + lane;
+    const bool ch_ok = ch < p.cout;
+    const float b = (bias && ch_ok) ? bias[ch] : 0.f;
+    int as = 0; unsigned aph = 0;
+    for (long long pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+      const int img = (int)(pair / p.pairs_per_img);
+      const int sp = 2 * (int)(pair % p.pairs_per_img) + half;
+      const int ti = sp / p.tiles_j, tj = sp - ti * p.tiles_j;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * 256 + half * 128);
+      float s1 = 0.f, s2 = 0.f;
+      if (q * 32 < p.cout) {                       // warp-uniform: quarters beyond cout hold nothing
+        const bool fast = (p.tw & 31) == 0;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          float v[32];
+          tc_ld32(taddr0 + c0, v);
+          if (fast) {           // the chunk is 32 consecutive x positions of tile row c0 / tw
+            const int ty = c0 / p.tw, tx0 = c0 - ty * p.tw;
+            const int i = ti * p.th + ty, j0 = tj * p.tw + tx0;
+            const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j0;
+            int nvalid = 0;
+            if (i < p.mi && oy < out.h) {
+              const int jlim = min(p.mj, (out.w - p.ox0 + p.so - 1) / p.so);    // j < jlim  <=>  j < mj and ox < out.w
+              nvalid = max(0, min(32, jlim - j0));
+            }
+            PxOff off;
+            off.out = img * out.sn + oy * out.sh + ox * out.sw;
+            off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
+            off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
+            if (nvalid > 0) px_chunk<true>(v, off, nvalid, p.so, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
+          } else {              // lane L describes pixel c0 + L of the tile
+            const int row = c0 + lane;
+            const int ty = row / p.tw, tx = row - ty * p.tw;
+            const int i = ti * p.th + ty, j = tj * p.tw + tx;
+            const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
+            const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
+            PxOff off;
+            off.out = valid ? img * out.sn + oy * out.sh + ox * out.sw : -1;
+            off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
+            off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
+            px_chunk<false>(v, off, 0, p.so, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
+          }
+        }
+        if (stats && ch_ok) {
+          float* srow = stats + ((long long)img * p.cout + ch) * 2;
+          atomicAdd(srow, s1);
+          atomicAdd(srow + 1, s2);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static bool img32_ok(const ast_image* im) {
+  if (!im) return true;
+  const long long span = (long long)(im->n - 1) * im->sn + (long long)(im->h - 1) * im->sh + (long long)(im->w - 1) * im->sw + im->c;
+  return im->sc == 1 && im->sn >= 0 && im->sh >= 0 && im->sw >= 0 && span < (1ll << 31);
+}
+static Img32 to_img32(const ast_image* im) {
+  Img32 r;
+  if (!im) { r.ptr = nullptr; r.dtype = 0; r.h = r.w = r.sn = r.sh = r.sw = 0; return r; }
+  r.ptr = (char*)im->ptr; r.dtype = im->dtype; r.h = im->h; r.w = im->w;
+  r.sn = (int)im->sn; r.sh = (int)im->sh; r.sw = (int)im->sw;
+  return r;
+}
+
+// 1 = launched, 0 = not applicable (the caller falls back to conv_ws / conv_tc), other = error.
+// mode: AST_CONV_PX env (0 off, 1 default).  The caller has validated pointers / alignment (conv_gather_tc).
+int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
+                   cudaStream_t stream) {
+  if (thin || (cpad != 64 && cpad != 128) || out->c != cpad) return 0;
+  if (!img32_ok(out) || !img32_ok(add) || !img32_ok(mask)) return 0;
+  const int esz = in->dtype == AST_F32 ? 4 : 2;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return 0;
+
+  PxParams p;
+  memset(&p, 0, sizeof(p));
+  p.mi = g->mi; p.mj = g->mj; p.si = g->si; p.so = g->so; p.oy0 = g->oy0; p.ox0 = g->ox0;
+  p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.n_img = in->n;
+  for (int t = 0; t < g->ntaps; ++t) { p.dy[t] = g->dy[t]; p.dx[t] = g->dx[t]; }
+  pick_tile(p.mi, p.mj, 128, &p.tw, &p.th);
+  p.tiles_i = (p.mi + p.th - 1) / p.th;
+  p.tiles_j = (p.mj + p.tw - 1) / p.tw;
+  p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
+  p.kc = p.rowb / esz;
+  p.kchunks = in->c / p.kc;
+  if (p.ntaps * p.kchunks * (p.rowb / 32) < 16) return 0;   // short K loops are epilogue bound: conv_tc's vector stores win
+  p.w_rows_per_img = 0;
+  if (g->w_img_stride) {
+    if (g->w_img_stride != (int64_t)g->ntaps * cpad * in->c) return 0;
+    p.w_rows_per_img = g->ntaps * cpad;
+  }
+  p.w_bytes = 128 * p.rowb;          // always a 128-row box: rows >= cout belong to the next tap (or are OOB zeros) and only
+  p.a_bytes = 128 * p.rowb;          // feed accumulator lanes that the epilogue ignores
+  p.stage_bytes = p.w_bytes + 2 * p.a_bytes;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > PX_MAX_STAGES) p.stages = PX_MAX_STAGES;
+  p.layout_type = p.rowb == 128 ? 2u : 4u;
+  p.sbo = 8u * p.rowb;
+  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  p.pairs_per_img = (p.tiles_i * p.tiles_j + 1) / 2;
+  p.total_pairs = (long long)p.n_img * p.pairs_per_img;
+
+  alignas(64) CUtensorMap tm_in, tm_w;
+  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {(cuuint64_t)in->sw * esz, (cuuint64_t)in->sh * esz, (cuuint64_t)in->sn * esz};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.tw * p.si), (cuuint32_t)(p.th * p.si), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.si, (cuuint32_t)p.si, 1};
+    CUresult r = encode(&tm_in, dt, 4, in->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_px: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return (int)r; }
+  }
+  {
+    const long long rows = (long long)g->ntaps * cpad * (g->w_img_stride ? in->n : 1);
+    cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_px: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const int grid = (int)(p.total_pairs < num_sms() ? p.total_pairs : num_sms());
+  cudaError_t e;
+  if (in->dtype == AST_BF16) {
+    e = cudaFuncSetAttribute(conv_px_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_px_kernel<0><<<grid, PX_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+  } else {
+    e = cudaFuncSetAttribute(conv_px_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv_px_kernel<1><<<grid, PX_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+  }
+  if (e != cudaSuccess) { set_error("conv_px: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
+}  // namespace ast

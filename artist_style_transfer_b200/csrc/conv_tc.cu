@@ -16,6 +16,9 @@ namespace ast {
 
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
 constexpr int MAX_STAGES = 8;
+#ifndef TC_PRODUCERS
+#define TC_PRODUCERS 4
+#endif
 
 struct TcParams {
   int mi, mj, tw, th, tiles_i, tiles_j, n_img, n_tiles_n, bn;
@@ -88,6 +91,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef TC_PROFILE
+  long long prof_wait = 0, prof_wait2 = 0, prof_t0 = 0, prof_a = 0, prof_b = 0;
+  const long long prof_start = clock64();
+#define TC_PROF_T0() prof_t0 = clock64()
+#define TC_PROF_ADD(v) v += clock64() - prof_t0
+#else
+#define TC_PROF_T0()
+#define TC_PROF_ADD(v)
+#endif
   const int ksteps = p.ntaps * p.kchunks;
   const unsigned tmem_cols = (2 * p.bn <= 32) ? 32 : (2 * p.bn <= 64) ? 64 : (2 * p.bn <= 128) ? 128 : (2 * p.bn <= 256) ? 256 : 512;
 
@@ -117,7 +129,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    int s = 0; unsigned ph = 0;
+    // TC_PRODUCERS lanes take the pipeline stages round-robin: ONE issuing thread sustains only ~45 B/clk (a wait +
+    // expect_tx + two TMA instructions cost it ~750 cycles), four reach the ~80 B/clk an SM can pull from L2
+    // (scratch/mma_bench.cu, profiles/r01_summary.md).
+    int s = 0, turn = 0; unsigned ph = 0;
+    if (lane < TC_PRODUCERS)
     for (long long tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
       long long r = tile;
       const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
@@ -136,20 +152,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int t = 0; t < p.ntaps; ++t) {
         const int cx = x0 + p.dx[t], cy = y0 + p.dy[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (lane == 0) {
+          if (turn == lane) {
+            TC_PROF_T0();
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            TC_PROF_ADD(prof_wait);
             unsigned char* sa = smem + (size_t)s * p.stage_bytes;
             if (CG == 1) {
+              TC_PROF_T0();
               mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
+              TC_PROF_ADD(prof_wait2);
+              TC_PROF_T0();
               tma_load_4d(sa, &tm_in, &full_bar[s], kc * p.kc, cx, cy, img);
+              TC_PROF_ADD(prof_a);
+              TC_PROF_T0();
               tma_load_2d(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
+              TC_PROF_ADD(prof_b);
             } else {     // both CTAs' bytes land on the LEADER's full barrier, which expects twice a stage
               if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)p.stage_bytes);
               tma_load_4d_2sm(sa, &tm_in, &full_bar[s], kc * p.kc, cx, cy, img);
               tma_load_2d_2sm(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
             }
           }
-          __syncwarp();
+          if (++turn == TC_PRODUCERS) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -160,11 +184,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const int kmma = p.rowb / 32;   // UMMA_K spans 32 bytes for both bf16 (16 elems) and tf32 (8 elems)
     const unsigned desc_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
     for (long long tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+      TC_PROF_T0();
       mbar_wait(&tempty_bar[as], aph ^ 1);
+      TC_PROF_ADD(prof_wait2);
       tc_fence_after();
       const unsigned d_tmem = tmem_base + (unsigned)(as * p.bn);
       for (int ks = 0; ks < ksteps; ++ks) {
+        TC_PROF_T0();
         mbar_wait(&full_bar[s], ph);
+        TC_PROF_ADD(prof_wait);
         tc_fence_after();
         if (lane == 0) {
           // descriptor hi word is constant; lo word = (addr >> 4) | LBO, advanced by 32 B (= 2) per UMMA_K step
@@ -220,7 +248,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const int i = ti * p.th + ty, j = tj * p.tw + tx;
       const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
       const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
+      TC_PROF_T0();
       mbar_wait(&tfull_bar[as], aph);
+      TC_PROF_ADD(prof_wait);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
       EpiRows rows;
@@ -242,6 +272,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     }
   }
 
+#ifdef TC_PROFILE
+  if (blockIdx.x == 3 && (threadIdx.x & 31) == 0 && warp <= 2)
+    printf("conv_tc prof: warp %d total %lld clk, wait %lld, wait2 %lld, tmaA %lld, tmaB %lld (stages/CTA ~%lld, bn %d kchunks %d taps %d)\n", warp,
+           clock64() - prof_start, prof_wait, prof_wait2, prof_a, prof_b, (p.total_tiles / gridDim.x) * p.ntaps * p.kchunks, p.bn, p.kchunks, p.ntaps);
+#endif
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -255,6 +290,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
                    cudaStream_t stream);   // conv_ws.cu: 1 = launched, 0 = not applicable
+int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
+                   cudaStream_t stream);   // conv_px.cu: 1 = launched, 0 = not applicable
 int tc_capabilities() { return 3; }   // 1 = conv_tc.cu, 2 = contract_tc.cu (both are always built together)
 
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
@@ -279,7 +317,14 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  // AST_CONV_PX: 0 = off, 1 (default) = pixels-as-N kernel for cout 64/128 where the weight-stationary kernel does not
+  // apply, 2 = also ahead of the weight-stationary kernel
+  static const int px_mode = [] { const char* e = getenv("AST_CONV_PX"); return e ? atoi(e) : 1; }();
+  if (px_mode == 2)
+    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
   if (int wr = conv_gather_ws(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return wr == 1 ? 0 : wr;
+  if (px_mode == 1)
+    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -309,6 +354,9 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   p.stage_bytes = p.a_bytes + (p.bn / p.cg) * p.rowb;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  static const int dbg_stages = [] { const char* e = getenv("AST_TC_STAGES"); return e ? atoi(e) : 0; }();   // experiments only
+  static const int dbg_grid = [] { const char* e = getenv("AST_TC_GRID"); return e ? atoi(e) : 0; }();
+  if (dbg_stages > 1 && dbg_stages < p.stages) p.stages = dbg_stages;
   p.layout_type = p.rowb == 128 ? 2u : 4u;       // SWIZZLE_128B / SWIZZLE_64B
   p.sbo = 8u * p.rowb;
   const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;   // TF32 / BF16
@@ -339,7 +387,8 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 8192;   // + per-warp store-transpose stage
-  const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   cudaError_t e;
   if (p.cg == 2) {

@@ -166,6 +166,51 @@ extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32
   return 0;
 }
 
+// Inverse companion of ast_row_im2col for a thin-OUTPUT k x k convolution (the 32->3 9x9 last layer, cnn.py:39):
+// the k vertical taps run as a tcgen05 conv whose output channel r = d*C + c holds, at pixel (y, x'), the partial sum
+// of output channel c for horizontal tap d; this kernel finishes the filter:
+//     out[n, y, x, c] = bias[c] + sum_{d < kw} part[n, y, x + d, d*C + c]
+// One block per (n, y) row: the row of partial sums is staged in shared memory with coalesced 16-byte loads.
+__global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const float* __restrict__ bias, int kw, int relu) {
+  extern __shared__ float row[];
+  const int n = blockIdx.x / out.h, y = blockIdx.x % out.h;
+  const int pc = part.c, C = out.c;
+  const float4* src = reinterpret_cast<const float4*>((const float*)part.ptr + img_off(part, n, y, 0, 0));
+  const int nvec = part.w * pc / 4;                  // the row is contiguous (checked on the host)
+  const int ps = pc + 1;                             // padded pixel stride: threads walk x, so pc (=32) would be a 32-way bank conflict
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const float4 t = __ldg(src + i);
+    float* dst = row + (4 * i / pc) * ps + (4 * i % pc);
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < out.w * C; idx += 256) {
+    const int x = idx % out.w, c = idx / out.w;      // consecutive threads -> consecutive x (NCHW outputs coalesce)
+    float v = bias ? bias[c] : 0.f;
+    for (int d = 0; d < kw; ++d) v += row[(x + d) * ps + d * C + c];
+    if (relu) v = fmaxf(v, 0.f);
+    st_elem(out, img_off(out, n, y, x, c), v);
+  }
+}
+
+extern "C" int ast_fold_rows(const ast_image* part, const ast_image* out, const float* bias, int32_t kw, int32_t relu,
+                             void* stream) {
+  AST_CHECK_ARG(part && out, "ast_fold_rows: null argument");
+  AST_CHECK_ARG(part->dtype == AST_F32 && kw >= 1 && part->n == out->n && part->h == out->h && part->w == out->w + kw - 1 &&
+                part->c >= kw * out->c, "ast_fold_rows: part must be fp32 [n, h, w+kw-1, >= kw*c]");
+  AST_CHECK_ARG(part->sc == 1 && part->sw == part->c && part->c % 4 == 0 && part->sh % 4 == 0 && part->sn % 4 == 0 &&
+                ((uintptr_t)part->ptr & 15) == 0, "ast_fold_rows: part rows must be dense and 16-byte aligned");
+  const size_t smem = (size_t)part->w * (part->c + 1) * sizeof(float);
+  AST_CHECK_ARG(smem <= 200 * 1024, "ast_fold_rows: row of %zu bytes does not fit shared memory", smem);
+  if ((long long)out->n * out->h * out->w * out->c == 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fold_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("ast_fold_rows: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+  fold_rows_kernel<<<out->n * out->h, 256, smem, (cudaStream_t)stream>>>(to_img(part), to_img(out), bias, kw, relu);
+  count_launch();
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shift, int32_t kw, int32_t sign,
                               int32_t px, int32_t py, int32_t reflect, int32_t round_tf32, void* stream) {
   AST_CHECK_ARG(src && out, "ast_row_im2col: null argument");

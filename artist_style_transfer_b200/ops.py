@@ -89,6 +89,10 @@ def _pack_weights_impl(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
     return out
 
 
+def _pw(name, t):
+    return "pointwise" + (f"|{name}{tuple(t.shape)}" if PROFILE_DETAIL and _prof is not None else "")
+
+
 def pack_weights_ex(w, tap_offs, a, a_valid, b, b_valid, b0, s_a, s_b1, s_b0, dtype):
     """dst[t][ia][ib] = w.flat[tap_offs[t] + ia*s_a + (ib//b0)*s_b1 + (ib%b0)*s_b0], zero outside the valid box."""
     with _timed("pack"):
@@ -102,7 +106,7 @@ def pack_weights_ex(w, tap_offs, a, a_valid, b, b_valid, b0, s_a, s_b1, s_b0, dt
 
 def row_im2col(src, out, kw, sign, px, py, reflect, shift=None, round_tf32=False):
     """out[n,y,x,d*C+c] = src[n, y-py, x+sign*d-px, c] (+shift); see include/ast.h ast_row_im2col."""
-    with _timed("pointwise"):
+    with _timed(_pw("row_im2col", out)):
         si, oi = image(src), image(out)
         check(_lib.load().ast_row_im2col(ref(si), ref(oi), ptr(shift), kw, sign, px, py, int(reflect), int(round_tf32),
                                          stream_ptr()), "ast_row_im2col")
@@ -111,9 +115,17 @@ def row_im2col(src, out, kw, sign, px, py, reflect, shift=None, round_tf32=False
 
 def unfold_rows(src, out, kh, sign, py=0):
     """out[n,y,x,d*C+j] = src[n, y+sign*d-py, x, j] (0 outside); see include/ast.h ast_unfold_rows."""
-    with _timed("pointwise"):
+    with _timed(_pw("unfold_rows", out)):
         si, oi = image(src), image(out)
         check(_lib.load().ast_unfold_rows(ref(si), ref(oi), kh, sign, py, stream_ptr()), "ast_unfold_rows")
+        return out
+
+
+def fold_rows(part, out, kw, bias=None, relu=False):
+    """out[n,y,x,c] = bias[c] + sum_d part[n,y,x+d,d*C+c]; see include/ast.h ast_fold_rows."""
+    with _timed(_pw("fold_rows", part)):
+        pi, oi = image(part), image(out)
+        check(_lib.load().ast_fold_rows(ref(pi), ref(oi), ptr(bias), kw, int(relu), stream_ptr()), "ast_fold_rows")
         return out
 
 
@@ -305,12 +317,12 @@ def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal
 
 
 def maxpool2_fwd(x):
-    with _timed("pointwise"):
+    with _timed(_pw("maxpool_fwd", x)):
         return _maxpool2_fwd_impl(x)
 
 
 def maxpool2_bwd(x, gy, gadd=None):
-    with _timed("pointwise"):
+    with _timed(_pw("maxpool_bwd", x)):
         return _maxpool2_bwd_impl(x, gy, gadd=gadd)
 
 
@@ -320,20 +332,20 @@ def gram(x, scale, tensor=False):
 
 
 def mse(a, b, loss, scale, grad=None, gscale=0.0):
-    with _timed("pointwise"):
+    with _timed(_pw("mse", a)):
         return _mse_impl(a, b, loss, scale, grad=grad, gscale=gscale)
 
 
 def copy_image(src, dst, shift=None, pad=0):
-    with _timed("pointwise"):
+    with _timed(_pw("copy_image", dst)):
         return _copy_image_impl(src, dst, shift=shift, pad=pad)
 
 
 def accumulate(x, acc):
-    with _timed("pointwise"):
+    with _timed(_pw("accumulate", x)):
         return _accumulate_impl(x, acc)
 
 
 def mask_add(a, b, mask, out):
-    with _timed("pointwise"):
+    with _timed(_pw("mask_add", a)):
         return _mask_add_impl(a, b, mask, out)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 2
+#define AST_ABI_VERSION 3
 
 typedef enum { AST_F32 = 0, AST_BF16 = 1, AST_TF32 = 2 /* fp32 storage rounded to TF32; pack_weights only */ } ast_dtype;
 
@@ -104,6 +104,12 @@ int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shif
 /* out[n, y, x, d*C + j] = src[n, y + sign*d - py, x, j] (0 outside), d in [0, kh): folds the kh vertical taps of an NHWC
  * tensor into channels so that a kh-tap ast_wgrad_gather becomes one tap over kh*C channels (thin 9x9 layers). */
 int ast_unfold_rows(const ast_image* src, const ast_image* out, int32_t kh, int32_t sign, int32_t py, void* stream);
+
+/* Finishes a thin-OUTPUT k x k convolution (cnn.py:39, the 32->3 9x9 layer) whose kw horizontal taps were computed as
+ * kw*C output channels of a k-tap vertical ast_conv_gather:
+ *   out[n, y, x, c] = bias[c] + sum_{d < kw} part[n, y, x + d, d*C + c]      (optional ReLU)
+ * part: fp32 NHWC [n, h, w + kw - 1, >= kw*C] with dense rows; out: any dtype / strides (e.g. an NCHW view). */
+int ast_fold_rows(const ast_image* part, const ast_image* out, const float* bias, int32_t kw, int32_t relu, void* stream);
 
 /* nn.InstanceNorm2d(affine=True), eps 1e-5, biased variance (cnn.py:68,114).
  * stats: mean[n*c], rstd[n*c] (fp32).  workspace: ast_instnorm_workspace_bytes(). */

@@ -166,3 +166,22 @@ def test_thin_layers_fast_mode(ast, cin, cout, k, norm, h, w):
     assert rel(layer.conv_layer.weight.grad, P["conv_layer.weight"].grad) < 2e-2
     if norm == "None":
         assert rel(layer.conv_layer.bias.grad, P["conv_layer.bias"].grad) < 1e-4
+
+
+def test_fold_rows_matches_direct_sum():
+    """ast_fold_rows: out[n,y,x,c] = bias[c] + sum_d part[n,y,x+d,d*C+c] (NCHW output view, optional ReLU)."""
+    from artist_style_transfer_b200 import ops
+    torch.manual_seed(5)
+    n, h, w, c, k = 2, 7, 13, 3, 9
+    part = torch.randn(n, h, w + k - 1, 32, device="cuda")
+    bias = torch.randn(c, device="cuda")
+    out = torch.empty(n, c, h, w, device="cuda")
+    ops.fold_rows(part, out.permute(0, 2, 3, 1), k, bias=bias, relu=False)
+    ref = bias.view(1, 1, 1, c).expand(n, h, w, c).clone()
+    for d in range(k):
+        ref += part[:, :, d:d + w, d * c:(d + 1) * c]
+    assert torch.allclose(out.permute(0, 2, 3, 1), ref, rtol=1e-6, atol=1e-6)
+    out2 = torch.empty(n, h, w, c, device="cuda", dtype=torch.bfloat16)
+    ops.fold_rows(part, out2, k, relu=True)
+    ref2 = torch.relu(ref - bias.view(1, 1, 1, c)).bfloat16()
+    assert torch.allclose(out2.float(), ref2.float(), rtol=1e-2, atol=1e-2)
