@@ -127,12 +127,17 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
       tc_fence_after();
       if (lane == 0) {
         const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
-        for (int u = 0; u < nt; ++u) {
+        // consecutive taps sit in consecutive column blocks (LBO apart) and in consecutive TMEM columns, so up to
+        // 256 / bn taps go into ONE MMA: an N = 256 instruction costs 128 cycles, an N <= 128 one ~104 (mma_bench)
+        const int gsz = p.bn <= 128 ? 256 / p.bn : 1;
+        for (int u = 0; u < nt; u += gsz) {
+          const int nu = min(gsz, nt - u);
+          const unsigned idesc = (p.idesc & ~(0x3Fu << 17)) | ((unsigned)((nu * p.bn) >> 3) << 17);
           const unsigned b_addr = a_addr + r_bytes + u * p.n_boxes * p.box_bytes;
           for (int k = 0; k < p.kmma; ++k) {
             const unsigned long long ad = make_mn_desc(a_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
             const unsigned long long bd = make_mn_desc(b_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
-            tc_mma<KIND>(tmem_base + (unsigned)(u * p.bn), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+            tc_mma<KIND>(tmem_base + (unsigned)(u * p.bn), ad, bd, idesc, (first && k == 0) ? 0u : 1u);
           }
         }
         tc_commit(&empty_bar[s]);

@@ -14,7 +14,7 @@
 // channel and 32 consecutive pixels of a tcgen05.ld: the bias is a scalar, the InstanceNorm statistics (sum x, sum x^2)
 // are plain per-thread sums, and for a fixed pixel the 32 lanes of a warp touch 32 consecutive channels, so the NHWC
 // stores and the add / mask loads are coalesced without a shared-memory transpose.
-#include "tc_common.cuh"
+#include "px_common.cuh"
 
 namespace ast {
 
@@ -35,93 +35,6 @@ struct PxParams {
   short dy[AST_MAX_TAPS];
   short dx[AST_MAX_TAPS];
 };
-
-struct Img32 {                     // 32-bit element strides (the host checks every tensor spans < 2^31 elements)
-  char* ptr;
-  int dtype, h, w, sn, sh, sw;
-};
-
-__device__ __forceinline__ float px_ld(const Img32& im, int off) {
-  return im.dtype == AST_F32 ? reinterpret_cast<const float*>(im.ptr)[off]
-                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(im.ptr)[off]);
-}
-__device__ __forceinline__ void px_st(const Img32& im, int off, float v) {
-  if (im.dtype == AST_F32) reinterpret_cast<float*>(im.ptr)[off] = v;
-  else reinterpret_cast<__nv_bfloat16*>(im.ptr)[off] = __float2bfloat16_rn(v);
-}
-
-// One 32-pixel x 32-channel accumulator chunk: v[e] = D^T[ch][pixel e].  FAST: the 32 pixels are consecutive in x inside
-// one tile row (tw % 32 == 0), so their offsets are affine in e (o = base + e*step, the first `nvalid` are in range);
-// otherwise lane e holds pixel e's offsets and they are broadcast with shuffles.
-struct PxOff { int out, add, mask; };      // FAST: offsets of pixel 0 (uniform); else of pixel `lane`; out < 0 = invalid
-template <bool FAST>
-__device__ __forceinline__ void px_chunk(float* v, const PxOff& off, int nvalid, int so, int ch, int lane, float b, int flags,
-                                         const Img32& add, const Img32& mask, const Img32& out, bool want_stats, float& s1,
-                                         float& s2) {
-#define PX_VALID(e) (FAST ? (e) < nvalid : __shfl_sync(0xffffffffu, off.out, (e)) >= 0)
-#define PX_OFF(field, sw, e) (FAST ? off.field + (e) * so * (sw) : __shfl_sync(0xffffffffu, off.field, (e)))
-  if (want_stats) {
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const float x = PX_VALID(e) ? v[e] : 0.f;
-      s1 += x; s2 = fmaf(x, x, s2);
-    }
-  }
-  // the add / mask operands of all 32 pixels are loaded up front (independent loads in flight), never interleaved
-  // with the stores: the compiler must assume out may alias them
-  if (add.ptr) {
-    float t[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const int oa = PX_OFF(add, add.sw, e);
-      t[e] = PX_VALID(e) ? px_ld(add, oa + ch) : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] += t[e];
-  }
-#pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    v[e] += b;
-    if (flags & AST_CONV_RELU) v[e] = fmaxf(v[e], 0.f);
-  }
-  if (mask.ptr) {
-    float t[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const int om = PX_OFF(mask, mask.sw, e);
-      t[e] = PX_VALID(e) ? px_ld(mask, om + ch) : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = t[e] > 0.f ? v[e] : 0.f;
-  }
-  if (flags & AST_CONV_ROUND_TF32) {
-#pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
-  }
-  if (out.dtype == AST_F32) {
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const int o = PX_OFF(out, out.sw, e);
-      if (PX_VALID(e)) reinterpret_cast<float*>(out.ptr)[o + ch] = v[e];
-    }
-  } else {
-    // bf16: neighbouring lanes trade values so that every lane stores TWO channels (4 bytes) of one pixel: even lanes
-    // serve pixel e, odd lanes pixel e+1 -> 16 store instructions of 2 x 64 B instead of 32 of 64 B
-    const int odd = lane & 1;
-#pragma unroll
-    for (int e = 0; e < 32; e += 2) {
-      const float mine = odd ? v[e + 1] : v[e];          // my channel, the pixel I store
-      const float give = odd ? v[e] : v[e + 1];          // my channel, the pixel the neighbour stores
-      const float got = __shfl_xor_sync(0xffffffffu, give, 1);
-      const int o = FAST ? off.out + (e + odd) * so * out.sw : __shfl_sync(0xffffffffu, off.out, e + odd);
-      const bool ok = FAST ? (e + odd) < nvalid : o >= 0;
-      const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine) : __floats2bfloat162_rn(mine, got);
-      if (ok) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + o + (ch & ~1)) = pk;
-    }
-  }
-#undef PX_VALID
-#undef PX_OFF
-}
 
 template <int KIND>
 __global__ void __launch_bounds__(PX_THREADS, 1)
@@ -245,7 +158,10 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             off.out = img * out.sn + oy * out.sh + ox * out.sw;
             off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
             off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
-            if (nvalid > 0) px_chunk<true>(v, off, nvalid, p.so, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
+            PxStep st;
+            st.out_r = st.add_r = st.mask_r = 0;
+            st.out_c = p.so * out.sw; st.add_c = p.so * add.sw; st.mask_c = p.so * mask.sw;
+            if (nvalid > 0) px_chunk<32>(v, off, st, 1, nvalid, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
           } else {              // lane L describes pixel c0 + L of the tile
             const int row = c0 + lane;
             const int ty = row / p.tw, tx = row - ty * p.tw;
@@ -256,7 +172,8 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             off.out = valid ? img * out.sn + oy * out.sh + ox * out.sw : -1;
             off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
             off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
-            px_chunk<false>(v, off, 0, p.so, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
+            PxStep st = {0, 0, 0, 0, 0, 0};
+            px_chunk<0>(v, off, st, 0, 0, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
           }
         }
         if (stats && ch_ok) {
@@ -277,19 +194,6 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
-}
-
-static bool img32_ok(const ast_image* im) {
-  if (!im) return true;
-  const long long span = (long long)(im->n - 1) * im->sn + (long long)(im->h - 1) * im->sh + (long long)(im->w - 1) * im->sw + im->c;
-  return im->sc == 1 && im->sn >= 0 && im->sh >= 0 && im->sw >= 0 && span < (1ll << 31);
-}
-static Img32 to_img32(const ast_image* im) {
-  Img32 r;
-  if (!im) { r.ptr = nullptr; r.dtype = 0; r.h = r.w = r.sn = r.sh = r.sw = 0; return r; }
-  r.ptr = (char*)im->ptr; r.dtype = im->dtype; r.h = im->h; r.w = im->w;
-  r.sn = (int)im->sn; r.sh = (int)im->sh; r.sw = (int)im->sw;
-  return r;
 }
 
 // 1 = launched, 0 = not applicable (the caller falls back to conv_ws / conv_tc), other = error.

@@ -1,0 +1,114 @@
+// Shared by conv_px.cu and conv_ws.cu: the "one thread = one output channel" epilogue of the pixels-as-N kernels.
+#pragma once
+#include "tc_common.cuh"
+
+namespace ast {
+
+struct Img32 {                     // 32-bit element strides (the host checks every tensor spans < 2^31 elements)
+  char* ptr;
+  int dtype, h, w, sn, sh, sw;
+};
+
+__device__ __forceinline__ float px_ld(const Img32& im, int off) {
+  return im.dtype == AST_F32 ? reinterpret_cast<const float*>(im.ptr)[off]
+                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(im.ptr)[off]);
+}
+__device__ __forceinline__ void px_st(const Img32& im, int off, float v) {
+  if (im.dtype == AST_F32) reinterpret_cast<float*>(im.ptr)[off] = v;
+  else reinterpret_cast<__nv_bfloat16*>(im.ptr)[off] = __float2bfloat16_rn(v);
+}
+
+// One 32-pixel x 32-channel accumulator chunk: v[e] = D^T[ch][pixel e] for the channel `ch` this thread owns.
+//   CW = 32: the 32 pixels are consecutive in x inside one tile row (conv_px, tw % 32 == 0);
+//   CW = 8 : they are 4 consecutive tile rows of 8 pixels (kept for tiles of 8-pixel rows; measured slower for a
+//            weight-stationary 32 x 8 variant because only cout/32 of the 4 TMEM lane quarters have epilogue warps);
+//   both: offsets are affine, o(e) = base + (e / CW) * row_step + (e % CW) * col_step, valid iff e / CW < nvr and e % CW < nvc;
+//   CW = 0 : lane e holds pixel e's offsets (out < 0 = invalid) and they are broadcast with shuffles.
+struct PxOff { int out, add, mask; };
+struct PxStep { int out_r, out_c, add_r, add_c, mask_r, mask_c; };
+template <int CW>
+__device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxStep& st, int nvr, int nvc, int ch, int lane,
+                                         float b, int flags, const Img32& add, const Img32& mask, const Img32& out,
+                                         bool want_stats, float& s1, float& s2) {
+  constexpr int W = CW ? CW : 1;
+  // idx may depend on the lane (bf16 store path): ONE shuffle / one affine evaluation per use
+#define PX_OFF(f, idx) (CW ? off.f + ((idx) / W) * st.f##_r + ((idx) % W) * st.f##_c : __shfl_sync(0xffffffffu, off.f, (idx)))
+#define PX_VALID(idx) (CW ? ((idx) / W < nvr && (idx) % W < nvc) : __shfl_sync(0xffffffffu, off.out, (idx)) >= 0)
+  if (want_stats) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float x = PX_VALID(e) ? v[e] : 0.f;
+      s1 += x; s2 = fmaf(x, x, s2);
+    }
+  }
+  // the add / mask operands of all 32 pixels are loaded up front (independent loads in flight), never interleaved
+  // with the stores: the compiler must assume out may alias them
+  if (add.ptr) {
+    float t[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int oa = PX_OFF(add, e);
+      t[e] = PX_VALID(e) ? px_ld(add, oa + ch) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] += t[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    v[e] += b;
+    if (flags & AST_CONV_RELU) v[e] = fmaxf(v[e], 0.f);
+  }
+  if (mask.ptr) {
+    float t[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int om = PX_OFF(mask, e);
+      t[e] = PX_VALID(e) ? px_ld(mask, om + ch) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = t[e] > 0.f ? v[e] : 0.f;
+  }
+  if (flags & AST_CONV_ROUND_TF32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+  }
+  if (out.dtype == AST_F32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int o = PX_OFF(out, e);
+      if (CW ? PX_VALID(e) : o >= 0) reinterpret_cast<float*>(out.ptr)[o + ch] = v[e];
+    }
+  } else {
+    // bf16: neighbouring lanes trade values so that every lane stores TWO channels (4 bytes) of one pixel: even lanes
+    // serve pixel e, odd lanes pixel e+1 -> 16 store instructions of 2 x 64 B instead of 32 of 64 B
+    const int odd = lane & 1;
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      const float mine = odd ? v[e + 1] : v[e];          // my channel, the pixel I store
+      const float give = odd ? v[e] : v[e + 1];          // my channel, the pixel the neighbour stores
+      const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+      const int o = PX_OFF(out, e + odd);
+      const bool ok = CW ? PX_VALID(e + odd) : o >= 0;
+      const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine) : __floats2bfloat162_rn(mine, got);
+      if (ok) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + o + (ch & ~1)) = pk;
+    }
+  }
+#undef PX_VALID
+#undef PX_OFF
+}
+
+inline bool img32_ok(const ast_image* im) {
+  if (!im) return true;
+  const long long span = (long long)(im->n - 1) * im->sn + (long long)(im->h - 1) * im->sh + (long long)(im->w - 1) * im->sw + im->c;
+  return im->sc == 1 && im->sn >= 0 && im->sh >= 0 && im->sw >= 0 && span < (1ll << 31);
+}
+inline Img32 to_img32(const ast_image* im) {
+  Img32 r;
+  if (!im) { r.ptr = nullptr; r.dtype = 0; r.h = r.w = r.sn = r.sh = r.sw = 0; return r; }
+  r.ptr = (char*)im->ptr; r.dtype = im->dtype; r.h = im->h; r.w = im->w;
+  r.sn = (int)im->sn; r.sh = (int)im->sh; r.sw = (int)im->sw;
+  return r;
+}
+
+
+}  // namespace ast

@@ -37,7 +37,7 @@ def read_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -52,7 +52,9 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock / throttle reasons of the samples whose timestamp falls inside [t_begin, t_end] (the sampler
+        is started before the warm-up so that it is already streaming when the timed region begins)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -61,22 +63,31 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], None, set()
+        import datetime
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx = float(f[2])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, mxv = float(f[1]), float(f[2])
             except ValueError:
                 continue
+            if t_begin is not None and not (t_begin - 0.03 <= ts <= t_end + 0.03):
+                continue
+            sm.append(clk); mx = mxv
+            try:
+                power.append(float(f[3]))
+            except ValueError:
+                pass
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
 def cpu_reference_step_rate(batch, size, steps, warmup, threads):
@@ -155,12 +166,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(W + (4 if not args.no_graph else 0)):   # graph mode: 3 eager steps + capture happen before timing
-        trainer.step(batches[i % nbuf])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(W + (4 if not args.no_graph else 0)):   # graph mode: 3 eager steps + capture happen before timing
+        trainer.step(batches[i % nbuf])
+    barrier()
+    t_begin = time.time()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -170,7 +182,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -212,7 +224,7 @@ def run_ours(args):
     conv_tf = GF_PER_IMG["conv_gather"] * scale * B / conv_ms            # GF/ms == TF/s
     peak_tf = peaks["bf16_tflops_sustained"]
     # TF32 peak is not in MEASURED_PEAKS.json: measure it the same way (cuBLAS 8192^3, best of 5).
-    # 72 % of the conv FLOPs of this mode run in TF32 (VGG + Gram backward), the rest in bf16 (TransformerNet).
+    # 42 % of the conv FLOPs of this mode run in TF32 (VGG forward + Gram backward), the rest in bf16.
     tf32_peak = None
     if rank == 0 and args.precision == "fast":
         old = torch.backends.cuda.matmul.allow_tf32
@@ -226,9 +238,11 @@ def run_ours(args):
         tf32_peak = 2 * 8192 ** 3 / best / 1e9
         torch.backends.cuda.matmul.allow_tf32 = old
         del a_, b_
-    tf32_share = (36.465 * 2 + 12.306 + 2.147) / GF_PER_IMG["conv_gather"]
+    # TF32: VGG forward on the generated batch (36.465) and on the content batch (12.306) + the Gram backward (2.147);
+    # bf16: TransformerNet forward / dgrad and, since the bf16 gradient chain, the VGG dgrad (36.465)
+    tf32_share = (36.465 + 12.306 + 2.147) / GF_PER_IMG["conv_gather"]
     mix_peak = None if not tf32_peak else 1.0 / (tf32_share / tf32_peak + (1 - tf32_share) / peaks["bf16_tflops"])
-    roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step: conv_tc_kernel + conv_ws_kernel)",
+    roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step: conv_px_kernel + conv_tc_kernel + conv_ws_kernel)",
                 "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                 "traffic": 375.0e6, "traffic_note": "dram read+write bytes of one conv_tc<tf32> launch (128->128 @128^2, "
                 "B=32) from profiles/r01b_conv_tc_ncu_full_excerpt.csv; algorithmic bytes of that launch: 537 MB",
