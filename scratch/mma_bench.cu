@@ -128,12 +128,18 @@ int main() {
   printf("%5s %5s %5s %6s %8s %12s %12s %10s %8s\n", "kind", "N", "mode", "depth", "copyKB/4", "clk/MMA", "TFLOP/s", "copy TB/s", "B/clk/SM");
   struct Cfg { int kind, n, mode, depth, copy_kb, nprod, lanes, commit_every, alt_acc, alt_ops, m; };
   std::vector<Cfg> cfgs;
+  // (a) MMA issue rate vs N and M, without / with a tcgen05.commit after every group of 4 MMAs
   for (int m : {64, 128})
-    for (int n : {64, 128, 256})
+    for (int n : {32, 64, 128, 256})
       for (int ce : {0, 1}) cfgs.push_back({0, n, 0, 8, 0, 1, 0, ce, 0, 0, m});
-  cfgs.push_back({0, 256, 3, 8, 48, 4, 1, 1, 1, 1, 128});
-  cfgs.push_back({0, 256, 3, 8, 48, 2, 1, 1, 1, 1, 128});
-  cfgs.push_back({0, 128, 3, 8, 32, 4, 1, 1, 1, 1, 128});
+  cfgs.push_back({1, 128, 0, 8, 0, 1, 0, 1, 0, 0, 128});
+  cfgs.push_back({1, 256, 0, 8, 0, 1, 0, 1, 0, 0, 128});
+  // (b) copies into shared memory issued by 1 / 2 / 4 producer lanes of one warp while the MMAs run (tiled TMA, 16 / 32 KB
+  //     per group and producer); commits go to a barrier no producer uses
+  for (int nprod : {1, 2, 3})
+    for (int copy_kb : {16, 32}) cfgs.push_back({0, 256, 3, 8, copy_kb, nprod, 1, 1, 0, 0, 128});
+  for (int nprod : {1, 2, 3})
+    cfgs.push_back({0, 256, 1, 8, 32, nprod, 1, 1, 0, 0, 128});
   for (const Cfg& c : cfgs) {
       {
         const int kind = c.kind, n = c.n, copy_kb = c.copy_kb;
