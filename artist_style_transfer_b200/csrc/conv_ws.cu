@@ -49,8 +49,10 @@ __device__ __forceinline__ unsigned long long pack_desc(unsigned lo, unsigned hi
   return d;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+// MINB = 2: built for two resident CTAs per SM (<= 102 registers): layers whose weights + patches need less than half of
+// the shared memory (the 32-channel 256^2 layers, conv1_1) are latency bound with one persistent CTA per SM.
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(WS_THREADS, MINB)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
                float* __restrict__ stats) {
@@ -331,17 +333,28 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_ws: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
   }
+  // two CTAs per SM when both fit (AST_WS_2CTA=0 disables): trim the patch ring to 3 buffers first
+  static const int two_env = [] { const char* e = getenv("AST_WS_2CTA"); return e ? atoi(e) : 1; }();
+  bool two = false;
+  if (two_env && p.w_resident) {
+    int nb = p.n_pbuf > 3 ? 3 : p.n_pbuf;
+    const size_t need = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)nb * p.patch_bytes + 8192;
+    if (2 * (need + 1024) <= 227 * 1024) { two = true; p.n_pbuf = nb; }
+  }
   const size_t smem = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)p.n_pbuf * p.patch_bytes + 8192;
-  const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  const int max_ctas = (two ? 2 : 1) * num_sms();
+  const int grid = (int)(p.total_tiles < max_ctas ? p.total_tiles : max_ctas);
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   cudaError_t e;
+#define WS_LAUNCH(K, B)                                                                                          \
+  e = cudaFuncSetAttribute(conv_ws_kernel<K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  if (e == cudaSuccess) conv_ws_kernel<K, B><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats)
   if (in->dtype == AST_BF16) {
-    e = cudaFuncSetAttribute(conv_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_ws_kernel<0><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
+    if (two) { WS_LAUNCH(0, 2); } else { WS_LAUNCH(0, 1); }
   } else {
-    e = cudaFuncSetAttribute(conv_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_ws_kernel<1><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
+    if (two) { WS_LAUNCH(1, 2); } else { WS_LAUNCH(1, 1); }
   }
+#undef WS_LAUNCH
   if (e != cudaSuccess) { set_error("conv_ws: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
