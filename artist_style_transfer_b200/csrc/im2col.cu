@@ -171,12 +171,14 @@ extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32
 // of output channel c for horizontal tap d; this kernel finishes the filter:
 //     out[n, y, x, c] = bias[c] + sum_{d < kw} part[n, y, x + d, d*C + c]
 // One block per (n, y) row: the row of partial sums is staged in shared memory with coalesced 16-byte loads.
-__global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const float* __restrict__ bias, int kw, int relu) {
+__global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const float* __restrict__ bias, int kw, int relu,
+                                                        int segw) {
   extern __shared__ float row[];
   const int n = blockIdx.x / out.h, y = blockIdx.x % out.h;
+  const int x0 = blockIdx.y * segw, nx = min(segw, out.w - x0);       // this block's output columns [x0, x0 + nx)
   const int pc = part.c, C = out.c;
-  const float4* src = reinterpret_cast<const float4*>((const float*)part.ptr + img_off(part, n, y, 0, 0));
-  const int nvec = part.w * pc / 4;                  // the row is contiguous (checked on the host)
+  const float4* src = reinterpret_cast<const float4*>((const float*)part.ptr + img_off(part, n, y, x0, 0));
+  const int nvec = (nx + kw - 1) * pc / 4;           // the row is contiguous (checked on the host)
   const int ps = pc + 1;                             // padded pixel stride: threads walk x, so pc (=32) would be a 32-way bank conflict
   for (int i = threadIdx.x; i < nvec; i += 256) {
     const float4 t = __ldg(src + i);
@@ -184,12 +186,12 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const
     dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < out.w * C; idx += 256) {
-    const int x = idx % out.w, c = idx / out.w;      // consecutive threads -> consecutive x (NCHW outputs coalesce)
+  for (int idx = threadIdx.x; idx < nx * C; idx += 256) {
+    const int x = idx % nx, c = idx / nx;            // consecutive threads -> consecutive x (NCHW outputs coalesce)
     float v = bias ? bias[c] : 0.f;
     for (int d = 0; d < kw; ++d) v += row[(x + d) * ps + d * C + c];
     if (relu) v = fmaxf(v, 0.f);
-    st_elem(out, img_off(out, n, y, x, c), v);
+    st_elem(out, img_off(out, n, y, x0 + x, c), v);
   }
 }
 
@@ -200,12 +202,14 @@ extern "C" int ast_fold_rows(const ast_image* part, const ast_image* out, const 
                 part->c >= kw * out->c, "ast_fold_rows: part must be fp32 [n, h, w+kw-1, >= kw*c]");
   AST_CHECK_ARG(part->sc == 1 && part->sw == part->c && part->c % 4 == 0 && part->sh % 4 == 0 && part->sn % 4 == 0 &&
                 ((uintptr_t)part->ptr & 15) == 0, "ast_fold_rows: part rows must be dense and 16-byte aligned");
-  const size_t smem = (size_t)part->w * (part->c + 1) * sizeof(float);
-  AST_CHECK_ARG(smem <= 200 * 1024, "ast_fold_rows: row of %zu bytes does not fit shared memory", smem);
+  const int segw = out->w < 256 ? out->w : 256;      // output columns per block (wide rows are split into segments)
+  const size_t smem = (size_t)(segw + kw - 1) * (part->c + 1) * sizeof(float);
+  AST_CHECK_ARG(smem <= 200 * 1024, "ast_fold_rows: segment of %zu bytes does not fit shared memory", smem);
   if ((long long)out->n * out->h * out->w * out->c == 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(fold_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("ast_fold_rows: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
-  fold_rows_kernel<<<out->n * out->h, 256, smem, (cudaStream_t)stream>>>(to_img(part), to_img(out), bias, kw, relu);
+  dim3 grid((unsigned)(out->n * out->h), (unsigned)((out->w + segw - 1) / segw));
+  fold_rows_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(to_img(part), to_img(out), bias, kw, relu, segw);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;

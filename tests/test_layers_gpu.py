@@ -168,11 +168,12 @@ def test_thin_layers_fast_mode(ast, cin, cout, k, norm, h, w):
         assert rel(layer.conv_layer.bias.grad, P["conv_layer.bias"].grad) < 1e-4
 
 
-def test_fold_rows_matches_direct_sum():
+@pytest.mark.parametrize("w", [13, 300])          # 300: wider than one 256-column block segment
+def test_fold_rows_matches_direct_sum(w):
     """ast_fold_rows: out[n,y,x,c] = bias[c] + sum_d part[n,y,x+d,d*C+c] (NCHW output view, optional ReLU)."""
     from artist_style_transfer_b200 import ops
     torch.manual_seed(5)
-    n, h, w, c, k = 2, 7, 13, 3, 9
+    n, h, c, k = 2, 7, 3, 9
     part = torch.randn(n, h, w + k - 1, 32, device="cuda")
     bias = torch.randn(c, device="cuda")
     out = torch.empty(n, c, h, w, device="cuda")
