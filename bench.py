@@ -90,6 +90,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def _finish(world):
+    """Multi-rank runs leave through os._exit: tearing down an NCCL communicator whose collectives were captured in a
+    (still alive) CUDA graph blocked both ranks for minutes at interpreter exit on the B200 boxes."""
+    if world > 1:
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
+
 def cpu_reference_step_rate(batch, size, steps, warmup, threads):
     """The reference's training step (oracle port of train_cnn.py:295-334 + Adam) on the host cores."""
     import torch
@@ -244,8 +252,8 @@ def run_ours(args):
     mix_peak = None if not tf32_peak else 1.0 / (tf32_share / tf32_peak + (1 - tf32_share) / peaks["bf16_tflops"])
     roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step: conv_px_kernel + conv_tc_kernel + conv_ws_kernel)",
                 "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
-                "traffic": 375.0e6, "traffic_note": "dram read+write bytes of one conv_tc<tf32> launch (128->128 @128^2, "
-                "B=32) from profiles/r01b_conv_tc_ncu_full_excerpt.csv; algorithmic bytes of that launch: 537 MB",
+                "traffic": 491.8e6, "traffic_note": "dram read+write bytes of one conv_px<tf32> launch (128->128 @128^2, "
+                "B=32) from profiles/r01f_conv_px_ncu_full_excerpt.csv; algorithmic bytes of that launch: 537 MB",
                 "peak_source": f"{peaks['src']} bf16 sustained", "launch_ms_avg": conv_ms / max(1.0, conv_launches),
                 "tf32_tflops_measured": tf32_peak, "tf32_flop_share": tf32_share,
                 "frac_of_precision_mix_peak": None if not mix_peak else conv_tf / mix_peak}
@@ -256,9 +264,11 @@ def run_ours(args):
                    "achieved": in_gb / (in_ms / 1e3), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": in_gb / (in_ms / 1e3) / peaks["hbm_gbs"], "traffic": None}
 
+    if world > 1:                      # everyone is done with the GPU work; from here on only rank 0 has something to do
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -283,8 +293,7 @@ def run_ours(args):
         "tensor_frac_whole_step": GF_PER_IMG["total"] * scale * B * K / ms / peak_tf,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def main():
