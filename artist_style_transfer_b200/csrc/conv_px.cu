@@ -29,6 +29,7 @@ struct PxParams {
   int cout, flags;                 // cout = weight rows per tap (64 or 128)
   int w_rows_per_img;
   int stages, w_bytes, a_bytes, stage_bytes, rowb;
+  int w_res, w_res_bytes, w_tile_bytes;   // weights resident in smem: all (tap, cin-chunk) tiles loaded once per CTA
   int pairs_per_img;
   unsigned idesc, layout_type, sbo;
   long long total_pairs;
@@ -42,9 +43,10 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
                float* __restrict__ stats) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long full_bar[PX_MAX_STAGES], empty_bar[PX_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) unsigned long long full_bar[PX_MAX_STAGES], empty_bar[PX_MAX_STAGES], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ unsigned tmem_slot;
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_w = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // resident weights (if any)
+  unsigned char* smem = smem_w + p.w_res_bytes;                                                // the stage ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksteps = p.ntaps * p.kchunks;
 
@@ -53,6 +55,7 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
+    mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -67,7 +70,16 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   if (warp == 0) {
     // ============================ TMA producers (lanes 0..PX_PRODUCERS-1 take the stages round-robin) ============
-    if (lane < PX_PRODUCERS) {
+    if (lane == 0 && p.w_res) {            // the whole packed filter, once per CTA: tile (t, kc) = cout rows
+      mbar_expect_tx(&wbar, (unsigned)(p.ntaps * p.kchunks * p.w_tile_bytes));
+      for (int t = 0; t < p.ntaps; ++t)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(smem_w + (size_t)(t * p.kchunks + kc) * p.w_tile_bytes, &tm_w, &wbar, kc * p.kc, t * p.cout);
+    }
+    // a lane must never run two ring cycles ahead of the consumer (the 1-bit mbarrier parity would alias): at most
+    // `stages` lanes take part, then consecutive items of one lane are <= one cycle apart
+    const int nprod = p.stages < PX_PRODUCERS ? p.stages : PX_PRODUCERS;
+    if (lane < nprod) {
       int s = 0, turn = 0; unsigned ph = 0;
       for (long long pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
         const int img = (int)(pair / p.pairs_per_img);
@@ -84,11 +96,11 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
               mbar_wait(&empty_bar[s], ph ^ 1);
               unsigned char* sw = smem + (size_t)s * p.stage_bytes;
               mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
-              tma_load_2d(sw, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
+              if (!p.w_res) tma_load_2d(sw, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
               tma_load_4d(sw + p.w_bytes, &tm_in, &full_bar[s], kc * p.kc, x0 + p.dx[t], y0 + p.dy[t], img);
               tma_load_4d(sw + p.w_bytes + p.a_bytes, &tm_in, &full_bar[s], kc * p.kc, x1 + p.dx[t], y1 + p.dy[t], img);
             }
-            if (++turn == PX_PRODUCERS) turn = 0;
+            if (++turn == nprod) turn = 0;
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -99,6 +111,8 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
     const int kmma = p.rowb / 32;
     const unsigned desc_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
+    if (p.w_res) mbar_wait(&wbar, 0);
+    const unsigned wres_addr = smem_u32(smem_w);
     for (long long pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
@@ -108,7 +122,9 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         tc_fence_after();
         if (lane == 0) {
           const unsigned w_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const unsigned a_lo = ((w_addr & 0x3FFFFu) >> 4) | (1u << 16);                   // A operand: weights
+          // A operand: weights - this stage's box, or the resident tile of (tap, cin-chunk) = ks (ks runs tap-major)
+          const unsigned a_src = p.w_res ? wres_addr + (unsigned)ks * (unsigned)p.w_tile_bytes : w_addr;
+          const unsigned a_lo = ((a_src & 0x3FFFFu) >> 4) | (1u << 16);
           const unsigned b_lo = (((w_addr + p.w_bytes) & 0x3FFFFu) >> 4) | (1u << 16);      // B operand: 256 pixels
           tc_mma<KIND>(d_tmem, pack_desc64(a_lo, desc_hi), pack_desc64(b_lo, desc_hi), p.idesc, ks > 0 ? 1u : 0u);
           tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 2, desc_hi), pack_desc64(b_lo + 2, desc_hi), p.idesc, 1u);
@@ -200,7 +216,7 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 // mode: AST_CONV_PX env (0 off, 1 default).  The caller has validated pointers / alignment (conv_gather_tc).
 int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
-                   cudaStream_t stream) {
+                   bool resident_only, cudaStream_t stream) {
   if (thin || (cpad != 64 && cpad != 128) || out->c != cpad) return 0;
   if (!img32_ok(out) || !img32_ok(add) || !img32_ok(mask)) return 0;
   const int esz = in->dtype == AST_F32 ? 4 : 2;
@@ -226,8 +242,24 @@ int conv_gather_px(const ast_image* in, const void* weights, const float* bias, 
   }
   p.w_bytes = 128 * p.rowb;          // always a 128-row box: rows >= cout belong to the next tap (or are OOB zeros) and only
   p.a_bytes = 128 * p.rowb;          // feed accumulator lanes that the epilogue ignores
+  // Resident weights (opt-in, AST_PX_RESIDENT=1): if the whole packed filter fits next to >= 2 pixel stages, it is loaded
+  // once per persistent CTA and a stage carries only the two pixel tiles (32 KB instead of 48 KB from L2 per 4 MMAs).
+  // The M = 128 read of the last tile runs up to 128 - cout rows into the first stage: finite data, ignored lanes.
+  // Measured (B=32, 256^2 step): slower than conv_ws for every layer it applies to - the 64->64 TF32 filter leaves room
+  // for only 2 stages (latency bound), and with cout = 64 only 4 of the 8 epilogue warps have a TMEM lane quarter to
+  // drain, which makes the masked VGG dgrads epilogue bound (0.38 -> 0.83 ms) - hence off by default.
+  static const int res_env = [] { const char* e = getenv("AST_PX_RESIDENT"); return e ? atoi(e) : 0; }();
+  p.w_tile_bytes = cpad * p.rowb;
+  p.w_res = 0; p.w_res_bytes = 0;
+  if (res_env && !g->w_img_stride) {
+    const int wb = (p.ntaps * p.kchunks * p.w_tile_bytes + 1023) & ~1023;
+    if (wb + 2 * 2 * p.a_bytes + 1024 <= 225 * 1024) { p.w_res = 1; p.w_res_bytes = wb; }
+  }
+  if (resident_only && !p.w_res) return 0;
+  if (p.w_res) p.w_bytes = 0;        // a stage then holds only the two pixel tiles
   p.stage_bytes = p.w_bytes + 2 * p.a_bytes;
-  p.stages = (200 * 1024) / p.stage_bytes;
+  p.stages = (225 * 1024 - 1024 - p.w_res_bytes) / p.stage_bytes;
+  if (!p.w_res && p.stages > (200 * 1024) / p.stage_bytes) p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > PX_MAX_STAGES) p.stages = PX_MAX_STAGES;
   p.layout_type = p.rowb == 128 ? 2u : 4u;
   p.sbo = 8u * p.rowb;
@@ -252,13 +284,13 @@ int conv_gather_px(const ast_image* in, const void* weights, const float* bias, 
     const long long rows = (long long)g->ntaps * cpad * (g->w_img_stride ? in->n : 1);
     cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
-    cuuint32_t box[2] = {(cuuint32_t)p.kc, 128};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)(p.w_res ? cpad : 128)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_px: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.w_res_bytes + (size_t)p.stages * p.stage_bytes + 1024;
   const int grid = (int)(p.total_pairs < num_sms() ? p.total_pairs : num_sms());
   cudaError_t e;
   if (in->dtype == AST_BF16) {

@@ -132,8 +132,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // TC_PRODUCERS lanes take the pipeline stages round-robin: ONE issuing thread sustains only ~45 B/clk (a wait +
     // expect_tx + two TMA instructions cost it ~750 cycles), four reach the ~80 B/clk an SM can pull from L2
     // (scratch/mma_bench.cu, profiles/r01_summary.md).
+    // (at most `stages` lanes: a lane running two ring cycles ahead would alias the 1-bit mbarrier parity)
     int s = 0, turn = 0; unsigned ph = 0;
-    if (lane < TC_PRODUCERS)
+    const int nprod = p.stages < TC_PRODUCERS ? p.stages : TC_PRODUCERS;
+    if (lane < nprod)
     for (long long tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
       long long r = tile;
       const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
@@ -173,7 +175,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
               tma_load_2d_2sm(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
             }
           }
-          if (++turn == TC_PRODUCERS) turn = 0;
+          if (++turn == nprod) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -292,7 +294,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
                    cudaStream_t stream);   // conv_ws.cu: 1 = launched, 0 = not applicable
 int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
-                   cudaStream_t stream);   // conv_px.cu: 1 = launched, 0 = not applicable
+                   bool resident_only, cudaStream_t stream);   // conv_px.cu: 1 = launched, 0 = not applicable
 int tc_capabilities() { return 3; }   // 1 = conv_tc.cu, 2 = contract_tc.cu (both are always built together)
 
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
@@ -317,14 +319,14 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
-  // AST_CONV_PX: 0 = off, 1 (default) = pixels-as-N kernel for cout 64/128 where the weight-stationary kernel does not
-  // apply, 2 = also ahead of the weight-stationary kernel
+  // AST_CONV_PX: 0 = off, 1 (default) = pixels-as-N kernel for cout 64/128: its resident-weight form ahead of the
+  // weight-stationary kernel, its streaming form after it; 2 = always ahead of the weight-stationary kernel
   static const int px_mode = [] { const char* e = getenv("AST_CONV_PX"); return e ? atoi(e) : 1; }();
-  if (px_mode == 2)
-    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
+  if (px_mode >= 1)     // resident-weight form first (mode 2: any form)
+    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, px_mode == 1, stream)) return pr == 1 ? 0 : pr;
   if (int wr = conv_gather_ws(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return wr == 1 ? 0 : wr;
   if (px_mode == 1)
-    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
+    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, false, stream)) return pr == 1 ? 0 : pr;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
