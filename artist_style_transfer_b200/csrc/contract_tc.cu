@@ -27,6 +27,7 @@ struct CtParams {
   float scale;
   int stages, box_bytes, stage_bytes, umma_k_bytes, kmma, upper_only;
   int tg, ngroups;                  // taps handled by one CTA (rows operand loaded once per stage for all of them)
+  int same;                         // Gram: rows and cols are the SAME tensor at the same pixels (see shared_r below)
   unsigned sbo, layout_type;
   unsigned idesc;
   short dy[AST_MAX_TAPS];
@@ -95,6 +96,9 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
   const unsigned tmem_base = tmem_slot;
   const int m0 = mb_idx * 128, n0 = nb_idx * p.bn;
   const int r_bytes = p.m_boxes * p.box_bytes;
+  // Gram blocks whose (valid) row channels lie inside the column channel range read the A operand straight out of the
+  // column boxes: no second TMA load of the same pixels (rows past m_valid read whatever follows and are ignored)
+  const bool shared_r = p.same && m0 >= n0 && min(m0 + 128, p.m_valid) <= n0 + p.bn;
 
   if (warp == 0) {
     int s = 0; unsigned ph = 0;
@@ -108,9 +112,10 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (lane == 0) {
         unsigned char* sr = smem + (size_t)s * p.stage_bytes;
-        mbar_expect_tx(&full_bar[s], (unsigned)((p.m_boxes + nt * p.n_boxes) * p.box_bytes));
-        for (int b = 0; b < p.m_boxes; ++b)
-          tma_load_4d(sr + b * p.box_bytes, &tm_r, &full_bar[s], m0 + b * p.cb, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
+        mbar_expect_tx(&full_bar[s], (unsigned)(((shared_r ? 0 : p.m_boxes) + nt * p.n_boxes) * p.box_bytes));
+        if (!shared_r)
+          for (int b = 0; b < p.m_boxes; ++b)
+            tma_load_4d(sr + b * p.box_bytes, &tm_r, &full_bar[s], m0 + b * p.cb, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
         for (int u = 0; u < nt; ++u)
           for (int b = 0; b < p.n_boxes; ++b)
             tma_load_4d(sr + r_bytes + (u * p.n_boxes + b) * p.box_bytes, &tm_c, &full_bar[s], n0 + b * p.cb,
@@ -126,14 +131,15 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
-        const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const unsigned stage_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const unsigned a_addr = shared_r ? stage_addr + r_bytes + (unsigned)((m0 - n0) / p.cb) * p.box_bytes : stage_addr;
         // consecutive taps sit in consecutive column blocks (LBO apart) and in consecutive TMEM columns, so up to
         // 256 / bn taps go into ONE MMA: an N = 256 instruction costs 128 cycles, an N <= 128 one ~104 (mma_bench)
         const int gsz = p.bn <= 128 ? 256 / p.bn : 1;
         for (int u = 0; u < nt; u += gsz) {
           const int nu = min(gsz, nt - u);
           const unsigned idesc = (p.idesc & ~(0x3Fu << 17)) | ((unsigned)((nu * p.bn) >> 3) << 17);
-          const unsigned b_addr = a_addr + r_bytes + u * p.n_boxes * p.box_bytes;
+          const unsigned b_addr = stage_addr + r_bytes + u * p.n_boxes * p.box_bytes;
           for (int k = 0; k < p.kmma; ++k) {
             const unsigned long long ad = make_mn_desc(a_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
             const unsigned long long bd = make_mn_desc(b_addr + k * p.umma_k_bytes, p.box_bytes, p.sbo, p.layout_type);
@@ -460,6 +466,8 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
     p.ngroups = (ntaps + tg_max - 1) / tg_max;
     p.tg = (ntaps + p.ngroups - 1) / p.ngroups;       // balance the groups
   }
+  p.same = (rows->ptr == cols->ptr && rows->c == cols->c && rows->sn == cols->sn && rows->sh == cols->sh &&
+            rows->sw == cols->sw && r_s == c_s && r_oy == 0 && r_ox == 0 && ntaps == 1 && p.dy[0] == 0 && p.dx[0] == 0) ? 1 : 0;
   p.stage_bytes = (p.m_boxes + p.tg * p.n_boxes) * p.box_bytes;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
@@ -481,7 +489,8 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   alignas(64) CUtensorMap tm_r, tm_c;
   if (int e = encode_operand(encode, &tm_r, rows, p.cb, p.tw, p.th, r_s)) return e;
   if (int e = encode_operand(encode, &tm_c, cols, p.cb, p.tw, p.th, c_s)) return e;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  // + m_boxes: a shared A operand (Gram) may read up to m_boxes boxes past the column boxes of the last stage
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (p.same ? (size_t)p.m_boxes * p.box_bytes : 0);
   dim3 grid((unsigned)(p.ksplit * (p.per_img ? p.n_img : 1)), p.ngroups, p.m_blocks * p.n_blocks);
   cudaError_t e;
   if (rows->dtype == AST_BF16) {

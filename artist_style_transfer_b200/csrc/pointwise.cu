@@ -175,6 +175,32 @@ __global__ void __launch_bounds__(NT) mask_add_kernel(Img a, Img b, Img mask, Im
   }
 }
 
+// 4 channels per thread (16 B fp32 / 8 B bf16 accesses); mixed dtypes allowed
+__global__ void __launch_bounds__(NT) mask_add_vec_kernel(Img a, Img b, Img mask, Img out) {
+  const int lanes = a.c / 4;
+  const long long total = (long long)a.n * a.h * a.w * lanes;
+  for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+    const int c = (int)(idx % lanes) * 4;
+    long long r = idx / lanes;
+    const int xx = (int)(r % a.w); r /= a.w;
+    const int y = (int)(r % a.h);
+    const int n = (int)(r / a.h);
+    float v[4], t[4];
+    ld4_img(a, img_off(a, n, y, xx, c), v);
+    if (b.ptr) {
+      ld4_img(b, img_off(b, n, y, xx, c), t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] += t[e];
+    }
+    if (mask.ptr) {
+      ld4_img(mask, img_off(mask, n, y, xx, c), t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = t[e] > 0.f ? v[e] : 0.f;
+    }
+    st4_img(out, img_off(out, n, y, xx, c), v);
+  }
+}
+
 static bool vec_ok(const ast_image* x) {
   return x->sc == 1 && x->c % 4 == 0 && x->sw % 4 == 0 && x->sh % 4 == 0 && x->sn % 4 == 0;
 }
@@ -265,7 +291,10 @@ extern "C" int ast_mask_add(const ast_image* a, const ast_image* b, const ast_im
   AST_CHECK_ARG(same_shape(a, out) && (!b || same_shape(b, a)) && (!mask || same_shape(mask, a)), "ast_mask_add: shape mismatch");
   const long long total = (long long)a->n * a->h * a->w * a->c;
   if (total == 0) return 0;
-  mask_add_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
+  if (vec_ok(a) && vec_ok(out) && (!b || vec_ok(b)) && (!mask || vec_ok(mask)))
+    mask_add_vec_kernel<<<blocks_for(total / 4), NT, 0, (cudaStream_t)stream>>>(to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
+  else
+    mask_add_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
