@@ -20,6 +20,7 @@ struct P {
   int lanes;                     // 1: the producers are lanes 0..nprod-1 of ONE warp instead of lane 0 of nprod warps
   int commit_every;              // tcgen05.commit after every commit_every groups of 4 MMAs (0 = never)
   int alt_acc, alt_ops;          // alternate the accumulator / the A operand address between groups
+  int rand;                      // random operand bits instead of zeros
   int nprod;                     // producer warps (1..4), each issuing iters/nprod groups
   unsigned idesc;
   const char* src;
@@ -32,7 +33,13 @@ __global__ void __launch_bounds__(160, 1) mma_loop(const __grid_constant__ CUten
   __shared__ unsigned tmem_slot;
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < (16384 + 32768 + 4 * 32768) / 16; i += blockDim.x) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (16384 + 32768 + 4 * 32768) / 16; i += blockDim.x) {
+    // p.rand: pseudo-random finite bf16 / tf32 bit patterns (small magnitudes) instead of zeros
+    unsigned h = (unsigned)i * 2654435761u + blockIdx.x * 97u;
+    unsigned a0 = p.rand ? (0x3c003c00u ^ ((h * 1664525u + 1013904223u) & 0x83ff83ffu)) : 0u;
+    unsigned a1 = p.rand ? (0x3c003c00u ^ ((h * 22695477u + 1u) & 0x83ff83ffu)) : 0u;
+    ((uint4*)smem)[i] = make_uint4(a0, a1, a0 ^ 0x00110011u, a1 ^ 0x01010101u);
+  }
   if (threadIdx.x == 0) {
     mbar_init(&done_bar, 1);
     for (int w = 0; w < 4; ++w) for (int i = 0; i < 8; ++i) mbar_init(&copy_bar[w][i], 1);
@@ -126,25 +133,17 @@ int main() {
   cudaFuncSetAttribute(mma_loop<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   printf("SMs %d, clock %d kHz\n", sms, khz);
   printf("%5s %5s %5s %6s %8s %12s %12s %10s %8s\n", "kind", "N", "mode", "depth", "copyKB/4", "clk/MMA", "TFLOP/s", "copy TB/s", "B/clk/SM");
-  struct Cfg { int kind, n, mode, depth, copy_kb, nprod, lanes, commit_every, alt_acc, alt_ops, m; };
+  struct Cfg { int kind, n, mode, depth, copy_kb, nprod, lanes, commit_every, alt_acc, alt_ops, m, rand; };
   std::vector<Cfg> cfgs;
-  // (a) MMA issue rate vs N and M, without / with a tcgen05.commit after every group of 4 MMAs
-  for (int m : {64, 128})
-    for (int n : {32, 64, 128, 256})
-      for (int ce : {0, 1}) cfgs.push_back({0, n, 0, 8, 0, 1, 0, ce, 0, 0, m});
-  cfgs.push_back({1, 128, 0, 8, 0, 1, 0, 1, 0, 0, 128});
-  cfgs.push_back({1, 256, 0, 8, 0, 1, 0, 1, 0, 0, 128});
-  // (b) copies into shared memory issued by 1 / 2 / 4 producer lanes of one warp while the MMAs run (tiled TMA, 16 / 32 KB
-  //     per group and producer); commits go to a barrier no producer uses
-  for (int nprod : {1, 2, 3})
-    for (int copy_kb : {16, 32}) cfgs.push_back({0, 256, 3, 8, copy_kb, nprod, 1, 1, 0, 0, 128});
-  for (int nprod : {1, 2, 3})
-    cfgs.push_back({0, 256, 1, 8, 32, nprod, 1, 1, 0, 0, 128});
+  for (int rnd : {0, 1})
+    for (int kind : {0, 1})
+      for (int n : {128, 256}) cfgs.push_back({kind, n, 0, 8, 0, 1, 0, 1, 1, 1, 128, rnd});
+  for (int rnd : {0, 1}) cfgs.push_back({0, 256, 3, 8, 32, 3, 1, 1, 1, 1, 128, rnd});
   for (const Cfg& c : cfgs) {
       {
         const int kind = c.kind, n = c.n, copy_kb = c.copy_kb;
         P p;
-        p.mode = c.mode; p.depth = c.depth; p.nprod = c.nprod; p.lanes = c.lanes; p.commit_every = c.commit_every; p.alt_acc = c.alt_acc; p.alt_ops = c.alt_ops;
+        p.mode = c.mode; p.depth = c.depth; p.nprod = c.nprod; p.lanes = c.lanes; p.commit_every = c.commit_every; p.rand = c.rand; p.alt_acc = c.alt_acc; p.alt_ops = c.alt_ops;
         p.n = n; p.iters = 20000; p.kind = kind; p.copy_kb = copy_kb; p.src = src;
         const unsigned fmt = kind ? 2u : 1u;
         p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(n >> 3) << 17) | (((unsigned)c.m >> 4) << 24);
@@ -164,8 +163,8 @@ int main() {
         avg /= sms; cavg /= sms;
         const double mmas = 4.0 * p.iters;
         const double groups = (double)(p.iters / p.nprod);
-        printf("%5s M=%3d N=%3d commit/%d altacc %d altops %d mode %d lanes %d nprod %d copy %2d KB/group | MMA %6.1f clk/MMA | producer %7.1f clk/group -> %6.1f B/clk/SM | kernel %.3f ms\n",
-               kind ? "tf32" : "bf16", c.m, n, c.commit_every, c.alt_acc, c.alt_ops, c.mode, c.lanes, c.nprod, copy_kb, n ? avg / mmas : 0.0, copy_kb ? cavg / groups : 0.0,
+        printf("rand %d %5s M=%3d N=%3d commit/%d altacc %d altops %d mode %d lanes %d nprod %d copy %2d KB/group | MMA %6.1f clk/MMA | producer %7.1f clk/group -> %6.1f B/clk/SM | kernel %.3f ms\n",
+               c.rand, kind ? "tf32" : "bf16", c.m, n, c.commit_every, c.alt_acc, c.alt_ops, c.mode, c.lanes, c.nprod, copy_kb, n ? avg / mmas : 0.0, copy_kb ? cavg / groups : 0.0,
                copy_kb ? copy_kb * 1024.0 * p.nprod / (cavg / groups) : 0.0, ms);
       }
   }
