@@ -265,7 +265,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
           if (stats) tc_epi_stats(v, valid, stats + ((long long)img * p.cout_valid + co) * 2, lane);
-          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
+          // (a mask prefetch like conv_ws's was tried here: the extra registers slowed the unmasked layers more than
+          // the masked deep VGG dgrads gained)
+          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
+                                  v, false);
         }
       }
       tc_fence_before();

@@ -217,6 +217,9 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const int i = ti * WS_TH + ty, j = tj * WS_TW + tx;
       const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
       const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
+      float pm[32];                                   // mask of this warp's first chunk, loaded while the MMAs still run
+      const bool use_pm = MINB == 1 && mask.ptr && !p.thin && cpar * 32 < p.bn;   // (the 2-CTA build has no registers to spare)
+      if (use_pm) tc_epi_prefetch_mask(mask, img, oy, ox, nt * p.bn + cpar * 32, valid, pm);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
@@ -230,7 +233,8 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
           if (stats) tc_epi_stats(v, valid, stats + ((long long)img * p.cout_valid + co) * 2, lane);
-          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane);
+          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
+                                  pm, use_pm && c0 == cpar * 32);
         }
       }
       tc_fence_before();

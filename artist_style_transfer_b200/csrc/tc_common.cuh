@@ -211,10 +211,19 @@ __device__ __forceinline__ void tc_epi_row_offsets(long long my_off, int lane, b
   }
 }
 
+// 32 mask values of (pixel, channels co .. co+31): issued BEFORE the epilogue waits for the accumulator so that their
+// latency hides behind the MMAs of the tile (the masked VGG dgrads spent 40 % of their time on these loads)
+__device__ __forceinline__ void tc_epi_prefetch_mask(const Img& mask, int img, int oy, int ox, int co, bool valid, float* m) {
+  if (!mask.ptr || !valid) return;
+  const long long o = img_off(mask, img, oy, ox, co);
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) ld4_img(mask, o + e, m + e);
+}
+
 __device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int img, int oy, int ox, bool valid, int cout,
                                                         int flags, const float* __restrict__ bias, const Img& add,
                                                         const Img& mask, const Img& out, const EpiRows& rows,
-                                                        unsigned char* stage, int lane) {
+                                                        unsigned char* stage, int lane, const float* pre_mask, bool have_pre) {
   if (co >= cout) return;                                   // uniform
   if (valid) {
     if (bias) {
@@ -233,7 +242,10 @@ __device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int im
 #pragma unroll
       for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
     }
-    if (mask.ptr) {
+    if (mask.ptr && have_pre) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = pre_mask[e] > 0.f ? v[e] : 0.f;
+    } else if (mask.ptr) {
       const long long o = img_off(mask, img, oy, ox, co);
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
