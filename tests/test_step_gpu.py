@@ -250,3 +250,30 @@ def test_cuda_graph_step_matches_eager(ast):
     for pa, pb in zip(res[False][1], res[True][1]):
         assert torch.isfinite(pb).all()
         assert float((pa - pb).abs().max()) <= 2 * 6 * 1e-3 + 1e-6
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_prefetch_pipeline_matches_direct_steps(ast, graph):
+    """PerceptualTrainer.prefetch(): pinned host batches copied on a side stream one step ahead give the same losses as
+    handing device tensors to step() (the overlap must not reorder or drop a batch)."""
+    host = [weights.content_batch(2, 64, 2, step=i).pin_memory() for i in range(6)]
+    res = {}
+    for mode in ("direct", "prefetch"):
+        net, vgg = build(ast, "fast")
+        style = ast.style_grams_single(vgg, weights.style_image(64, 2).cuda(), 2)
+        tr = ast.PerceptualTrainer(net, vgg, style, lr=1e-3, cuda_graph=graph)
+        losses = []
+        if mode == "direct":
+            for h in host:
+                losses.append(tuple(float(v) for v in tr.step(h.cuda())))
+        else:
+            nxt = tr.prefetch(host[0])
+            for i in range(len(host)):
+                cur = nxt
+                if i + 1 < len(host):
+                    nxt = tr.prefetch(host[i + 1])
+                losses.append(tuple(float(v) for v in tr.step(cur)))
+        res[mode] = losses
+    for a, b in zip(res["direct"], res["prefetch"]):
+        np.testing.assert_allclose(np.array(a), np.array(b), rtol=2e-3)
+    assert res["prefetch"][3] != res["prefetch"][4]
