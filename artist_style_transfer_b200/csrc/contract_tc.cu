@@ -53,6 +53,7 @@ template <int KIND>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c, const CtParams p,
                    float* __restrict__ out, const int* __restrict__ tap_off) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
   __shared__ unsigned tmem_slot;
@@ -208,6 +209,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
 
 // fills the strict lower triangle of each C x C matrix from the upper one
 __global__ void mirror_upper_kernel(float* __restrict__ g, int c, long long total) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % c);
     const int i = (int)((idx / c) % c);
@@ -261,6 +263,7 @@ constexpr int THIN_BOX = THIN_KP * 64;         // bytes per box
 __global__ void __launch_bounds__(CT_THREADS, 1)
 contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c,
                      const CtThinParams p, float* __restrict__ out, const int* __restrict__ tap_off) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
   __shared__ unsigned tmem_slot;
@@ -410,7 +413,7 @@ static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, i
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   cudaError_t e = cudaFuncSetAttribute(contract_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("contract_thin: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
-  contract_thin_kernel<<<grid, CT_THREADS, smem, stream>>>(tm_r, tm_c, p, out, tap_off);
+  launch_k(contract_thin_kernel, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 1;
@@ -495,10 +498,10 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   cudaError_t e;
   if (rows->dtype == AST_BF16) {
     e = cudaFuncSetAttribute(contract_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) contract_tc_kernel<0><<<grid, CT_THREADS, smem, stream>>>(tm_r, tm_c, p, out, tap_off);
+    if (e == cudaSuccess) launch_k(contract_tc_kernel<0>, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off);
   } else {
     e = cudaFuncSetAttribute(contract_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) contract_tc_kernel<1><<<grid, CT_THREADS, smem, stream>>>(tm_r, tm_c, p, out, tap_off);
+    if (e == cudaSuccess) launch_k(contract_tc_kernel<1>, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off);
   }
   if (e != cudaSuccess) { set_error("contract_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
@@ -514,7 +517,7 @@ int gram_tc(const ast_image* x, float* g, float scale, cudaStream_t s) {
   const long long total = (long long)x->n * x->c * x->c;
   long long blocks = (total + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  mirror_upper_kernel<<<(int)blocks, 256, 0, s>>>(g, x->c, total);
+  launch_k(mirror_upper_kernel, (int)blocks, 256, 0, s, g, x->c, total);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(PX_THREADS, 1)
 conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const PxParams p,
                const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
                float* __restrict__ stats) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[PX_MAX_STAGES], empty_bar[PX_MAX_STAGES], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ unsigned tmem_slot;
@@ -295,10 +296,10 @@ int conv_gather_px(const ast_image* in, const void* weights, const float* bias, 
   cudaError_t e;
   if (in->dtype == AST_BF16) {
     e = cudaFuncSetAttribute(conv_px_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_px_kernel<0><<<grid, PX_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+    if (e == cudaSuccess) launch_k(conv_px_kernel<0>, grid, PX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
   } else {
     e = cudaFuncSetAttribute(conv_px_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_px_kernel<1><<<grid, PX_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+    if (e == cudaSuccess) launch_k(conv_px_kernel<1>, grid, PX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
   }
   if (e != cudaSuccess) { set_error("conv_px: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const TcParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
                float* __restrict__ stats) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ unsigned tmem_slot;
@@ -421,10 +422,10 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   }
   if (in->dtype == AST_BF16) {
     e = cudaFuncSetAttribute(conv_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<0, 1><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
+    if (e == cudaSuccess) launch_k(conv_tc_kernel<0, 1>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   } else {
     e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_tc_kernel<1, 1><<<grid, TC_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
+    if (e == cudaSuccess) launch_k(conv_tc_kernel<1, 1>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   }
   if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(WS_THREADS, MINB)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
                float* __restrict__ stats) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ __align__(8) unsigned long long wfull[WS_MAX_WBUF], wempty[WS_MAX_WBUF];
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(WSX_THREADS, 1)
 conv_wsx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
                 const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
                 float* __restrict__ stats) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ unsigned tmem_slot;
@@ -525,10 +527,10 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
     cudaError_t ex;
     if (in->dtype == AST_BF16) {
       ex = cudaFuncSetAttribute(conv_wsx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
-      if (ex == cudaSuccess) conv_wsx_kernel<0><<<grid_x, WSX_THREADS, smem_x, stream>>>(tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+      if (ex == cudaSuccess) launch_k(conv_wsx_kernel<0>, grid_x, WSX_THREADS, smem_x, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
     } else {
       ex = cudaFuncSetAttribute(conv_wsx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
-      if (ex == cudaSuccess) conv_wsx_kernel<1><<<grid_x, WSX_THREADS, smem_x, stream>>>(tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+      if (ex == cudaSuccess) launch_k(conv_wsx_kernel<1>, grid_x, WSX_THREADS, smem_x, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
     }
     if (ex != cudaSuccess) { set_error("conv_wsx: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ex)); return (int)ex; }
     count_launch();
@@ -550,7 +552,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   cudaError_t e;
 #define WS_LAUNCH(K, B)                                                                                          \
   e = cudaFuncSetAttribute(conv_ws_kernel<K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-  if (e == cudaSuccess) conv_ws_kernel<K, B><<<grid, WS_THREADS, smem, stream>>>(tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats)
+  if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats)
   if (in->dtype == AST_BF16) {
     if (two) { WS_LAUNCH(0, 2); } else { WS_LAUNCH(0, 1); }
   } else {

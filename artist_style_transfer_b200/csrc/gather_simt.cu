@@ -28,6 +28,7 @@ template <typename TI>
 __global__ void __launch_bounds__(256)
 conv_gather_simt_kernel(Img in, const TI* __restrict__ wts, const float* __restrict__ bias,
                         const float* __restrict__ in_shift, Img add, Img mask, Img out, GeomDev g) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
 
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256)
 wgrad_gather_simt_kernel(Img x, Img gout, float* __restrict__ dw, const int* __restrict__ tap_off,
                          long long s_co, long long s_ci, GeomDev g, int nci_tiles, long long chunk,
                          long long dw_img_stride, int ksplit, float scale) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   __shared__ __align__(16) float Ys[BK][BN + 4];
   __shared__ __align__(16) float Xs[BK][BM + 4];
   const int tid = threadIdx.x;
@@ -273,6 +275,7 @@ wgrad_gather_simt_kernel(Img x, Img gout, float* __restrict__ dw, const int* __r
 template <typename TO, bool ROUND_TF32 = false>
 __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps,
                                     int a, int b, long long s_a, long long s_b, TO* __restrict__ dst) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)ntaps * a * b;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -315,10 +318,10 @@ extern "C" int ast_conv_gather(const ast_image* in, const void* weights, const f
   dim3 grid((mtot + BM - 1) / BM, (out->c + BN - 1) / BN, in->n);
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   if (in->dtype == AST_F32)
-    conv_gather_simt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_k(conv_gather_simt_kernel<float>, grid, 256, 0, (cudaStream_t)stream, 
         to_img(in), (const float*)weights, bias, in_shift, addi, maski, to_img(out), g);
   else
-    conv_gather_simt_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_k(conv_gather_simt_kernel<__nv_bfloat16>, grid, 256, 0, (cudaStream_t)stream, 
         to_img(in), (const __nv_bfloat16*)weights, bias, in_shift, addi, maski, to_img(out), g);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
@@ -341,7 +344,7 @@ int launch_wgrad_simt(const ast_image* x, const ast_image* gout, float* dw, cons
   if (chunk < 256) chunk = 256;
   ksplit = (mtot + chunk - 1) / chunk;
   dim3 grid((unsigned)(ksplit * (dw_img_stride ? x->n : 1)), geom->ntaps, nco * nci);
-#define LAUNCH(TX, TG) wgrad_gather_simt_kernel<TX, TG><<<grid, 256, 0, s>>>(to_img(x), to_img(gout), dw, tap_off, s_co, s_ci, g, nci, chunk, dw_img_stride, (int)ksplit, scale)
+#define LAUNCH(TX, TG) launch_k(wgrad_gather_simt_kernel<TX, TG>, grid, 256, 0, s, to_img(x), to_img(gout), dw, tap_off, s_co, s_ci, g, nci, chunk, dw_img_stride, (int)ksplit, scale)
   if (x->dtype == AST_F32 && gout->dtype == AST_F32) LAUNCH(float, float);
   else if (x->dtype == AST_BF16 && gout->dtype == AST_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (x->dtype == AST_F32 && gout->dtype == AST_BF16) LAUNCH(float, __nv_bfloat16);
@@ -372,11 +375,11 @@ extern "C" int ast_pack_weights(const float* src, const int32_t* tap_off, int32_
   const long long total = (long long)ntaps * a * b;
   const int blocks = (int)min((total + 255) / 256, (long long)num_sms() * 8);
   if (dst_dtype == AST_F32)
-    pack_weights_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, tap_off, ntaps, a, b, s_a, s_b, (float*)dst);
+    launch_k(pack_weights_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, src, tap_off, ntaps, a, b, s_a, s_b, (float*)dst);
   else if (dst_dtype == AST_TF32)
-    pack_weights_kernel<float, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, tap_off, ntaps, a, b, s_a, s_b, (float*)dst);
+    launch_k(pack_weights_kernel<float, true>, blocks, 256, 0, (cudaStream_t)stream, src, tap_off, ntaps, a, b, s_a, s_b, (float*)dst);
   else if (dst_dtype == AST_BF16)
-    pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, tap_off, ntaps, a, b, s_a, s_b, (__nv_bfloat16*)dst);
+    launch_k(pack_weights_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, src, tap_off, ntaps, a, b, s_a, s_b, (__nv_bfloat16*)dst);
   else AST_CHECK_ARG(false, "ast_pack_weights: bad dtype %d", dst_dtype);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();

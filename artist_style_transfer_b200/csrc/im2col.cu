@@ -14,6 +14,7 @@ namespace ast {
 __global__ void __launch_bounds__(256)
 row_im2col_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int sign, int px, int py, int reflect,
                   int round_tf32) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int C = src.c;
   const long long total = (long long)out.n * out.h * out.w * out.c;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
@@ -46,6 +47,7 @@ template <int OUTC, int KW, int CC>
 __global__ void __launch_bounds__(256)
 row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw_rt, int sign, int px, int py, int reflect,
                       int round_tf32) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int C = CC > 0 ? CC : src.c;
   const int kw = KW > 0 ? KW : kw_rt;
   const long long total = (long long)out.n * out.h * out.w;
@@ -109,6 +111,7 @@ template <typename TO, bool ROUND_TF32>
 __global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps, int a,
                                        int a_valid, int b, int b_valid, int b0, long long s_a, long long s_b1,
                                        long long s_b0, TO* __restrict__ dst) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)ntaps * a * b;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -125,6 +128,7 @@ __global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int*
 // out[n, y, x, d*C + j] = src[n, y + sign*d - py, x, j]  (0 outside): folds kh vertical taps of an NHWC tensor into
 // channels with 16-byte copies, so a kh-tap filter-gradient contraction becomes ONE tap with kh*C channels.
 __global__ void __launch_bounds__(256) unfold_rows_kernel(Img src, Img out, int kh, int sign, int py, int esz) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int cpp = src.c * esz / 16;                 // 16-byte chunks per source pixel
   const long long total = (long long)out.n * out.h * out.w * kh * cpp;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
@@ -160,7 +164,7 @@ extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32
   if (total == 0) return 0;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-  unfold_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), kh, sign, py, esz);
+  launch_k(unfold_rows_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, to_img(src), to_img(out), kh, sign, py, esz);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -173,6 +177,7 @@ extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32
 // One block per (n, y) row: the row of partial sums is staged in shared memory with coalesced 16-byte loads.
 __global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const float* __restrict__ bias, int kw, int relu,
                                                         int segw) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ float row[];
   const int n = blockIdx.x / out.h, y = blockIdx.x % out.h;
   const int x0 = blockIdx.y * segw, nx = min(segw, out.w - x0);       // this block's output columns [x0, x0 + nx)
@@ -209,7 +214,7 @@ extern "C" int ast_fold_rows(const ast_image* part, const ast_image* out, const 
   cudaError_t e = cudaFuncSetAttribute(fold_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("ast_fold_rows: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)(out->n * out->h), (unsigned)((out->w + segw - 1) / segw));
-  fold_rows_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(to_img(part), to_img(out), bias, kw, relu, segw);
+  launch_k(fold_rows_kernel, grid, 256, smem, (cudaStream_t)stream, to_img(part), to_img(out), bias, kw, relu, segw);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -230,7 +235,7 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
     const long long pixels = total / out->c;
     long long pb = (pixels + 255) / 256;
     if (pb > (long long)num_sms() * 32) pb = (long long)num_sms() * 32;
-#define RIK(O, K, C) row_im2col_pix_kernel<O, K, C><<<(int)pb, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32)
+#define RIK(O, K, C) launch_k(row_im2col_pix_kernel<O, K, C>, (int)pb, 256, 0, (cudaStream_t)stream, to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32)
     if (out->c == 32 && kw == 9 && src->c == 3) RIK(32, 9, 3);
     else if (out->c == 16 && kw == 3 && src->c == 3) RIK(16, 3, 3);
     else if (out->c == 32) RIK(32, 0, 0);
@@ -242,7 +247,7 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
   }
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
-  row_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(to_img(src), to_img(out), shift, kw, sign, px, py,
+  launch_k(row_im2col_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, to_img(src), to_img(out), shift, kw, sign, px, py,
                                                                    reflect, round_tf32);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
@@ -259,7 +264,7 @@ extern "C" int ast_pack_weights_ex(const float* src, const int32_t* tap_off, int
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
   cudaStream_t s = (cudaStream_t)stream;
-#define PK(T, R) pack_weights_ex_kernel<T, R><<<(int)blocks, 256, 0, s>>>(src, tap_off, ntaps, a, a_valid, b, b_valid, b0, s_a, s_b1, s_b0, (T*)dst)
+#define PK(T, R) launch_k(pack_weights_ex_kernel<T, R>, (int)blocks, 256, 0, s, src, tap_off, ntaps, a, a_valid, b, b_valid, b0, s_a, s_b1, s_b0, (T*)dst)
   if (dst_dtype == AST_F32) PK(float, false);
   else if (dst_dtype == AST_TF32) PK(float, true);
   else if (dst_dtype == AST_BF16) PK(__nv_bfloat16, false);

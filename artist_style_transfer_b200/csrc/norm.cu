@@ -12,6 +12,7 @@ constexpr int NT = 256;
 template <typename T>
 __global__ void __launch_bounds__(NT)
 in_stats_partial_kernel(Img x, float* __restrict__ ws, int nblk, int chunk) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ float sm[];
   const int C = x.c, lanes = C / VEC, slots = NT / lanes;
@@ -71,6 +72,7 @@ in_stats_partial_kernel(Img x, float* __restrict__ ws, int nblk, int chunk) {
 
 __global__ void in_stats_final_kernel(const float* __restrict__ ws, int nblk, int C, int hw, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float na = 0.f, ma = 0.f, qa = 0.f;
@@ -93,6 +95,7 @@ template <typename TX, typename TO>
 __global__ void __launch_bounds__(NT)
 in_apply_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, Img res, Img out, int pad, int relu) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = 4;  // 4 channels per thread regardless of dtype (8B bf16 / 16B fp32 accesses)
   const int C = x.c, lanes = C / VEC;
   const long long total = (long long)out.n * out.h * out.w * lanes;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(NT)
 in_bwd_stats_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
                     int relu, float* __restrict__ s1o, float* __restrict__ s2o, int chunk) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = 4;
   extern __shared__ float sm[];
   const int C = x.c, lanes = C / VEC, slots = NT / lanes;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(NT)
 in_bwd_apply_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
                     int relu, const float* __restrict__ s1, const float* __restrict__ s2, Img dx, Img gtotal) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = 4;
   const int C = x.c, lanes = C / VEC;
   const float inv_hw = 1.f / (float)(x.h * x.w);
@@ -255,6 +260,7 @@ in_bwd_apply_kernel(Img x, const float* __restrict__ mean, const float* __restri
 
 __global__ void in_finalize_kernel(const float* __restrict__ sums, int total, float inv_hw, float eps,
                                    float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float m = sums[2 * i] * inv_hw;
@@ -308,9 +314,9 @@ extern "C" int ast_instnorm_stats(const ast_image* x, float* mean, float* rstd, 
   const size_t smem = (NT + 2 * slots * x->c) * sizeof(float);
   dim3 grid(nblk, x->n);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x->dtype == AST_F32) in_stats_partial_kernel<float><<<grid, NT, smem, s>>>(to_img(x), (float*)workspace, nblk, chunk);
-  else in_stats_partial_kernel<__nv_bfloat16><<<grid, NT, smem, s>>>(to_img(x), (float*)workspace, nblk, chunk);
-  in_stats_final_kernel<<<x->n, 128, 0, s>>>((const float*)workspace, nblk, x->c, hw, eps, mean, rstd);
+  if (x->dtype == AST_F32) launch_k(in_stats_partial_kernel<float>, grid, NT, smem, s, to_img(x), (float*)workspace, nblk, chunk);
+  else launch_k(in_stats_partial_kernel<__nv_bfloat16>, grid, NT, smem, s, to_img(x), (float*)workspace, nblk, chunk);
+  launch_k(in_stats_final_kernel, x->n, 128, 0, s, (const float*)workspace, nblk, x->c, hw, eps, mean, rstd);
   count_launch(2);
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -321,7 +327,7 @@ extern "C" int ast_instnorm_finalize(const float* sums, int32_t n, int32_t c, in
   AST_CHECK_ARG(sums && mean && rstd && hw > 0, "ast_instnorm_finalize: bad argument");
   const int total = n * c;
   if (total == 0) return 0;
-  in_finalize_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, total, 1.f / (float)hw, eps, mean, rstd);
+  launch_k(in_finalize_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, sums, total, 1.f / (float)hw, eps, mean, rstd);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -343,7 +349,7 @@ extern "C" int ast_instnorm_apply(const ast_image* x, const float* mean, const f
   const int blocks = (int)min((total + NT - 1) / NT, (long long)num_sms() * 16);
   Img r = residual ? to_img(residual) : null_img();
   cudaStream_t s = (cudaStream_t)stream;
-#define LA(TX, TO) in_apply_kernel<TX, TO><<<blocks, NT, 0, s>>>(to_img(x), mean, rstd, gamma, beta, r, to_img(out), pad, relu)
+#define LA(TX, TO) launch_k(in_apply_kernel<TX, TO>, blocks, NT, 0, s, to_img(x), mean, rstd, gamma, beta, r, to_img(out), pad, relu)
   if (x->dtype == AST_F32 && out->dtype == AST_F32) LA(float, float);
   else if (x->dtype == AST_BF16 && out->dtype == AST_BF16) LA(__nv_bfloat16, __nv_bfloat16);
   else if (x->dtype == AST_F32 && out->dtype == AST_BF16) LA(float, __nv_bfloat16);
@@ -382,9 +388,9 @@ extern "C" int ast_instnorm_bwd_stats(const ast_image* x, const float* mean, con
   dim3 grid(nblk, x->n);
   Img gp = gpad ? to_img(gpad) : null_img(), ge = gextra ? to_img(gextra) : null_img();
   if (x->dtype == AST_F32)
-    in_bwd_stats_kernel<float><<<grid, NT, smem, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
+    launch_k(in_bwd_stats_kernel<float>, grid, NT, smem, s, to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
   else
-    in_bwd_stats_kernel<__nv_bfloat16><<<grid, NT, smem, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
+    launch_k(in_bwd_stats_kernel<__nv_bfloat16>, grid, NT, smem, s, to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -407,7 +413,7 @@ extern "C" int ast_instnorm_bwd_apply(const ast_image* x, const float* mean, con
   Img gp = gpad ? to_img(gpad) : null_img(), ge = gextra ? to_img(gextra) : null_img();
   Img gt = gtotal ? to_img(gtotal) : null_img();
   cudaStream_t s = (cudaStream_t)stream;
-#define LB(TX, TO) in_bwd_apply_kernel<TX, TO><<<blocks, NT, 0, s>>>(to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, to_img(dx), gt)
+#define LB(TX, TO) launch_k(in_bwd_apply_kernel<TX, TO>, blocks, NT, 0, s, to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, to_img(dx), gt)
   if (x->dtype == AST_F32 && dx->dtype == AST_F32) LB(float, float);
   else if (x->dtype == AST_BF16 && dx->dtype == AST_BF16) LB(__nv_bfloat16, __nv_bfloat16);
   else if (x->dtype == AST_F32 && dx->dtype == AST_BF16) LB(float, __nv_bfloat16);

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(NF_THREADS, NF_MINB)
 in_apply_fast_kernel(Lin x, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, Lin res, Lin out, NfShape sh,
                      int relu) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = Vec16<T>::N;
   const int C = sh.C, lanes = C / VEC, slots = NF_THREADS / lanes;
   const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(NF_THREADS, NF_MINB)
 in_bwd_stats_fast_kernel(Lin x, const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, const float* __restrict__ beta, Lin gpad, Lin gextra,
                          NfShape sh, int relu, float* __restrict__ s1o, float* __restrict__ s2o) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ float sm[];
   const int C = sh.C, lanes = C / VEC, slots = NF_THREADS / lanes;
@@ -303,6 +305,7 @@ in_bwd_apply_fast_kernel(Lin x, const float* __restrict__ mean, const float* __r
                          const float* __restrict__ gamma, const float* __restrict__ beta, Lin gpad, Lin gextra,
                          NfShape sh, int relu, const float* __restrict__ s1, const float* __restrict__ s2, Lin dx,
                          Lin gtotal) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = Vec16<T>::N;
   const int C = sh.C, lanes = C / VEC, slots = NF_THREADS / lanes;
   const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
@@ -395,9 +398,9 @@ int instnorm_apply_fast(const ast_image* x, const float* mean, const float* rstd
   const int nblk = grid_rows(x->n, out->h, &sh.rows);
   dim3 grid(nblk, x->n);
   if (x->dtype == AST_F32)
-    in_apply_fast_kernel<float><<<grid, NF_THREADS, 0, s>>>(to_lin(x), mean, rstd, gamma, beta, to_lin(residual), to_lin(out), sh, relu);
+    launch_k(in_apply_fast_kernel<float>, grid, NF_THREADS, 0, s, to_lin(x), mean, rstd, gamma, beta, to_lin(residual), to_lin(out), sh, relu);
   else
-    in_apply_fast_kernel<__nv_bfloat16><<<grid, NF_THREADS, 0, s>>>(to_lin(x), mean, rstd, gamma, beta, to_lin(residual), to_lin(out), sh, relu);
+    launch_k(in_apply_fast_kernel<__nv_bfloat16>, grid, NF_THREADS, 0, s, to_lin(x), mean, rstd, gamma, beta, to_lin(residual), to_lin(out), sh, relu);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 1;
@@ -422,9 +425,9 @@ int instnorm_bwd_stats_fast(const ast_image* x, const float* mean, const float* 
   dim3 grid(nblk, x->n);
   const size_t smem = 2 * (size_t)(NF_THREADS / (x->c / vec)) * x->c * sizeof(float);
   if (x->dtype == AST_F32)
-    in_bwd_stats_fast_kernel<float><<<grid, NF_THREADS, smem, s>>>(to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2);
+    launch_k(in_bwd_stats_fast_kernel<float>, grid, NF_THREADS, smem, s, to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2);
   else
-    in_bwd_stats_fast_kernel<__nv_bfloat16><<<grid, NF_THREADS, smem, s>>>(to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2);
+    launch_k(in_bwd_stats_fast_kernel<__nv_bfloat16>, grid, NF_THREADS, smem, s, to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 1;
@@ -443,9 +446,9 @@ int instnorm_bwd_apply_fast(const ast_image* x, const float* mean, const float* 
   const int nblk = grid_rows(x->n, x->h, &sh.rows);
   dim3 grid(nblk, x->n);
   if (x->dtype == AST_F32)
-    in_bwd_apply_fast_kernel<float><<<grid, NF_THREADS, 0, s>>>(to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2, to_lin(dx), to_lin(gtotal));
+    launch_k(in_bwd_apply_fast_kernel<float>, grid, NF_THREADS, 0, s, to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2, to_lin(dx), to_lin(gtotal));
   else
-    in_bwd_apply_fast_kernel<__nv_bfloat16><<<grid, NF_THREADS, 0, s>>>(to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2, to_lin(dx), to_lin(gtotal));
+    launch_k(in_bwd_apply_fast_kernel<__nv_bfloat16>, grid, NF_THREADS, 0, s, to_lin(x), mean, rstd, gamma, beta, to_lin(gpad), to_lin(gextra), sh, relu, s1, s2, to_lin(dx), to_lin(gtotal));
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 1;

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(NS_THREADS, 2)
 in_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta, Rows res, Rows out, NsShape sh,
                        int relu) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(NS_THREADS, 2)
 in_bwd_stats_staged_kernel(Rows x, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, Rows gpad, Rows gextra,
                            NsShape sh, int relu, float* __restrict__ s1o, float* __restrict__ s2o) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -333,6 +335,7 @@ in_bwd_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
                            const float* __restrict__ gamma, const float* __restrict__ beta, Rows gpad, Rows gextra,
                            NsShape sh, int relu, const float* __restrict__ s1, const float* __restrict__ s2, Rows dx,
                            Rows gtotal) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -451,10 +454,10 @@ int instnorm_apply_staged(const ast_image* x, const float* mean, const float* rs
   cudaError_t e;
   if (x->dtype == AST_F32) {
     e = ns_attr(in_apply_staged_kernel<float>, smem);
-    if (e == cudaSuccess) in_apply_staged_kernel<float><<<grid, NS_THREADS, smem, s>>>(to_rows(x), mean, rstd, gamma, beta, to_rows(residual), to_rows(out), sh, relu);
+    if (e == cudaSuccess) launch_k(in_apply_staged_kernel<float>, grid, NS_THREADS, smem, s, to_rows(x), mean, rstd, gamma, beta, to_rows(residual), to_rows(out), sh, relu);
   } else {
     e = ns_attr(in_apply_staged_kernel<__nv_bfloat16>, smem);
-    if (e == cudaSuccess) in_apply_staged_kernel<__nv_bfloat16><<<grid, NS_THREADS, smem, s>>>(to_rows(x), mean, rstd, gamma, beta, to_rows(residual), to_rows(out), sh, relu);
+    if (e == cudaSuccess) launch_k(in_apply_staged_kernel<__nv_bfloat16>, grid, NS_THREADS, smem, s, to_rows(x), mean, rstd, gamma, beta, to_rows(residual), to_rows(out), sh, relu);
   }
   if (e != cudaSuccess) { set_error("instnorm_apply_staged: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
@@ -486,10 +489,10 @@ int instnorm_bwd_stats_staged(const ast_image* x, const float* mean, const float
   cudaError_t e;
   if (x->dtype == AST_F32) {
     e = ns_attr(in_bwd_stats_staged_kernel<float>, smem);
-    if (e == cudaSuccess) in_bwd_stats_staged_kernel<float><<<grid, NS_THREADS, smem, s>>>(to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2);
+    if (e == cudaSuccess) launch_k(in_bwd_stats_staged_kernel<float>, grid, NS_THREADS, smem, s, to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2);
   } else {
     e = ns_attr(in_bwd_stats_staged_kernel<__nv_bfloat16>, smem);
-    if (e == cudaSuccess) in_bwd_stats_staged_kernel<__nv_bfloat16><<<grid, NS_THREADS, smem, s>>>(to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2);
+    if (e == cudaSuccess) launch_k(in_bwd_stats_staged_kernel<__nv_bfloat16>, grid, NS_THREADS, smem, s, to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2);
   }
   if (e != cudaSuccess) { set_error("instnorm_bwd_stats_staged: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
@@ -513,10 +516,10 @@ int instnorm_bwd_apply_staged(const ast_image* x, const float* mean, const float
   cudaError_t e;
   if (x->dtype == AST_F32) {
     e = ns_attr(in_bwd_apply_staged_kernel<float>, smem);
-    if (e == cudaSuccess) in_bwd_apply_staged_kernel<float><<<grid, NS_THREADS, smem, s>>>(to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2, to_rows(dx), to_rows(gtotal));
+    if (e == cudaSuccess) launch_k(in_bwd_apply_staged_kernel<float>, grid, NS_THREADS, smem, s, to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2, to_rows(dx), to_rows(gtotal));
   } else {
     e = ns_attr(in_bwd_apply_staged_kernel<__nv_bfloat16>, smem);
-    if (e == cudaSuccess) in_bwd_apply_staged_kernel<__nv_bfloat16><<<grid, NS_THREADS, smem, s>>>(to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2, to_rows(dx), to_rows(gtotal));
+    if (e == cudaSuccess) launch_k(in_bwd_apply_staged_kernel<__nv_bfloat16>, grid, NS_THREADS, smem, s, to_rows(x), mean, rstd, gamma, beta, to_rows(gpad), to_rows(gextra), sh, relu, s1, s2, to_rows(dx), to_rows(gtotal));
   }
   if (e != cudaSuccess) { set_error("instnorm_bwd_apply_staged: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();

@@ -9,6 +9,7 @@ namespace ast {
 constexpr int NT = 256;
 
 __global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = x.c / 4;
   const long long total = (long long)y.n * y.h * y.w * lanes;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y) {
 
 // one thread per 2x2 window (ceil-div grid so odd trailing rows/cols of x still get gadd*mask)
 __global__ void __launch_bounds__(NT) maxpool2_bwd_kernel(Img x, Img gy, Img gadd, Img gx) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = x.c / 4;
   const int wh = (x.h + 1) / 2, ww = (x.w + 1) / 2;
   const long long total = (long long)x.n * wh * ww * lanes;
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(NT) maxpool2_bwd_kernel(Img x, Img gy, Img gad
 }
 
 __global__ void __launch_bounds__(NT) mse_kernel(Img a, Img b, float* loss, float scale, Img grad, float gscale) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)a.n * a.h * a.w * a.c;
   float part = 0.f;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(NT) mse_kernel(Img a, Img b, float* loss, floa
 
 // vectorised NHWC variant of the same thing (all images sc == 1, c % 4 == 0)
 __global__ void __launch_bounds__(NT) mse_vec_kernel(Img a, Img b, float* loss, float scale, Img grad, float gscale) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = a.c / 4;
   const long long total = (long long)a.n * a.h * a.w * lanes;
   float part = 0.f;
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(NT) mse_vec_kernel(Img a, Img b, float* loss, 
 }
 
 __global__ void __launch_bounds__(NT) copy_image_kernel(Img src, Img dst, const float* __restrict__ shift, int pad) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
   // iterate in the destination's fastest-varying order for coalesced writes
   const bool chan_fast = dst.sc == 1;
@@ -148,6 +153,7 @@ __global__ void __launch_bounds__(NT) copy_image_kernel(Img src, Img dst, const 
 }
 
 __global__ void __launch_bounds__(NT) accumulate_kernel(Img x, Img acc) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)x.n * x.h * x.w * x.c;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
     const int c = (int)(idx % x.c);
@@ -161,6 +167,7 @@ __global__ void __launch_bounds__(NT) accumulate_kernel(Img x, Img acc) {
 }
 
 __global__ void __launch_bounds__(NT) mask_add_kernel(Img a, Img b, Img mask, Img out) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)a.n * a.h * a.w * a.c;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
     const int c = (int)(idx % a.c);
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(NT) mask_add_kernel(Img a, Img b, Img mask, Im
 
 // 4 channels per thread (16 B fp32 / 8 B bf16 accesses); mixed dtypes allowed
 __global__ void __launch_bounds__(NT) mask_add_vec_kernel(Img a, Img b, Img mask, Img out) {
+  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = a.c / 4;
   const long long total = (long long)a.n * a.h * a.w * lanes;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -225,7 +233,7 @@ extern "C" int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, void* st
   AST_CHECK_ARG(y->n == x->n && y->c == x->c && y->h == x->h / 2 && y->w == x->w / 2, "ast_maxpool2_fwd: y must be (h/2, w/2)");
   const long long total = (long long)y->n * y->h * y->w * (y->c / 4);
   if (total == 0) return 0;
-  maxpool2_fwd_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(x), to_img(y));
+  launch_k(maxpool2_fwd_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(y));
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -240,7 +248,7 @@ extern "C" int ast_maxpool2_bwd(const ast_image* x, const ast_image* y, const as
   AST_CHECK_ARG(same_shape(gx, x) && (!gadd || same_shape(gadd, x)), "ast_maxpool2_bwd: gx/gadd shape");
   const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * (x->c / 4);
   if (total == 0) return 0;
-  maxpool2_bwd_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(x), to_img(gy), gadd ? to_img(gadd) : null_img(), to_img(gx));
+  launch_k(maxpool2_bwd_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(gy), gadd ? to_img(gadd) : null_img(), to_img(gx));
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -254,9 +262,9 @@ extern "C" int ast_mse(const ast_image* a, const ast_image* b, float* loss, floa
   if (total == 0) return 0;
   Img gi = grad ? to_img(grad) : null_img();
   if (vec_ok(a) && vec_ok(b) && (!grad || vec_ok(grad)))
-    mse_vec_kernel<<<blocks_for(total / 4), NT, 0, (cudaStream_t)stream>>>(to_img(a), to_img(b), loss, scale, gi, gscale);
+    launch_k(mse_vec_kernel, blocks_for(total / 4), NT, 0, (cudaStream_t)stream, to_img(a), to_img(b), loss, scale, gi, gscale);
   else
-    mse_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(a), to_img(b), loss, scale, gi, gscale);
+    launch_k(mse_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(a), to_img(b), loss, scale, gi, gscale);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -269,7 +277,7 @@ extern "C" int ast_copy_image(const ast_image* src, const ast_image* dst, const 
   AST_CHECK_ARG(pad < src->h && pad < src->w, "ast_copy_image: pad too large");
   const long long total = (long long)dst->n * dst->h * dst->w * dst->c;
   if (total == 0) return 0;
-  copy_image_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(src), to_img(dst), shift, pad);
+  launch_k(copy_image_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(src), to_img(dst), shift, pad);
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -280,7 +288,7 @@ extern "C" int ast_accumulate(const ast_image* x, const ast_image* acc, void* st
   AST_CHECK_ARG(same_shape(x, acc) && acc->dtype == AST_F32, "ast_accumulate: acc must be fp32 of the same shape");
   const long long total = (long long)x->n * x->h * x->w * x->c;
   if (total == 0) return 0;
-  accumulate_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(x), to_img(acc));
+  launch_k(accumulate_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(acc));
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
@@ -292,9 +300,9 @@ extern "C" int ast_mask_add(const ast_image* a, const ast_image* b, const ast_im
   const long long total = (long long)a->n * a->h * a->w * a->c;
   if (total == 0) return 0;
   if (vec_ok(a) && vec_ok(out) && (!b || vec_ok(b)) && (!mask || vec_ok(mask)))
-    mask_add_vec_kernel<<<blocks_for(total / 4), NT, 0, (cudaStream_t)stream>>>(to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
+    launch_k(mask_add_vec_kernel, blocks_for(total / 4), NT, 0, (cudaStream_t)stream, to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
   else
-    mask_add_kernel<<<blocks_for(total), NT, 0, (cudaStream_t)stream>>>(to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
+    launch_k(mask_add_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
   count_launch();
   AST_CUDA_LAUNCH_CHECK();
   return 0;
