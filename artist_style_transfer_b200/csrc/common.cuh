@@ -42,11 +42,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // it lets ITS successor be scheduled early and then blocks until the predecessor grid has completed and its memory is
 // visible.  No kernel touches global memory before pdl_sync(), so the semantics are those of plain stream order.
 // Both instructions are no-ops without the attribute.  Measured on the B=32 step (CUDA graph): 13.86 ms with PDL vs
-// 13.55 ms without - the early-scheduled successors take SM slots from the multi-wave kernels - so it is OFF by default.
-__device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
+// 13.55 ms without when every kernel triggers early (successors take SM slots from multi-wave kernels), 13.65 ms when only
+// the single-wave persistent kernels trigger - so it is OFF by default.
+__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Only the single-wave persistent kernels let their successor be scheduled early (its CTAs then fill SMs as this grid's
+// CTAs retire); multi-wave kernels would lose SM slots to the waiting successor.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 inline bool pdl_enabled() {
   static const int on = [] { const char* e = getenv("AST_PDL"); return e ? atoi(e) : 0; }();
   return on != 0;

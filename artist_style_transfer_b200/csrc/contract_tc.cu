@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
 contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c, const CtParams p,
                    float* __restrict__ out, const int* __restrict__ tap_off) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
   __shared__ unsigned tmem_slot;
@@ -210,6 +211,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
 // fills the strict lower triangle of each C x C matrix from the upper one
 __global__ void mirror_upper_kernel(float* __restrict__ g, int c, long long total) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % c);
     const int i = (int)((idx / c) % c);
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
 contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c,
                      const CtThinParams p, float* __restrict__ out, const int* __restrict__ tap_off) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
   __shared__ unsigned tmem_slot;

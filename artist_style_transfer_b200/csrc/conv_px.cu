@@ -43,6 +43,7 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
                float* __restrict__ stats) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[PX_MAX_STAGES], empty_bar[PX_MAX_STAGES], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ unsigned tmem_slot;

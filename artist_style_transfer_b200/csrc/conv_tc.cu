@@ -86,6 +86,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
                float* __restrict__ stats) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ unsigned tmem_slot;

@@ -58,6 +58,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
                float* __restrict__ stats) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ __align__(8) unsigned long long wfull[WS_MAX_WBUF], wempty[WS_MAX_WBUF];
@@ -268,6 +269,7 @@ conv_wsx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
                 float* __restrict__ stats) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ unsigned tmem_slot;

@@ -111,6 +111,7 @@ in_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* __re
                        const float* __restrict__ gamma, const float* __restrict__ beta, Rows res, Rows out, NsShape sh,
                        int relu) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -265,6 +266,7 @@ in_bwd_stats_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
                            const float* __restrict__ gamma, const float* __restrict__ beta, Rows gpad, Rows gextra,
                            NsShape sh, int relu, float* __restrict__ s1o, float* __restrict__ s2o) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -336,6 +338,7 @@ in_bwd_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
                            NsShape sh, int relu, const float* __restrict__ s1, const float* __restrict__ s2, Rows dx,
                            Rows gtotal) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
+  pdl_trigger();
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
