@@ -164,6 +164,24 @@ def _thin_out_pack_dgrad(st, w, dtype):   # [dy][c][dx*cout + co] = W[co][c][dy]
                                k2, 1, st.cin * k2, dtype)
 
 
+class _ZeroArena:
+    """One zero-filled fp32 buffer per forward / backward pass, carved into the many small accumulators (InstanceNorm
+    sums, filter-gradient scratch, dead conv-bias gradients): one fill kernel instead of ~50 per step."""
+
+    def __init__(self, sizes, device):
+        self.buf = torch.zeros(sum((s + 3) // 4 * 4 for s in sizes), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        numel = 1
+        for d in shape:
+            numel *= d
+        view = self.buf[self.off:self.off + numel].view(*shape)
+        self.off += (numel + 3) // 4 * 4          # keep every slice 16-byte aligned (vector atomics)
+        assert self.off <= self.buf.numel()
+        return view
+
+
 class _StageFunction(torch.autograd.Function):
     """Forward/backward of a list of stages as ONE autograd node (x: NCHW fp32 in, NCHW fp32 out)."""
 
@@ -191,6 +209,7 @@ class _StageFunction(torch.autograd.Function):
             ops.copy_image(x.permute(0, 2, 3, 1), node, pad=p0)
         nodes, node_pad, saved = [node], [p0], []
         out = None
+        zeros = _ZeroArena([n * st.cout * 2 for st in stages if st.norm], dev)
         for i, st in enumerate(stages):
             cw, cb, gam, bet = P[i]
             xin = nodes[-1]
@@ -227,7 +246,7 @@ class _StageFunction(torch.autograd.Function):
                 # conv bias is dead under InstanceNorm and is not added
                 use_tc = mode == "fast" and ops.tc_eligible(xin, st.cout)
                 if use_tc and _fused_stats():      # sum x / sum x^2 accumulated by the conv epilogue: no stats pass
-                    sums = torch.zeros(n * st.cout * 2, dtype=torch.float32, device=dev)
+                    sums = zeros.take(n * st.cout * 2)
                     ops.conv_gather(xin, wp, launches, raw, tensor=True, stats=sums)
                     mean, rstd = ops.instnorm_finalize(sums, n, st.cout, ho * wo)
                 else:
@@ -267,6 +286,8 @@ class _StageFunction(torch.autograd.Function):
         gpad = [None] * (L + 1)
         gextra = [None] * (L + 1)
         grads = []
+        zeros = _ZeroArena([max(st.k * st.k * st.cout * st.cin, st.k * 32 * max(st.cout, st.cin)) + st.cout
+                            for st in stages], gout.device)
         for i in reversed(range(L)):
             st = stages[i]
             cw, cb, gam, bet = P[i]
@@ -291,11 +312,11 @@ class _StageFunction(torch.autograd.Function):
                     gextra[j] = ge
                 d_raw = torch.empty_like(raw)
                 gtotal = torch.empty(raw.shape, dtype=gdt, device=raw.device) if st.res_from is not None else None
-                s1, s2 = ops.instnorm_bwd(raw, mean, rstd, gam.detach(), bet.detach(), gpad[j], node_pad[j],
-                                          gextra[j], st.relu, d_raw, gtotal)
-                g_bet = s1.view(n, c).sum(0)
-                g_gam = s2.view(n, c).sum(0)
-                g_cb = torch.zeros_like(cb)          # exactly zero under InstanceNorm
+                s12 = ops.instnorm_bwd(raw, mean, rstd, gam.detach(), bet.detach(), gpad[j], node_pad[j],
+                                       gextra[j], st.relu, d_raw, gtotal)
+                g12 = s12.view(2, n, c).sum(1)       # per-(n,c) sums of g' and g'*xhat -> dbeta, dgamma in one reduction
+                g_bet, g_gam = g12[0], g12[1]
+                g_cb = zeros.take(st.cout)           # exactly zero under InstanceNorm
                 if gtotal is not None:
                     assert gextra[st.res_from + 1] is None
                     gextra[st.res_from + 1] = gtotal
@@ -307,14 +328,14 @@ class _StageFunction(torch.autograd.Function):
             if i == 0 and ctx.thin_in and thin_taps:
                 # k vertical taps handled as a tap group inside the contraction kernel (d_raw loaded once per stage):
                 # tmp[dy][co][dx*cin+c] += sum_p dY[p][co] * Xr[p + dy rows][dx*cin+c]
-                tmp = torch.zeros((st.k, st.cout, 32), dtype=torch.float32, device=xin.device)
+                tmp = zeros.take(st.k, st.cout, 32)
                 ops.wgrad_gather(xin, d_raw, launches, tmp, 32, 1, st.cout * 32, 0, tensor=wtc)
                 g_cw = tmp[:, :, :st.k * st.cin].reshape(st.k, st.cout, st.k, st.cin).permute(1, 3, 0, 2).contiguous()
             elif not st.norm and thin_out and thin_taps:
                 # tmp[dy][dx*cout+co][c] += sum_{y,x'} Dr[y][x'][dx*cout+co] * xin[y+dy][x'][c]
                 taps, wt = _vtaps(st.k)
                 lw = [cg.Launch(d_raw.shape[1], d_raw.shape[2], 1, 1, 0, 0, taps, wt, 0)]
-                tmp = torch.zeros((st.k, 32, st.cin), dtype=torch.float32, device=xin.device)
+                tmp = zeros.take(st.k, 32, st.cin)
                 ops.wgrad_gather(xin, d_raw, lw, tmp, st.cin, 1, 32 * st.cin, 0, tensor=True)
                 g_cw = tmp[:, :st.k * st.cout, :].reshape(st.k, st.k, st.cout, st.cin).permute(2, 3, 0, 1).contiguous()
             elif i == 0 and ctx.thin_in:
@@ -325,7 +346,7 @@ class _StageFunction(torch.autograd.Function):
                 ops.unfold_rows(xin, xf, st.k, 1)
                 one_tap[0].mi, one_tap[0].mj = h_, w_
                 # operands swapped (the 288-channel tensor provides the M rows): tmp[dy*32 + dx*cin+c][co]
-                tmp = torch.zeros((st.k * 32, st.cout), dtype=torch.float32, device=xin.device)
+                tmp = zeros.take(st.k * 32, st.cout)
                 ops.wgrad_gather(d_raw, xf, one_tap, tmp, st.cout, 1, 0, 0, tensor=wtc)
                 g_cw = (tmp.view(st.k, 32, st.cout)[:, :st.k * st.cin, :].reshape(st.k, st.k, st.cin, st.cout)
                         .permute(3, 2, 0, 1).contiguous())
@@ -336,7 +357,7 @@ class _StageFunction(torch.autograd.Function):
                 df = torch.empty((xin.shape[0], xin.shape[1], xin.shape[2], st.k * 32), dtype=adt, device=xin.device)
                 ops.unfold_rows(d_raw, df, st.k, -1)
                 one_tap[0].mi, one_tap[0].mj = xin.shape[1], xin.shape[2]
-                tmp = torch.zeros((st.k * 32, st.cin), dtype=torch.float32, device=xin.device)
+                tmp = zeros.take(st.k * 32, st.cin)
                 ops.wgrad_gather(xin, df, one_tap, tmp, st.cin, 1, 0, 0, tensor=True)
                 g_cw = (tmp.view(st.k, 32, st.cin)[:, :st.k * st.cout, :].reshape(st.k, st.k, st.cout, st.cin)
                         .permute(2, 3, 0, 1).contiguous())
@@ -344,7 +365,7 @@ class _StageFunction(torch.autograd.Function):
             elif wtc:
                 # tap-major scratch tmp[tap][co][ci]: ci contiguous, so the contraction epilogue reduces with 16-byte
                 # vector atomics; the permute to the parameter layout is one small copy
-                tmp = torch.zeros((k2, st.cout, st.cin), dtype=torch.float32, device=xin.device)
+                tmp = zeros.take(k2, st.cout, st.cin)
                 ops.wgrad_gather(xin, d_raw, launches, tmp, st.cin, 1, st.k * st.cout * st.cin, st.cout * st.cin,
                                  tensor=True)
                 tmp = tmp.view(st.k, st.k, st.cout, st.cin)

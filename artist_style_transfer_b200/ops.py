@@ -214,10 +214,11 @@ def _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=No
 
 
 def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None):
-    """Returns (s1, s2) with dbeta = s1.view(N,C).sum(0), dgamma = s2.view(N,C).sum(0); fills dx (and gtotal)."""
+    """Returns s12 of shape (2, N*C): dbeta = s12[0].view(N,C).sum(0), dgamma = s12[1].view(N,C).sum(0); fills dx
+    (and gtotal)."""
     n, _, _, c = x.shape
-    s1 = torch.empty(n * c, dtype=torch.float32, device=x.device)
-    s2 = torch.empty_like(s1)
+    s12 = torch.empty((2, n * c), dtype=torch.float32, device=x.device)     # one allocation: the caller reduces both
+    s1, s2 = s12[0], s12[1]                                                  # over the batch with one kernel
     lib = _lib.load()
     xi, gp, ge, dxi, gt = image(x), image(gpad), image(gextra), image(dx), image(gtotal)
     check(lib.ast_instnorm_bwd_stats(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge),
@@ -225,7 +226,7 @@ def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, 
     check(lib.ast_instnorm_bwd_apply(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge),
                                      int(relu), ptr(s1), ptr(s2), ref(dxi), ref(gt), stream_ptr()),
           "ast_instnorm_bwd_apply")
-    return s1, s2
+    return s12
 
 
 def _maxpool2_fwd_impl(x):

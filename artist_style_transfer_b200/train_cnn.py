@@ -410,7 +410,8 @@ class PerceptualTrainer:
         self.content_weight, self.style_weight = content_weight, style_weight
         self.params = [p for p in transfer.parameters()]
         on_cuda = self.params[0].is_cuda
-        self.optimizer = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay,
+        # fused=True: torch's single-kernel Adam (same update rule, L2 weight decay) instead of ~15 foreach kernels per step
+        self.optimizer = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay, fused=bool(on_cuda),
                                           capturable=bool(cuda_graph and on_cuda))                 # :247
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=max(1, num_epochs // num_steps),
                                                          gamma=0.5)                                # :248
