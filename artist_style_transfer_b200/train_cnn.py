@@ -340,28 +340,73 @@ def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group
 
 
 class _MSEFunction(torch.autograd.Function):
-    """mean((a-b)^2) with the gradient w.r.t. `a` produced in the same pass (nn.MSELoss, train_cnn.py:249,307)."""
+    """weight * mean((a-b)^2) with the gradient w.r.t. `a` produced in the same pass (nn.MSELoss, train_cnn.py:249,307).
+
+    unit_grad=True promises that the upstream gradient of this loss is exactly 1 (perceptual_step calls
+    total.backward() itself with total = content + style): backward then returns the stored gradient as is instead of
+    multiplying a feature-map-sized tensor by a device scalar (0.19 ms per step at B=32 for the relu2_2 content term).
+    """
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, weight=1.0, unit_grad=False):
         av = a.detach().permute(0, 2, 3, 1)
         bv = b.detach().permute(0, 2, 3, 1)
         loss = torch.zeros(1, dtype=torch.float32, device=a.device)
         grad = torch.empty(av.shape, dtype=torch.float32, device=a.device) if a.requires_grad else None
         numel = a.numel()
-        ops.mse(av, bv, loss, 1.0 / numel, grad, 2.0 / numel)
-        ctx.grad = grad
+        ops.mse(av, bv, loss, float(weight) / numel, grad, 2.0 * float(weight) / numel)
+        ctx.grad, ctx.unit_grad = grad, unit_grad
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        ga = ctx.grad.permute(0, 3, 1, 2) * g if ctx.grad is not None else None
-        return ga, None
+        if ctx.grad is None:
+            return None, None, None, None
+        ga = ctx.grad if ctx.unit_grad else ctx.grad * g
+        return ga.permute(0, 3, 1, 2), None, None, None
 
 
-def mse_loss(a, b):
-    """Fused MSE forward+gradient for two [B,C,H,W] tensors (b is treated as a constant)."""
-    return _MSEFunction.apply(a, b)
+class _ContentGramFunction(torch.autograd.Function):
+    """relu2_2 feeds BOTH the content loss (train_cnn.py:307) and a style Gram (:321-325).  As two autograd nodes their
+    gradients meet in an autograd add over two feature-map-sized tensors (0.12 ms per step at B=32); here one node
+    returns (weighted content loss, Gram) and its backward adds the stored content gradient inside the epilogue of the
+    Gram-backward convolution (`add` operand of ast_conv_gather).  unit_grad as in _MSEFunction."""
+
+    @staticmethod
+    def forward(ctx, f, content_feat, weight, fast, unit_grad):
+        b, c, h, w = f.shape
+        fv = f.detach()
+        if fv.dtype not in (torch.float32, torch.bfloat16):
+            fv = fv.float()
+        xv = fv.permute(0, 2, 3, 1)
+        loss = torch.zeros(1, dtype=torch.float32, device=f.device)
+        grad = torch.empty(xv.shape, dtype=torch.float32, device=f.device)
+        numel = f.numel()
+        ops.mse(xv, content_feat.detach().permute(0, 2, 3, 1), loss, float(weight) / numel, grad, 2.0 * float(weight) / numel)
+        g = ops.gram(xv, 1.0 / (c * h * w), tensor=fast and b > 0 and ops.tc_contract_eligible(xv, xv))
+        ctx.save_for_backward(fv)
+        ctx.grad, ctx.fast, ctx.unit_grad = grad, fast, unit_grad
+        return loss[0], g
+
+    @staticmethod
+    def backward(ctx, g_loss, dg):
+        (fv,) = ctx.saved_tensors
+        b, c, h, w = fv.shape
+        cgrad = ctx.grad if ctx.unit_grad else ctx.grad * g_loss
+        x = fv.permute(0, 2, 3, 1)
+        if dg is None:
+            return cgrad.permute(0, 3, 1, 2), None, None, None, None
+        d = ((dg + dg.transpose(1, 2)) * (1.0 / (c * h * w))).to(fv.dtype).contiguous()
+        out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
+        fast = ctx.fast
+        ops.conv_gather(x, d.view(b, 1, c, c), cg.conv_fwd(1, 1, 0, h, w), out, add=cgrad, w_img_stride=c * c,
+                        tensor=fast and x.is_contiguous() and ops.tc_eligible(x, c), round_tf32=fast)
+        return out.permute(0, 3, 1, 2), None, None, None, None
+
+
+def mse_loss(a, b, weight=1.0):
+    """Fused (weighted) MSE forward+gradient for two [B,C,H,W] tensors (b is treated as a constant)."""
+    return _MSEFunction.apply(a, b, weight, False)
 
 
 def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CONTENT_WEIGHT,
@@ -377,10 +422,13 @@ def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CON
     with torch.no_grad():
         content_feat = vgg(content_batch, shift=shift, upto="relu2_2")["relu2_2"]   # :300
     gen_feats = vgg(generated, shift=shift)                                    # :301
-    content_loss = mse_loss(gen_feats["relu2_2"], content_feat) * content_weight    # :307-308
+    # :307-308 and the relu2_2 Gram of :321-325 as ONE autograd node (the weight is folded into the kernel; with
+    # backward=True the upstream gradient of the content term is exactly 1)
+    content_loss, gram22 = _ContentGramFunction.apply(gen_feats["relu2_2"], content_feat, content_weight,
+                                                      vgg._mode() == "fast", bool(backward))
     style_loss = 0
     for key, value in gen_feats.items():                                       # :321-325
-        g = gram(value, precision=vgg._mode())
+        g = gram22 if key == "relu2_2" else gram(value, precision=vgg._mode())
         style_loss = style_loss + mse_loss(g.unsqueeze(1), style_gram[key].unsqueeze(1))
     style_loss = style_loss * style_weight
     total = content_loss + style_loss                                          # :329
