@@ -288,6 +288,16 @@ class _StageFunction(torch.autograd.Function):
         grads = []
         zeros = _ZeroArena([max(st.k * st.k * st.cout * st.cin, st.k * 32 * max(st.cout, st.cin)) + st.cout
                             for st in stages], gout.device)
+        # per-(n,c) InstanceNorm-backward sums of all layers with the same channel count share one buffer
+        # [layer][2][n][c], so dbeta / dgamma of those layers come out of ONE batch reduction at the end
+        nb = gout.shape[0]
+        bank_rows = {}
+        for st in stages:
+            if st.norm:
+                bank_rows[st.cout] = bank_rows.get(st.cout, 0) + 1
+        banks = {c: torch.empty((rows, 2, nb, c), dtype=torch.float32, device=gout.device) for c, rows in bank_rows.items()}
+        bank_next = {c: 0 for c in bank_rows}
+        bank_slot = {}
         for i in reversed(range(L)):
             st = stages[i]
             cw, cb, gam, bet = P[i]
@@ -312,10 +322,12 @@ class _StageFunction(torch.autograd.Function):
                     gextra[j] = ge
                 d_raw = torch.empty_like(raw)
                 gtotal = torch.empty(raw.shape, dtype=gdt, device=raw.device) if st.res_from is not None else None
-                s12 = ops.instnorm_bwd(raw, mean, rstd, gam.detach(), bet.detach(), gpad[j], node_pad[j],
-                                       gextra[j], st.relu, d_raw, gtotal)
-                g12 = s12.view(2, n, c).sum(1)       # per-(n,c) sums of g' and g'*xhat -> dbeta, dgamma in one reduction
-                g_bet, g_gam = g12[0], g12[1]
+                slot = bank_next[c]
+                bank_next[c] += 1
+                bank_slot[i] = (c, slot)
+                ops.instnorm_bwd(raw, mean, rstd, gam.detach(), bet.detach(), gpad[j], node_pad[j],
+                                 gextra[j], st.relu, d_raw, gtotal, s12=banks[c][slot].view(2, n * c))
+                g_bet = g_gam = None                 # filled from the bank reductions after the loop
                 g_cb = zeros.take(st.cout)           # exactly zero under InstanceNorm
                 if gtotal is not None:
                     assert gextra[st.res_from + 1] is None
@@ -395,7 +407,13 @@ class _StageFunction(torch.autograd.Function):
                     ops.copy_image(d_raw, src)
                 ops.conv_gather(src, wpd, dl, g_in, tensor=ctx.mode == "fast" and ops.tc_eligible(src, st.cin))
                 gpad[i] = g_in
-            grads.append((g_cw, g_cb, g_gam, g_bet))
+            grads.append([g_cw, g_cb, g_gam, g_bet, i])
+        reduced = {c: bank.sum(2) for c, bank in banks.items()}       # [layer][2][c]: dbeta = [.,0], dgamma = [.,1]
+        for gr in grads:
+            if gr[4] in bank_slot:
+                c, slot = bank_slot[gr[4]]
+                gr[3], gr[2] = reduced[c][slot, 0], reduced[c][slot, 1]
+        grads = [tuple(gr[:4]) for gr in grads]
         grads.reverse()
         flat = []
         for st, (g_cw, g_cb, g_gam, g_bet) in zip(stages, grads):

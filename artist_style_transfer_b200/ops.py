@@ -213,11 +213,12 @@ def _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=No
     return out
 
 
-def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None):
+def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None, s12=None):
     """Returns s12 of shape (2, N*C): dbeta = s12[0].view(N,C).sum(0), dgamma = s12[1].view(N,C).sum(0); fills dx
-    (and gtotal)."""
+    (and gtotal).  `s12` may be a caller-provided (2, N*C) fp32 view (e.g. a slice of one buffer shared by layers)."""
     n, _, _, c = x.shape
-    s12 = torch.empty((2, n * c), dtype=torch.float32, device=x.device)     # one allocation: the caller reduces both
+    if s12 is None:
+        s12 = torch.empty((2, n * c), dtype=torch.float32, device=x.device)  # one allocation: the caller reduces both
     s1, s2 = s12[0], s12[1]                                                  # over the batch with one kernel
     lib = _lib.load()
     xi, gp, ge, dxi, gt = image(x), image(gpad), image(gextra), image(dx), image(gtotal)
@@ -312,9 +313,9 @@ def instnorm_apply(x, mean, rstd, gamma, beta, out, pad, relu, residual=None):
         return _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=residual)
 
 
-def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None):
+def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None, s12=None):
     with _timed("instnorm" + (f"|bwd{tuple(x.shape)}" if PROFILE_DETAIL and _prof is not None else "")):
-        return _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=gtotal)
+        return _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=gtotal, s12=s12)
 
 
 def maxpool2_fwd(x):
