@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("AST_B200_LIB") or os.path.join(_HERE, "libast_b200.so
 AST_F32, AST_BF16 = 0, 1
 AST_MAX_TAPS = 81
 CONV_RELU, CONV_REFLECT, CONV_TENSOR = 1, 2, 4
+CONV_POOL_ONLY = 16
 
 _DTYPES = {torch.float32: AST_F32, torch.bfloat16: AST_BF16}
 
@@ -29,7 +30,7 @@ class GatherGeom(ctypes.Structure):
                 ("oy0", ctypes.c_int32), ("ox0", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("flags", ctypes.c_int32),
                 ("dy", ctypes.c_int16 * AST_MAX_TAPS), ("dx", ctypes.c_int16 * AST_MAX_TAPS),
-                ("w_img_stride", ctypes.c_int64), ("stats", ctypes.c_void_p)]
+                ("w_img_stride", ctypes.c_int64), ("stats", ctypes.c_void_p), ("pooled", ctypes.POINTER(Image))]
 
 
 _lib = None

@@ -219,7 +219,7 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
                    bool resident_only, cudaStream_t stream) {
-  if (thin || (cpad != 64 && cpad != 128) || out->c != cpad) return 0;
+  if (thin || g->pooled || (cpad != 64 && cpad != 128) || out->c != cpad) return 0;
   if (!img32_ok(out) || !img32_ok(add) || !img32_ok(mask)) return 0;
   const int esz = in->dtype == AST_F32 ? 4 : 2;
   EncodeTiledFn encode = get_encode();

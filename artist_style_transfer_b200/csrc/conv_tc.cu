@@ -330,6 +330,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (px_mode >= 1)     // resident-weight form first (mode 2: any form)
     if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, px_mode == 1, stream)) return pr == 1 ? 0 : pr;
   if (int wr = conv_gather_ws(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return wr == 1 ? 0 : wr;
+  AST_CHECK_ARG(!g->pooled, "conv_tc: a pooled output needs the weight-stationary kernel (stride 1, filter resident in smem)");
   if (px_mode == 1)
     if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, false, stream)) return pr == 1 ? 0 : pr;
 

@@ -56,7 +56,7 @@ template <int KIND, int MINB>
 __global__ void __launch_bounds__(WS_THREADS, MINB)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
-               float* __restrict__ stats) {
+               float* __restrict__ stats, const Img pooled) {
   pdl_sync();   // programmatic dependent launch: see common.cuh
   pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
@@ -226,7 +226,8 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
       EpiRows rows;
-      if (!p.thin) tc_epi_row_offsets(valid ? img_off(out, img, oy, ox, 0) : -1, lane, out.dtype == AST_F32, rows);
+      const bool store_out = !(p.flags & AST_CONV_POOL_ONLY);
+      if (!p.thin) tc_epi_row_offsets((valid && store_out) ? img_off(out, img, oy, ox, 0) : -1, lane, out.dtype == AST_F32, rows);
       for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
         float v[32];
         tc_ld32(taddr0 + c0, v);
@@ -237,6 +238,20 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           if (stats) tc_epi_stats(v, valid, stats + ((long long)img * p.cout_valid + co) * 2, lane);
           tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
                                   pm, use_pm && c0 == cpar * 32);
+          if (pooled.ptr) {
+            // nn.MaxPool2d(2, 2) of the finished values (v was updated in place): a tile row is 8 pixels and a warp owns 4
+            // tile rows, so the 2x2 window of pixel (ty, tx) = lanes l, l^1 (x neighbour), l^8 (y neighbour), l^9
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float m = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
+              v[e] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            }
+            if (!(lane & 9) && i + 1 < p.mi && j + 1 < p.mj && co < p.cout) {   // even (ty, tx), window fully inside
+              const long long po = img_off(pooled, img, i >> 1, j >> 1, co);
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) st4_img(pooled, po + e, v + e);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -431,6 +446,13 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
                                           // 3 = also stream weights for big layers, 9 = base_offset experiment
   if (mode == 0) return 0;
   if (g->si != 1 || g->w_img_stride != 0) return 0;
+  if (g->pooled) {          // fused MaxPool2d(2,2) output: plain stride-1 launches with a full NHWC output only
+    const ast_image* q = g->pooled;
+    if (thin || g->so != 1 || g->oy0 != 0 || g->ox0 != 0) return 0;
+    AST_CHECK_ARG(q->n == in->n && q->h == g->mi / 2 && q->w == g->mj / 2 && q->c == out->c && q->sc == 1 &&
+                  q->sw % 4 == 0 && q->sh % 4 == 0 && q->sn % 4 == 0 && ((uintptr_t)q->ptr & 15) == 0,
+                  "conv_ws: pooled must be [n, mi/2, mj/2, cout] NHWC with 16-byte aligned pixels");
+  }
   const int esz = in->dtype == AST_F32 ? 4 : 2;
   int dy_min = 1 << 30, dy_max = -(1 << 30), dx_min = 1 << 30, dx_max = -(1 << 30);
   for (int t = 0; t < g->ntaps; ++t) {
@@ -458,7 +480,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   static const int swap_env = [] { const char* e = getenv("AST_WS_SWAP"); return e ? atoi(e) : 0; }();
   bool swap = false;
   p.th = WS_TH;
-  if (swap_env && !thin && p.n_tiles_n == 1 && (cpad == 32 || cpad == 64 || cpad == 128) && out->c == cpad &&
+  if (swap_env && !g->pooled && !thin && p.n_tiles_n == 1 && (cpad == 32 || cpad == 64 || cpad == 128) && out->c == cpad &&
       img32_ok(out) && img32_ok(add) && img32_ok(mask)) {
     const int pb = (p.pw * (32 + (dy_max - dy_min)) * p.rowb + 1023) & ~1023;
     if (budget >= 2 * pb) { swap = true; p.th = 32; }
@@ -551,10 +573,11 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   const int max_ctas = (two ? 2 : 1) * num_sms();
   const int grid = (int)(p.total_tiles < max_ctas ? p.total_tiles : max_ctas);
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
+  Img pooli = g->pooled ? to_img(g->pooled) : null_img();
   cudaError_t e;
 #define WS_LAUNCH(K, B)                                                                                          \
   e = cudaFuncSetAttribute(conv_ws_kernel<K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-  if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats)
+  if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats, pooli)
   if (in->dtype == AST_BF16) {
     if (two) { WS_LAUNCH(0, 2); } else { WS_LAUNCH(0, 1); }
   } else {

@@ -310,6 +310,7 @@ extern "C" int ast_conv_gather(const ast_image* in, const void* weights, const f
   AST_CHECK_ARG(!mask || same_shape(mask, out), "ast_conv_gather: mask image shape mismatch");
   AST_CHECK_ARG(in->dtype == AST_F32 || in->dtype == AST_BF16, "ast_conv_gather: bad input dtype");
   AST_CHECK_ARG(!geom->stats || (geom->flags & AST_CONV_TENSOR), "ast_conv_gather: fused statistics are a tensor-core epilogue feature");
+  AST_CHECK_ARG(!geom->pooled || (geom->flags & AST_CONV_TENSOR), "ast_conv_gather: the pooled output is a tensor-core epilogue feature");
   if (geom->flags & AST_CONV_TENSOR)
     return conv_gather_tc(in, weights, bias, in_shift, add, mask, out, geom, (cudaStream_t)stream);
   if (in->n == 0 || out->c == 0) return 0;

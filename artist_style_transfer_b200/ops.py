@@ -55,7 +55,7 @@ def profile_end():
     return out
 
 
-def _geom(launch, flags=0, w_img_stride=0, stats=None):
+def _geom(launch, flags=0, w_img_stride=0, stats=None, pooled=None):
     g = GatherGeom()
     g.mi, g.mj, g.si, g.so, g.oy0, g.ox0 = launch.mi, launch.mj, launch.si, launch.so, launch.oy0, launch.ox0
     g.ntaps = len(launch.taps)
@@ -65,6 +65,9 @@ def _geom(launch, flags=0, w_img_stride=0, stats=None):
         g.dx[t] = dx
     g.w_img_stride = w_img_stride
     g.stats = None if stats is None else stats.data_ptr()
+    if pooled is not None:
+        g._pooled_img = pooled                      # keep the ctypes struct alive as long as the geometry
+        g.pooled = _lib.ctypes.pointer(pooled)
     return g
 
 
@@ -146,16 +149,19 @@ def tc_eligible(x, cout):
 
 
 def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
-                reflect=False, tensor=False, w_img_stride=0, round_tf32=False, stats=None):
-    """Run every launch of an op. x/out/add/mask: (N,H,W,C)-ordered tensors; wpacked: [taps][cout][cin]."""
+                reflect=False, tensor=False, w_img_stride=0, round_tf32=False, stats=None, pooled=None,
+                pool_only=False):
+    """Run every launch of an op. x/out/add/mask: (N,H,W,C)-ordered tensors; wpacked: [taps][cout][cin].
+    pooled: optional (N,H/2,W/2,C) tensor receiving MaxPool2d(2,2) of the result (weight-stationary kernel only)."""
     lib = _lib.load()
     flags = ((CONV_RELU if relu else 0) | (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
-             | (CONV_ROUND_TF32 if round_tf32 else 0))
+             | (CONV_ROUND_TF32 if round_tf32 else 0) | (_lib.CONV_POOL_ONLY if pool_only else 0))
     xi, oi, ai, mi = image(x), image(out), image(add), image(mask)
+    pooled = image(pooled)
     cout, cin = wpacked.shape[-2], wpacked.shape[-1]
     esz = wpacked.element_size()
     for l in launches:
-        g = _geom(l, flags, w_img_stride, stats)
+        g = _geom(l, flags, w_img_stride, stats, pooled)
         wp = _lib.ctypes.c_void_p(wpacked.data_ptr() + l.woff * cout * cin * esz)
         check(lib.ast_conv_gather(ref(xi), wp, ptr(bias), ptr(in_shift), ref(ai), ref(mi), ref(oi), ref(g),
                                   stream_ptr()), "ast_conv_gather")
@@ -285,14 +291,14 @@ def pack_weights(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
 
 
 def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False, reflect=False,
-                tensor=False, w_img_stride=0, round_tf32=False, stats=None):
+                tensor=False, w_img_stride=0, round_tf32=False, stats=None, pooled=None, pool_only=False):
     label = "conv_gather_tc" if tensor else "conv_gather_simt"
     if PROFILE_DETAIL and _prof is not None:
         label += f"|{tuple(x.shape)}->{tuple(out.shape)} taps={sum(len(l.taps) for l in launches)} {str(x.dtype)[6:]}"
     with _timed(label):
         return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu,
                                  reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32,
-                                 stats=stats)
+                                 stats=stats, pooled=pooled, pool_only=pool_only)
 
 
 def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False, tensor=False):

@@ -44,6 +44,10 @@ def _vgg_layout():
     return layers
 
 
+def _fuse_pool():
+    return os.environ.get("AST_FUSE_POOL", "1") == "1"
+
+
 def _vgg_bwd_bf16():
     return os.environ.get("AST_VGG_BWD", "bf16") != "tf32"
 
@@ -52,7 +56,7 @@ class _VGGFunction(torch.autograd.Function):
     """conv3x3(pad 1)+ReLU / maxpool chain up to `upto`, returning the tapped activations (NCHW views)."""
 
     @staticmethod
-    def forward(ctx, x, module, upto, shift, *weights):
+    def forward(ctx, x, module, upto, shift, only_last, *weights):
         if not x.is_cuda:
             raise RuntimeError("VGG16 kernels run on CUDA only (no CPU fallback)")
         tensor = module._mode() == "fast" and _lib.has_tc_conv()
@@ -61,6 +65,7 @@ class _VGGFunction(torch.autograd.Function):
         dev = x32.device
         cur = x32.permute(0, 2, 3, 1)            # NCHW tensor described as an (N,H,W,C) view; conv1_1 reads it directly
         acts, taps, plan = {}, [], []
+        pooled_next = None
         packed = module._packed(tensor)
         for idx, kind, cin, cout in module._layout:
             if idx > upto:
@@ -80,18 +85,38 @@ class _VGGFunction(torch.autograd.Function):
                 launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
                 out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
                 wp, bias = packed[idx]
-                ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None, relu=True,
-                                tensor=tensor and ops.tc_eligible(cur, cout), round_tf32=tensor)
+                use_tc = tensor and ops.tc_eligible(cur, cout)
+                # conv1_2 -> ReLU -> MaxPool2d: the weight-stationary kernel also writes the pooled tensor (saves the pool
+                # kernel's 537 MB read at B=32); when nothing needs the full-resolution relu1_2 (no-grad content branch
+                # asking only for its last tap) it is not even stored
+                fuse_pool = (use_tc and _fuse_pool() and cin == 64 and cout == 64 and idx + 2 <= upto
+                             and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0)
+                if fuse_pool:
+                    pooled_next = torch.empty((n, cur.shape[1] // 2, cur.shape[2] // 2, cout), dtype=torch.float32, device=dev)
+                    skip_full = only_last and not ctx.needs_input_grad[0]
+                    ops.conv_gather(cur, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True,
+                                    pooled=pooled_next, pool_only=skip_full)
+                    if skip_full:
+                        out = None
+                else:
+                    ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None, relu=True,
+                                    tensor=use_tc, round_tf32=tensor)
                 plan.append((idx, "conv", cur, out))
                 cur = out
             elif kind == "pool":
-                out = ops.maxpool2_fwd(cur)
+                if pooled_next is not None:
+                    out, pooled_next = pooled_next, None
+                else:
+                    out = ops.maxpool2_fwd(cur)
                 plan.append((idx, "pool", cur, out))
                 cur = out
-            if idx in _TAPS:
+            if idx in _TAPS and cur is not None:
                 taps.append((idx, cur))
         ctx.module, ctx.plan, ctx.tensor = module, plan, tensor
         ctx.tap_idx = [i for i, _ in taps]
+        if only_last:
+            taps = taps[-1:]
+            ctx.tap_idx = ctx.tap_idx[-1:]
         outs = tuple(t.permute(0, 3, 1, 2) for _, t in taps)
         return outs
 
@@ -150,7 +175,7 @@ class _VGGFunction(torch.autograd.Function):
                 ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc, round_tf32=tensor and not bf16_bwd)
             g = gin
         ctx.plan = None
-        return (gx, None, None, None) + tuple(None for _ in module._weights())
+        return (gx, None, None, None, None) + tuple(None for _ in module._weights())
 
 
 class VGG16(nn.Module, _cnn._Precision):
@@ -226,7 +251,7 @@ class VGG16(nn.Module, _cnn._Precision):
             self._pack_cache["dgrad_key"], self._pack_cache["dgrad"] = key, out
         return self._pack_cache["dgrad"]
 
-    def forward(self, x, shift=None, upto=None):
+    def forward(self, x, shift=None, upto=None, only_last=False):
         if self.just_content or upto == "relu2_2":
             last = 8
         elif upto is None or upto == "relu4_3":
@@ -235,10 +260,12 @@ class VGG16(nn.Module, _cnn._Precision):
             last = {v: k for k, v in _TAPS.items()}[upto]
         if x.dim() == 3:
             x = x.unsqueeze(0)
-        outs = _VGGFunction.apply(x, self, last, shift, *self._weights())
+        outs = _VGGFunction.apply(x, self, last, shift, bool(only_last or self.just_content), *self._weights())
         if self.just_content:
             return outs[-1]                                        # train_cnn.py:64-68
         names = [v for k, v in _TAPS.items() if k <= last]
+        if only_last:                                              # only the deepest requested tap is materialised
+            names = names[-1:]
         return dict(zip(names, outs))                              # insertion order relu1_2..relu4_3 (:70-77)
 
 
@@ -420,7 +447,7 @@ def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CON
     shift = neg_mean(content_batch.device)
     generated = transfer(content_batch)                                        # :299
     with torch.no_grad():
-        content_feat = vgg(content_batch, shift=shift, upto="relu2_2")["relu2_2"]   # :300
+        content_feat = vgg(content_batch, shift=shift, upto="relu2_2", only_last=True)["relu2_2"]   # :300
     gen_feats = vgg(generated, shift=shift)                                    # :301
     # :307-308 and the relu2_2 Gram of :321-325 as ONE autograd node (the weight is folded into the kernel; with
     # backward=True the upstream gradient of the content term is exactly 1)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 3
+#define AST_ABI_VERSION 4
 
 typedef enum { AST_F32 = 0, AST_BF16 = 1, AST_TF32 = 2 /* fp32 storage rounded to TF32; pack_weights only */ } ast_dtype;
 
@@ -61,10 +61,16 @@ typedef struct {
   float*  stats;           /* optional fp32 [n][cout][2] (sum x, sum x^2 of the fp32 results, BEFORE bias/activation),
                               accumulated by the tensor-core epilogue: InstanceNorm statistics fused into the producing
                               conv (cnn.py:63,68).  Zeroed by the caller; NULL = off; tensor-core launches only. */
+  const ast_image* pooled; /* optional [n, mi/2, mj/2, cout]: nn.MaxPool2d(2, 2) of the epilogue result, written by the same
+                              kernel (torchvision VGG16 features idx 4/9/16 after the conv+ReLU before them,
+                              train_cnn.py:54,72-73).  Plain stride-1 launches (so = 1, no phase offset) of the
+                              weight-stationary tensor-core kernel only: any other request is an error.  With
+                              AST_CONV_POOL_ONLY the full-resolution `out` is not written (no-grad content branch). */
 } ast_gather_geom;
 
 #define AST_CONV_RELU     1   /* epilogue max(v,0)                       (nn.ReLU, train_cnn.py VGG idx 1,3,...)   */
 #define AST_CONV_REFLECT  2   /* mirror out-of-range input coordinates   (nn.ReflectionPad2d, cnn.py:58)          */
+#define AST_CONV_POOL_ONLY 16  /* with geom.pooled: skip the store of the full-resolution output                      */
 #define AST_CONV_TENSOR   4   /* request the tcgen05/TMA kernel; error if the shape is not supported              */
 #define AST_CONV_ROUND_TF32 8 /* round the fp32 result to TF32 (cvt.rna) so a kind::tf32 consumer sees exact operands */
 

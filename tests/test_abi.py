@@ -21,7 +21,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ast.h but not exported by libast_b200.so"
     assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
-    assert lib.ast_abi_version() == 3
+    assert lib.ast_abi_version() == 4
     assert lib.ast_instnorm_workspace_bytes(4, 128) > 0
     assert lib.ast_launch_count() >= 0
 

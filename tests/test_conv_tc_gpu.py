@@ -198,3 +198,38 @@ def test_gram_tc(env, c, h, w, n):
     ref = port.gram(f.double().cpu().permute(0, 3, 1, 2))
     assert rel(g_tc, ref) < 1e-5, rel(g_tc, ref)
     assert float((g_tc - g_tc.transpose(1, 2)).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("pool_only", [False, True])
+def test_conv_ws_fused_maxpool(env, pool_only):
+    """ast_gather_geom.pooled: the weight-stationary kernel also writes MaxPool2d(2,2) of conv+bias+ReLU (VGG conv1_2 ->
+    pool, train_cnn.py:54,72-73); with AST_CONV_POOL_ONLY the full-resolution output is left untouched."""
+    cg, ops = env
+    torch.manual_seed(11)
+    n, h, w, c = 2, 20, 24, 64
+    x = torch.randn(n, h, w, c, device="cuda")
+    wt = torch.randn(c, c, 3, 3, device="cuda") / 24
+    bias = torch.randn(c, device="cuda")
+    launches = cg.conv_fwd(3, 1, 1, h, w)
+    wp = ops.pack_weights(wt, launches, c, c, c * 9, 9, 3, 1, ops.TF32)
+    y = torch.full((n, h, w, c), -7.0, device="cuda")
+    yp = torch.empty(n, h // 2, w // 2, c, device="cuda")
+    ops.conv_gather(x, wp, launches, y, bias=bias, relu=True, tensor=True, pooled=yp, pool_only=pool_only)
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2).double().cpu(), wt.double().cpu(), bias.double().cpu(), padding=1))
+    refp = F.max_pool2d(ref, 2, 2).permute(0, 2, 3, 1)
+    assert rel(yp, refp) < 2e-3                      # TF32 operands
+    if pool_only:
+        assert bool((y == -7.0).all())
+    else:
+        assert rel(y, ref.permute(0, 2, 3, 1)) < 2e-3
+        assert torch.equal(yp, F.max_pool2d(y.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))   # pooling itself is exact
+
+
+def test_conv_pooled_rejected_where_unsupported(env):
+    cg, ops = env
+    x = torch.randn(1, 8, 8, 512, device="cuda")
+    wp = torch.randn(9, 512, 512, device="cuda")
+    y = torch.empty(1, 8, 8, 512, device="cuda")
+    yp = torch.empty(1, 4, 4, 512, device="cuda")
+    with pytest.raises(RuntimeError, match="pooled"):
+        ops.conv_gather(x, wp, cg.conv_fwd(3, 1, 1, 8, 8), y, tensor=True, pooled=yp)
