@@ -3,12 +3,17 @@
 //   D[128 pixels x BN couts] (fp32, TMEM)  +=  A_tap[128 pixels x KC cin] (smem, TMA)  x  W_tap[BN x KC]^T (smem, TMA)
 //
 // One persistent CTA per SM, warp-specialised (DESIGN.md "conv_tc"):
-//   warp 0      TMA producer: per (tap, cin-chunk) one 4-D box of the NHWC activation tensor (OOB = zero padding,
-//               elementStrides = input stride) and one 2-D box of the packed weights, 128B/64B-swizzled, K-major
+//   warp 0      TMA producers (up to 4 lanes take the stages round-robin): per (tap, cin-chunk) one 4-D box of the
+//               NHWC activation tensor (OOB = zero padding, elementStrides = input stride) and one 2-D box of the
+//               packed weights, 128B/64B-swizzled, K-major
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::f16 for bf16, kind::tf32 for fp32 data),
 //               tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32x32b -> bias / tap-gradient add / ReLU / ReLU-mask / tf32 rounding ->
-//               16-byte vector stores straight to the NHWC output (double-buffered accumulator in TMEM)
+//   warps 2-9   epilogue (two warps per TMEM lane quarter): tcgen05.ld 32x32b -> fused InstanceNorm sums / bias /
+//               tap-gradient add / ReLU / ReLU-mask / tf32 rounding -> smem-transposed 16-byte stores to the NHWC
+//               output (double-buffered accumulator in TMEM)
+// This file is the dispatcher of the tensor-core convolutions as well: conv_gather_tc() first offers a launch to the
+// weight-stationary kernel (conv_ws.cu) and to the pixels-as-N kernel (conv_px.cu, cout 64/128) and runs the kernel below
+// for everything else (256/512-channel layers, short K loops, 3-channel "thin" outputs, per-image weights).
 // Replaces cuDNN/oneDNN convolution forward / backward-data at the call sites listed in include/ast.h.
 #include "tc_common.cuh"
 
