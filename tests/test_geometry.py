@@ -93,3 +93,22 @@ def test_sizes():
     assert cg.convT_out_size(64, 3, 2, 1, 1) == 128
     assert sum(len(l.taps) for l in cg.convT_fwd(3, 2, 1, 1, 8, 8)) == 9
     assert [len(l.taps) for l in cg.convT_fwd(3, 2, 1, 1, 8, 8)] == [1, 2, 2, 4]      # SURVEY 8c sub-pixel phases
+
+
+def test_zero_arena_slices_are_disjoint_aligned_and_zero():
+    """cnn._ZeroArena: one zero buffer carved into 16-byte aligned, non-overlapping accumulators."""
+    import torch
+    from artist_style_transfer_b200.cnn import _ZeroArena
+    sizes = [5, 64, 3 * 7, 1]
+    arena = _ZeroArena(sizes, torch.device("cpu"))
+    views = [arena.take(5), arena.take(8, 8), arena.take(3, 7), arena.take(1)]
+    base = arena.buf.data_ptr()
+    spans = []
+    for v, n in zip(views, sizes):
+        assert v.numel() == n and float(v.abs().sum()) == 0.0
+        assert (v.data_ptr() - base) % 16 == 0
+        spans.append((v.data_ptr() - base, v.data_ptr() - base + 4 * n))
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    views[1].fill_(1.0)
+    assert float(views[0].sum()) == 0.0 and float(views[2].sum()) == 0.0
