@@ -44,6 +44,10 @@ def _vgg_layout():
     return layers
 
 
+def _conv11_fold():
+    return os.environ.get("AST_CONV11_FOLD", "1") == "1"
+
+
 def _fuse_pool():
     return os.environ.get("AST_FUSE_POOL", "1") == "1"
 
@@ -160,8 +164,20 @@ class _VGGFunction(torch.autograd.Function):
             # g is d/d(relu out) masked == d/d(conv out).  dgrad to the conv input:
             if idx == 0:
                 gx = torch.empty((out.shape[0], 3, out.shape[1], out.shape[2]), dtype=torch.float32, device=g.device)
-                launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
-                ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1), tensor=tensor)
+                if tensor and _conv11_fold() and g.dtype == torch.bfloat16:
+                    # d(image) of conv1_1 as 3 VERTICAL taps whose 9 (of 32) output channels are the partial sums of the
+                    # 3 horizontal taps x 3 image channels, finished by ast_fold_rows - 12 instead of 36 N=32 MMAs per
+                    # 128 pixels and no strided 3-channel epilogue:
+                    #   P[a][u][kx][ci] = sum_{ky,co} g[a-ky+1][u][co] W[co][ci][ky][kx],  gx[a][b][ci] = sum_kx P[a][b-kx+1][kx][ci]
+                    hh, ww = out.shape[1], out.shape[2]
+                    part = torch.empty((out.shape[0], hh, ww + 2, 32), dtype=torch.float32, device=g.device)
+                    taps = [(1 - ky, -1) for ky in range(3)]
+                    lv = [cg.Launch(hh, ww + 2, 1, 1, 0, 0, taps, [(ky, 0) for ky in range(3)], 0)]
+                    ops.conv_gather(g, module._packed_conv11_vdgrad(g.dtype), lv, part, tensor=True)
+                    ops.fold_rows(part, gx.permute(0, 2, 3, 1), 3)
+                else:
+                    launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
+                    ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1), tensor=tensor)
                 break
             launches = cg.conv_dgrad(3, 1, 1, xin.shape[1], xin.shape[2])
             gin = torch.empty(xin.shape, dtype=gdt, device=g.device)
@@ -250,6 +266,18 @@ class VGG16(nn.Module, _cnn._Precision):
                     out[idx] = ops.pack_weights(w, launches, cin, cout, 9, cin * 9, 3, 1, wdt)
             self._pack_cache["dgrad_key"], self._pack_cache["dgrad"] = key, out
         return self._pack_cache["dgrad"]
+
+    def _packed_conv11_vdgrad(self, dtype):
+        """[ky][d*3 + ci (9 of 32)][co] = W[co][ci][ky][2 - d]: conv1_1's data gradient as a 3-vertical-tap conv with the
+        horizontal taps in the output channels (see _VGGFunction.backward); cached like the other packs."""
+        key = self._cache_key("c11v", dtype)
+        if self._pack_cache.get("c11v_key") != key:
+            w = self.features[0].weight.detach().float()                       # (64, 3, 3, 3) = [co][ci][ky][kx]
+            wv = w.flip(3).permute(2, 3, 1, 0).reshape(3, 9, w.shape[0])       # [ky][d*3+ci][co]
+            pk = torch.zeros((3, 32, w.shape[0]), dtype=torch.float32, device=w.device)
+            pk[:, :9, :] = wv
+            self._pack_cache["c11v_key"], self._pack_cache["c11v"] = key, pk.to(dtype).contiguous()
+        return self._pack_cache["c11v"]
 
     def forward(self, x, shift=None, upto=None, only_last=False):
         if self.just_content or upto == "relu2_2":
