@@ -28,7 +28,7 @@ struct Rows {            // dense-row tensor: element offset of pixel (n, i, j) 
 
 struct NsShape {
   int C, H, W, pad;
-  int rows;              // image rows per block
+  int nblk;              // blocks per image: block b owns rows [b*R/nblk, (b+1)*R/nblk) of the R iterated rows
   int seg, nseg;         // pixels per row segment (of the iterated row), segments per row
   int stages, slab_bytes;
 };
@@ -119,7 +119,7 @@ in_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* __re
   ns_init(full, empty, sh.stages);
   const int n = blockIdx.y, C = sh.C;
   const int OH = sh.H + 2 * sh.pad, OW = sh.W + 2 * sh.pad;
-  const int rbeg = blockIdx.x * sh.rows, rend = min(OH, rbeg + sh.rows);
+  const int rbeg = (int)((long long)blockIdx.x * OH / sh.nblk), rend = (int)((long long)(blockIdx.x + 1) * OH / sh.nblk);
   const int nunits = (rend - rbeg) * sh.nseg;
   const int nslabs = res.ptr ? 2 : 1;
   const int stage_bytes = nslabs * sh.slab_bytes;
@@ -273,7 +273,7 @@ in_bwd_stats_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
   const unsigned buf = (smem_u32(smem_raw) + 127u) & ~127u;
   ns_init(full, empty, sh.stages);
   const int n = blockIdx.y, C = sh.C;
-  const int rbeg = blockIdx.x * sh.rows, rend = min(sh.H, rbeg + sh.rows);
+  const int rbeg = (int)((long long)blockIdx.x * sh.H / sh.nblk), rend = (int)((long long)(blockIdx.x + 1) * sh.H / sh.nblk);
   const int nunits = (rend - rbeg) * sh.nseg;
   const int nslabs = 1 + (gpad.ptr ? 1 : 0) + (gextra.ptr ? 1 : 0);
   const int stage_bytes = nslabs * sh.slab_bytes;
@@ -345,7 +345,7 @@ in_bwd_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
   const unsigned buf = (smem_u32(smem_raw) + 127u) & ~127u;
   ns_init(full, empty, sh.stages);
   const int n = blockIdx.y, C = sh.C;
-  const int rbeg = blockIdx.x * sh.rows, rend = min(sh.H, rbeg + sh.rows);
+  const int rbeg = (int)((long long)blockIdx.x * sh.H / sh.nblk), rend = (int)((long long)(blockIdx.x + 1) * sh.H / sh.nblk);
   const int nunits = (rend - rbeg) * sh.nseg;
   const int nslabs = 1 + (gpad.ptr ? 1 : 0) + (gextra.ptr ? 1 : 0);
   const int stage_bytes = nslabs * sh.slab_bytes;
@@ -428,11 +428,13 @@ static bool ns_plan(NsShape* sh, int n, int C, int H, int W, int pad, int rows_t
   sh->stages = NS_SMEM_BUDGET / (nslabs * sh->slab_bytes);
   if (sh->stages > NS_MAX_STAGES) sh->stages = NS_MAX_STAGES;
   if (sh->stages < 2) return false;
+  // as many blocks per image as fit one wave of 2 blocks per SM; rows are split proportionally (7/8 rows each at
+  // H = 64, B = 32: 288 of the 296 block slots busy instead of 256 with a fixed 8 rows per block)
   int nb = (2 * num_sms()) / n;
   if (nb > rows_total) nb = rows_total;
   if (nb < 1) nb = 1;
-  sh->rows = (rows_total + nb - 1) / nb;
-  *nblk = (rows_total + sh->rows - 1) / sh->rows;
+  sh->nblk = nb;
+  *nblk = nb;
   return true;
 }
 
