@@ -51,3 +51,31 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
                 assert "/root/reference" not in src or f.endswith(".py"), f
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of ast_image and ast_gather_geom as gcc sees include/ast.h == the ctypes mirror in _lib.py
+    (a silent mismatch would shift every field after it, e.g. the `stats` / `pooled` pointers)."""
+    import shutil
+    import subprocess
+    from artist_style_transfer_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "ast.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu\\n", sizeof(ast_image), offsetof(ast_image, sn), offsetof(ast_image, c), offsetof(ast_image, sc));\n'
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ast_gather_geom), offsetof(ast_gather_geom, dy), offsetof(ast_gather_geom, dx),\n'
+        '         offsetof(ast_gather_geom, w_img_stride), offsetof(ast_gather_geom, stats), offsetof(ast_gather_geom, pooled));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = [int(v) for v in out]
+    img, geom = _lib.Image, _lib.GatherGeom
+    want = [ctypes.sizeof(img), img.sn.offset, img.c.offset, img.sc.offset,
+            ctypes.sizeof(geom), geom.dy.offset, geom.dx.offset, geom.w_img_stride.offset, geom.stats.offset,
+            geom.pooled.offset]
+    assert got == want, (got, want)
