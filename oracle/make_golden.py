@@ -50,6 +50,20 @@ def summarize_gram(g):
             "fro": g.flatten(1).norm(dim=1).numpy(), "sum": g.flatten(1).sum(dim=1).numpy()}
 
 
+def run_forward(cnn, train_cnn, batch, height, width, dtype, seed=2):
+    """StyleTransfer.forward (cnn.py:45-49) alone at an arbitrary H x W (BASELINE config 4: 1080 x 1920 stylisation,
+    inference.py:115)."""
+    from oracle import weights
+    tsd = weights.transfer_state_dict(seed)
+    transfer, _ = build_reference_nets(cnn, train_cnn, tsd, weights.vgg_state_dict(seed), dtype)
+    content = weights.content_batch(batch, height, seed, width=width).to(dtype)
+    with torch.no_grad():
+        gen = transfer(content).double()
+    sy, sx = max(1, height // 32), max(1, width // 32)
+    return {"generated_sub": gen[:, :, ::sy, ::sx].numpy(), "generated_norm": np.array(float(gen.norm())),
+            "generated_rowsum": gen.sum(dim=3).numpy(), "generated_colsum": gen.sum(dim=2).numpy()}
+
+
 def run_step(cnn, train_cnn, batch, size, dtype, seed=2, with_grads=True):
     """Body of train_cnn.py:295-333 with method 0 ('random') style setup :184-190."""
     from oracle import weights
@@ -130,6 +144,12 @@ def main():
         ("step_b4_s256_f32", lambda: run_step(cnn, train_cnn, 4, 256, torch.float32)),
         ("step_b4_s256_f64", lambda: run_step(cnn, train_cnn, 4, 256, torch.float64)),
         ("smartavg_b2_s64_n5_f64", lambda: run_smartaverage(cnn, train_cnn, 2, 64, 5, torch.float64)),
+        # BASELINE configs[1] at the bench's own batch (B=32/GPU), configs[2] smartaverage at 512^2, configs[3] 1080p
+        # stylisation, configs[4] 1024^2 step (relu1_2 Gram with K = 1,048,576): fp32 = north_star's "PyTorch fp32 path"
+        ("step_b32_s256_f32", lambda: run_step(cnn, train_cnn, 32, 256, torch.float32, with_grads=False)),
+        ("smartavg_b1_s512_n8_f32", lambda: run_smartaverage(cnn, train_cnn, 1, 512, 8, torch.float32)),
+        ("fwd_b1_1080x1920_f64", lambda: run_forward(cnn, train_cnn, 1, 1080, 1920, torch.float64)),
+        ("step_b1_s1024_f32", lambda: run_step(cnn, train_cnn, 1, 1024, torch.float32, with_grads=False)),
     ]
     only = set(sys.argv[1:])
     for name, fn in jobs:
