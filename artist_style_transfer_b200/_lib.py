@@ -11,12 +11,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AST_B200_LIB points at another build of the same library (kernel A/B experiments); default: the in-tree build
 LIB_PATH = os.environ.get("AST_B200_LIB") or os.path.join(_HERE, "libast_b200.so")
 
-AST_F32, AST_BF16 = 0, 1
+AST_F32, AST_BF16, AST_TF32, AST_U8 = 0, 1, 2, 3
 AST_MAX_TAPS = 81
 CONV_RELU, CONV_REFLECT, CONV_TENSOR = 1, 2, 4
 CONV_POOL_ONLY = 16
+IN_SUMS_ZEROED = 2
+GRAM_COUNTERS_PER_IMAGE = 16
 
-_DTYPES = {torch.float32: AST_F32, torch.bfloat16: AST_BF16}
+_DTYPES = {torch.float32: AST_F32, torch.bfloat16: AST_BF16, torch.uint8: AST_U8}
 
 
 class Image(ctypes.Structure):
@@ -33,6 +35,26 @@ class GatherGeom(ctypes.Structure):
                 ("w_img_stride", ctypes.c_int64), ("stats", ctypes.c_void_p), ("pooled", ctypes.POINTER(Image))]
 
 
+class PackMap(ctypes.Structure):
+    _fields_ = [("off", ctypes.c_int64), ("stride", ctypes.c_int64 * 2), ("tap", ctypes.c_int32), ("dtype", ctypes.c_int32)]
+
+
+class ParamDesc(ctypes.Structure):
+    _fields_ = [("p_off", ctypes.c_int64), ("s_off", ctypes.c_int64), ("numel", ctypes.c_int64),
+                ("dim", ctypes.c_int32 * 4), ("g_off", ctypes.c_int64), ("g_stride", ctypes.c_int64 * 2),
+                ("g_tap", ctypes.c_int32), ("n_pack", ctypes.c_int32), ("pack", PackMap * 2)]
+
+
+class AdamState(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("lr", "beta1", "beta2", "eps", "weight_decay", "grad_scale", "step",
+                                              "bias_c1", "bias_c2")]
+
+
+class ReduceDesc(ctypes.Structure):
+    _fields_ = [("src_off", ctypes.c_int64), ("dst_off", ctypes.c_int64), ("row_stride", ctypes.c_int64),
+                ("rows", ctypes.c_int32), ("cols", ctypes.c_int32)]
+
+
 _lib = None
 _P = ctypes.POINTER
 _vp = ctypes.c_void_p
@@ -46,7 +68,6 @@ _SIGNATURES = {
                             ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int32, _vp],
     "ast_row_im2col": [_P(Image), _P(Image), _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                        ctypes.c_int32, ctypes.c_int32, _vp],
-    "ast_unfold_rows": [_P(Image), _P(Image), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_fold_rows": [_P(Image), _P(Image), _vp, ctypes.c_int32, ctypes.c_int32, _vp],
     "ast_instnorm_stats": [_P(Image), _vp, _vp, ctypes.c_float, _vp, _vp],
     "ast_instnorm_finalize": [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, _vp, _vp, _vp],
@@ -55,16 +76,24 @@ _SIGNATURES = {
                                _vp, _vp, _vp],
     "ast_instnorm_bwd_apply": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
                                _vp, _vp, _P(Image), _P(Image), _vp],
+    "ast_instnorm_bwd": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
+                         _vp, _vp, _vp, _P(Image), _P(Image), _vp],
     "ast_maxpool2_fwd": [_P(Image), _P(Image), _vp],
     "ast_maxpool2_bwd": [_P(Image), _P(Image), _P(Image), _P(Image), _P(Image), _vp],
     "ast_gram": [_P(Image), _vp, ctypes.c_float, ctypes.c_int32, _vp],
+    "ast_gram_mse": [_P(Image), _vp, ctypes.c_float, _vp, ctypes.c_int64, _vp, ctypes.c_float, _vp, ctypes.c_float, _vp,
+                     ctypes.c_int32, _vp],
+    "ast_adam_step": [_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp],
+    "ast_batch_reduce": [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp],
+    "ast_channel_sum": [_P(Image), _vp, _vp],
     "ast_mse": [_P(Image), _P(Image), _vp, ctypes.c_float, _P(Image), ctypes.c_float, _vp],
     "ast_copy_image": [_P(Image), _P(Image), _vp, ctypes.c_int32, _vp],
     "ast_accumulate": [_P(Image), _P(Image), _vp],
     "ast_mask_add": [_P(Image), _P(Image), _P(Image), _P(Image), _vp],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["ast_instnorm_workspace_bytes", "ast_last_error", "ast_abi_version",
-                                      "ast_launch_count", "ast_capabilities"])
+                                      "ast_launch_count", "ast_capabilities", "ast_adam_work_item", "ast_family_count",
+                                      "ast_family_name", "ast_family_stats", "ast_family_reset"])
 
 
 def load():
@@ -87,6 +116,13 @@ def load():
     lib.ast_abi_version.restype = ctypes.c_int
     lib.ast_launch_count.restype = ctypes.c_int64
     lib.ast_capabilities.restype = ctypes.c_int
+    lib.ast_adam_work_item.restype = ctypes.c_int32
+    lib.ast_family_count.restype = ctypes.c_int
+    lib.ast_family_name.argtypes = [ctypes.c_int]
+    lib.ast_family_name.restype = ctypes.c_char_p
+    lib.ast_family_stats.argtypes = [ctypes.c_int, _P(ctypes.c_int64), _P(ctypes.c_double), _P(ctypes.c_double)]
+    lib.ast_family_stats.restype = ctypes.c_int
+    lib.ast_family_reset.restype = None
     _lib = lib
     return lib
 
@@ -105,12 +141,21 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _check_device(t):
+    """The library launches on the CURRENT device / current stream (one process per GPU): a tensor that lives on another
+    GPU would be handed to a kernel running on the wrong device, so refuse it loudly."""
+    if not t.is_cuda:
+        raise RuntimeError("artist_style_transfer_b200 kernels need CUDA tensors (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}; "
+                           "call torch.cuda.set_device(...) (one process per GPU) or wrap the call in torch.cuda.device(...)")
+
+
 def image(t):
     """ast_image of a 4-D tensor given in logical (N, H, W, C) order with arbitrary strides."""
     if t is None:
         return None
-    if not t.is_cuda:
-        raise RuntimeError("artist_style_transfer_b200 kernels need CUDA tensors (no CPU fallback)")
+    _check_device(t)
     n, h, w, c = t.shape
     sn, sh, sw, sc = t.stride()
     return Image(t.data_ptr(), _DTYPES[t.dtype], n, h, w, c, sn, sh, sw, sc)
@@ -131,3 +176,25 @@ def has_tc_gram():
 
 def launch_count():
     return int(load().ast_launch_count())
+
+
+def family_stats():
+    """{family: (launches, algorithmic flops, algorithmic bytes)} of everything launched by this process so far."""
+    lib = load()
+    out = {}
+    for f in range(lib.ast_family_count()):
+        n, fl, by = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+        lib.ast_family_stats(f, ctypes.byref(n), ctypes.byref(fl), ctypes.byref(by))
+        out[lib.ast_family_name(f).decode()] = (n.value, fl.value, by.value)
+    return out
+
+
+def family_delta(before, after=None):
+    after = family_stats() if after is None else after
+    return {k: tuple(a - b for a, b in zip(after[k], before[k])) for k in after}
+
+
+def device_bytes(ctypes_obj, device):
+    """Upload a ctypes struct / array to a uint8 device tensor (descriptor tables of the table-driven kernels)."""
+    buf = bytes(ctypes_obj)
+    return torch.frombuffer(bytearray(buf), dtype=torch.uint8).to(device)

@@ -17,6 +17,28 @@ void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- per-kernel-family accounting (ast_family_stats): launches + ALGORITHMIC flops / bytes computed from the launch
+// geometry on the host.  bench.py divides these by the device time of the same family in the CUDA-graph replay; the
+// tests use the launch counts to assert which kernel a case really ran on.
+enum Family {
+  FAM_CONV_TC = 0, FAM_CONV_PX, FAM_CONV_WS, FAM_CONV_SIMT, FAM_WGRAD_TC, FAM_WGRAD_THIN, FAM_WGRAD_SIMT, FAM_GRAM_TC,
+  FAM_GRAM_SIMT, FAM_IN_APPLY, FAM_IN_BWD, FAM_IN_STATS, FAM_POOL, FAM_MSE, FAM_POINTWISE, FAM_OPTIM, FAM_COUNT
+};
+void count_work(int family, double flops, double bytes);
+inline double esize(const ast_image* im) { return im->dtype == AST_F32 ? 4.0 : (im->dtype == AST_U8 ? 1.0 : 2.0); }
+inline double img_bytes(const ast_image* im) { return im ? (double)im->n * im->h * im->w * im->c * esize(im) : 0.0; }
+inline double conv_flops(const ast_image* in, const ast_image* out, const ast_gather_geom* g) {
+  return 2.0 * in->n * g->mi * g->mj * g->ntaps * in->c * out->c;
+}
+// input pixels the launch covers (a phase of a strided op touches 1/so^2 of the output and all of its input window)
+inline double conv_bytes(const ast_image* in, const ast_image* out, const ast_gather_geom* g, const ast_image* add = nullptr,
+                         const ast_image* mask = nullptr) {
+  double pix_in = (double)g->mi * g->mj * g->si * g->si;
+  if (pix_in > (double)in->h * in->w) pix_in = (double)in->h * in->w;
+  const double pix_out = (double)g->mi * g->mj;
+  return in->n * (pix_in * in->c * esize(in) + pix_out * out->c * (esize(out) + (add ? esize(add) : 0) + (mask ? esize(mask) : 0)));
+}
+
 #define AST_CHECK_ARG(cond, ...)                    \
   do {                                              \
     if (!(cond)) {                                  \
@@ -35,33 +57,14 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     }                                                                       \
   } while (0)
 
-// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
-// Every kernel of the library is launched through launch_k().  With AST_PDL=1 the launch carries
-// cudaLaunchAttributeProgrammaticStreamSerialization: the grid may be scheduled while its predecessor in the stream is
-// still draining, and every kernel starts with pdl_sync() = { griddepcontrol.launch_dependents; griddepcontrol.wait; }:
-// it lets ITS successor be scheduled early and then blocks until the predecessor grid has completed and its memory is
-// visible.  No kernel touches global memory before pdl_sync(), so the semantics are those of plain stream order.
-// Both instructions are no-ops without the attribute.  Measured on the B=32 step (CUDA graph): 13.86 ms with PDL vs
-// 13.55 ms without when every kernel triggers early (successors take SM slots from multi-wave kernels), 13.65 ms when only
-// the single-wave persistent kernels trigger - so it is OFF by default.
-__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Only the single-wave persistent kernels let their successor be scheduled early (its CTAs then fill SMs as this grid's
-// CTAs retire); multi-wave kernels would lose SM slots to the waiting successor.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-inline bool pdl_enabled() {
-  static const int on = [] { const char* e = getenv("AST_PDL"); return e ? atoi(e) : 0; }();
-  return on != 0;
-}
+// Every kernel of the library is launched through launch_k() (one place for launch attributes).  Programmatic dependent
+// launch was measured slower on this path (early-scheduled successors take SM slots from multi-wave kernels:
+// 13.86 vs 13.55 ms per step, profiles/r01_summary.md) and is not used.
 template <typename... KP, typename... A>
 inline cudaError_t launch_k(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr.val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
 }
 
@@ -96,11 +99,16 @@ template <> struct DT<__nv_bfloat16> {
   __device__ static __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// AST_U8 (host-boundary images): loads widen exactly; stores follow numpy's `.clip(0, 255).astype('uint8')`
+// (inference.py:116, train_cnn.py:112): clamp, then truncate toward zero.
 __device__ __forceinline__ float ld_elem(const Img& im, long long off) {
-  return im.dtype == AST_F32 ? ((const float*)im.ptr)[off] : __bfloat162float(((const __nv_bfloat16*)im.ptr)[off]);
+  if (im.dtype == AST_F32) return ((const float*)im.ptr)[off];
+  if (im.dtype == AST_U8) return (float)((const unsigned char*)im.ptr)[off];
+  return __bfloat162float(((const __nv_bfloat16*)im.ptr)[off]);
 }
 __device__ __forceinline__ void st_elem(const Img& im, long long off, float v) {
   if (im.dtype == AST_F32) ((float*)im.ptr)[off] = v;
+  else if (im.dtype == AST_U8) ((unsigned char*)im.ptr)[off] = (unsigned char)__float2uint_rz(fminf(fmaxf(v, 0.f), 255.f));
   else ((__nv_bfloat16*)im.ptr)[off] = __float2bfloat16_rn(v);
 }
 __device__ __forceinline__ long long img_off(const Img& im, int n, int y, int x, int c) {

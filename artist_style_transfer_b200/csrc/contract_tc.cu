@@ -49,15 +49,28 @@ __device__ __forceinline__ unsigned long long make_mn_desc(unsigned saddr, unsig
   return d;
 }
 
+// Gram finishing step (north_star: "fuse the 1/(CHW) scale and the style-MSE reduction into the epilogue"): the LAST of the
+// split-K CTAs of one output block (atomic ticket) mirrors the block into the lower triangle, accumulates
+//   loss += loss_scale * sum_{i,j} (G_ij - S_ij)^2        (upper triangle, off-diagonal entries counted twice)
+// and writes D = d_scale * (G - S), the symmetric per-image 1x1 weights of the Gram backward (TF32-rounded).
+struct GramFin {
+  int enabled;
+  int* counters;                 // [n_img][m_blocks * n_blocks], zero on entry
+  const float* target;           // S, or null (then only the mirror is done)
+  long long target_img_stride;   // 0 = one target shared by the batch (train_cnn.py:187-190 expands one style Gram)
+  double* loss; float loss_scale;   // fp64 accumulator: hundreds of small fp32 addends into a ~1e4 total would be truncated
+  float* dmat; float d_scale;    // null = no gradient requested
+};
+
 template <int KIND>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c, const CtParams p,
-                   float* __restrict__ out, const int* __restrict__ tap_off) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
+                   float* __restrict__ out, const int* __restrict__ tap_off, const GramFin fin) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
   __shared__ unsigned tmem_slot;
+  __shared__ int s_last;
+  __shared__ float s_red[4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.y * p.tg;                                   // first tap of this CTA's tap group
@@ -198,6 +211,68 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
         }
       }
     }
+    if (fin.enabled) {
+      // ---- ticket: the last split-K CTA of this (image, block) sees every contribution (release/acquire through the
+      // fence + atomic; the block is then read with ld.global.cg, i.e. from L2 where the reductions landed)
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int prev = atomicAdd(fin.counters + (long long)img_fixed * AST_GRAM_COUNTERS_PER_IMAGE + blockIdx.z, 1);
+        s_last = prev == p.ksplit - 1;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        const int C = p.n_valid;
+        float* G = out + (long long)img_fixed * p.out_img_stride;
+        const float* S = fin.target ? fin.target + (long long)img_fixed * fin.target_img_stride : nullptr;
+        float* D = fin.dmat ? fin.dmat + (long long)img_fixed * p.out_img_stride : nullptr;
+        // 32 x 32 tiles of the block, one warp each; transposed copies go through a padded shared-memory tile (the
+        // pipeline stages are idle by now) so that both the (m, n) and the (n, m) stores are coalesced
+        float* tg = reinterpret_cast<float*>(smem) + (warp - 2) * (2 * 32 * 33);
+        float* td = tg + 32 * 33;
+        float part = 0.f;
+        const int tiles_n = p.bn / 32;
+        for (int tile = warp - 2; tile < 4 * tiles_n; tile += 4) {
+          const int tr = tile / tiles_n, tc = tile - tr * tiles_n;
+          const int mb0 = m0 + tr * 32, nb0 = n0 + tc * 32;
+          if (mb0 >= p.m_valid || nb0 >= C || nb0 + 31 < mb0) continue;     // tile outside the matrix / strictly below the diagonal
+          const int n = nb0 + lane;
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int mm = mb0 + r;
+            float gv = 0.f, dv = 0.f;
+            if (mm < p.m_valid && n < C && n >= mm) {
+              gv = __ldcg(G + (long long)mm * C + n);
+              if (S) {
+                dv = gv - __ldg(S + (long long)mm * C + n);
+                part = fmaf(n > mm ? 2.f : 1.f, dv * dv, part);
+                if (D) D[(long long)mm * C + n] = round_tf32(fin.d_scale * dv);
+              }
+            }
+            tg[r * 33 + lane] = gv;
+            td[r * 33 + lane] = dv;
+          }
+          __syncwarp();
+          // transposed: row n' = nb0 + r, column m' = mb0 + lane  (strictly lower entries only)
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int nn = nb0 + r, mm = mb0 + lane;
+            if (nn < C && mm < p.m_valid && nn > mm) {
+              G[(long long)nn * C + mm] = tg[lane * 33 + r];
+              if (D) D[(long long)nn * C + mm] = round_tf32(fin.d_scale * td[lane * 33 + r]);
+            }
+          }
+          __syncwarp();
+        }
+        if (S && fin.loss) {
+          part = warp_sum(part);
+          if (lane == 0) s_red[warp - 2] = part;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) atomicAdd(fin.loss, (double)fin.loss_scale * (double)(s_red[0] + s_red[1] + s_red[2] + s_red[3]));
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -210,8 +285,6 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
 
 // fills the strict lower triangle of each C x C matrix from the upper one
 __global__ void mirror_upper_kernel(float* __restrict__ g, int c, long long total) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % c);
     const int i = (int)((idx / c) % c);
@@ -226,11 +299,9 @@ static int encode_operand(EncodeTiledFn encode, CUtensorMap* tm, const ast_image
   cuuint64_t strides[3] = {(cuuint64_t)im->sw * esz, (cuuint64_t)im->sh * esz, (cuuint64_t)im->sn * esz};
   cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(tw * s), (cuuint32_t)(th * s), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
-  CUresult r = encode(tm, dt, 4, im->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      im->dtype == AST_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("contract_tc: cuTensorMapEncodeTiled failed: %d", (int)r); return (int)r; }
-  return 0;
+  return cached_tensor_map(encode, tm, dt, 4, im->ptr, dims, strides, box, estr,
+                           im->dtype == AST_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 static int check_operand(const char* who, const ast_image* im) {
@@ -265,8 +336,6 @@ constexpr int THIN_BOX = THIN_KP * 64;         // bytes per box
 __global__ void __launch_bounds__(CT_THREADS, 1)
 contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_c,
                      const CtThinParams p, float* __restrict__ out, const int* __restrict__ tap_off) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[CT_MAX_STAGES], empty_bar[CT_MAX_STAGES], tfull_bar;
   __shared__ unsigned tmem_slot;
@@ -377,19 +446,15 @@ static int encode_thin_operand(EncodeTiledFn encode, CUtensorMap* tm, const ast_
   cuuint64_t strides[3] = {(cuuint64_t)im->sw * 2, (cuuint64_t)im->sh * 2, (cuuint64_t)im->sn * 2};
   cuuint32_t box[4] = {32, (cuuint32_t)(tw * s), (cuuint32_t)(th * s), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, im->ptr, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("contract_thin: cuTensorMapEncodeTiled failed: %d", (int)r); return (int)r; }
-  return 0;
+  return cached_tensor_map(encode, tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, im->ptr, dims, strides, box, estr,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 // returns 1 when the thin kernel took the job, 0 when not applicable, < 0 / CUDA error codes otherwise
 static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols,
                          int c_s, const short* dy, const short* dx, int ntaps, int mi, int mj, float* out,
                          const int* tap_off, long long s_m, long long s_n, float scale, cudaStream_t stream) {
-  static const int enabled = [] { const char* e = getenv("AST_WGRAD_THIN"); return e ? atoi(e) : 1; }();
-  if (!enabled || rows->dtype != AST_BF16 || rows->c > 32 || cols->c > 32 || ntaps < 2 || ntaps > 60) return 0;
+  if (rows->dtype != AST_BF16 || rows->c > 32 || cols->c > 32 || ntaps < 2 || ntaps > 60) return 0;
   CtThinParams p;
   memset(&p, 0, sizeof(p));
   p.mi = mi; p.mj = mj; p.n_img = rows->n; p.ntaps = ntaps; p.ngrp = (ntaps + 3) / 4;
@@ -414,10 +479,11 @@ static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, i
   if (int e = encode_thin_operand(encode, &tm_r, rows, p.tw, p.th, r_s)) return e;
   if (int e = encode_thin_operand(encode, &tm_c, cols, p.tw, p.th, c_s)) return e;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(contract_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = set_max_smem(contract_thin_kernel, smem);
   if (e != cudaSuccess) { set_error("contract_thin: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   launch_k(contract_thin_kernel, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off);
   count_launch();
+  count_work(FAM_WGRAD_THIN, 2.0 * rows->n * mi * mj * ntaps * rows->c * cols->c, img_bytes(rows) + img_bytes(cols));
   AST_CUDA_LAUNCH_CHECK();
   return 1;
 }
@@ -425,7 +491,8 @@ static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, i
 // rows = operand that provides the M (<=128 per block) dimension, cols = the N dimension.
 int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols, int c_s, const short* dy,
                 const short* dx, int ntaps, int mi, int mj, float* out, const int* tap_off, long long s_m,
-                long long s_n, long long out_img_stride, float scale, int upper_only, cudaStream_t stream) {
+                long long s_n, long long out_img_stride, float scale, int upper_only, cudaStream_t stream,
+                const GramFin* finp) {
   AST_CHECK_ARG(rows->dtype == cols->dtype, "contract_tc: operands must share a dtype");
   AST_CHECK_ARG(rows->n == cols->n, "contract_tc: batch mismatch");
   if (int e = check_operand("contract_tc(rows)", rows)) return e;
@@ -435,7 +502,7 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "contract_tc: cuTensorMapEncodeTiled entry point not available");
   const int esz = rows->dtype == AST_F32 ? 4 : 2;
-  if (!upper_only && out_img_stride == 0) {
+  if (!upper_only && out_img_stride == 0 && !finp) {
     const int tr = contract_thin(encode, rows, r_s, r_oy, r_ox, cols, c_s, dy, dx, ntaps, mi, mj, out, tap_off, s_m, s_n,
                                  scale, stream);
     if (tr != 0) return tr == 1 ? 0 : tr;
@@ -463,10 +530,7 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   p.box_bytes = p.kp * 128;
   // tap groups: one CTA accumulates `tg` taps (tg*bn TMEM columns) from ONE load of the rows operand per stage
   {
-    const char* env = getenv("AST_WGRAD_TG");
     int tg_max = 512 / p.bn;
-    if (env) tg_max = atoi(env) < tg_max ? atoi(env) : tg_max;
-    if (tg_max < 1) tg_max = 1;
     if (tg_max > ntaps) tg_max = ntaps;
     while (tg_max > 1 && 2 * (p.m_boxes + tg_max * p.n_boxes) * p.box_bytes > 200 * 1024) --tg_max;
     p.ngroups = (ntaps + tg_max - 1) / tg_max;
@@ -498,32 +562,58 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   // + m_boxes: a shared A operand (Gram) may read up to m_boxes boxes past the column boxes of the last stage
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (p.same ? (size_t)p.m_boxes * p.box_bytes : 0);
   dim3 grid((unsigned)(p.ksplit * (p.per_img ? p.n_img : 1)), p.ngroups, p.m_blocks * p.n_blocks);
+  GramFin fin;
+  memset(&fin, 0, sizeof(fin));
+  if (finp) {
+    AST_CHECK_ARG(p.per_img && upper_only && s_n == 1 && s_m == cols->c && p.ngroups == 1,
+                  "contract_tc: the Gram finishing step needs a per-image upper-triangle launch");
+    AST_CHECK_ARG(p.stages * p.stage_bytes >= 4 * 2 * 32 * 33 * (int)sizeof(float), "contract_tc: no room for the mirror tiles");
+    AST_CHECK_ARG(p.m_blocks * p.n_blocks <= AST_GRAM_COUNTERS_PER_IMAGE, "contract_tc: C=%d needs more ticket counters", cols->c);
+    fin = *finp;
+    fin.enabled = 1;
+  }
   cudaError_t e;
   if (rows->dtype == AST_BF16) {
-    e = cudaFuncSetAttribute(contract_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_k(contract_tc_kernel<0>, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off);
+    e = set_max_smem(contract_tc_kernel<0>, smem);
+    if (e == cudaSuccess) launch_k(contract_tc_kernel<0>, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off, fin);
   } else {
-    e = cudaFuncSetAttribute(contract_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_k(contract_tc_kernel<1>, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off);
+    e = set_max_smem(contract_tc_kernel<1>, smem);
+    if (e == cudaSuccess) launch_k(contract_tc_kernel<1>, grid, CT_THREADS, smem, stream, tm_r, tm_c, p, out, tap_off, fin);
   }
   if (e != cudaSuccess) { set_error("contract_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  if (upper_only)   // Gram: upper-triangle flops C(C+1)HW per image, one read of F + one write of G
+    count_work(FAM_GRAM_TC, (double)rows->n * rows->c * (rows->c + 1.0) * mi * mj, img_bytes(rows) + 4.0 * rows->n * rows->c * rows->c);
+  else
+    count_work(FAM_WGRAD_TC, 2.0 * rows->n * mi * mj * ntaps * rows->c * cols->c, img_bytes(rows) + img_bytes(cols));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
 
-int gram_tc(const ast_image* x, float* g, float scale, cudaStream_t s) {
-  cudaMemsetAsync(g, 0, sizeof(float) * (size_t)x->n * x->c * x->c, s);
-  int rc = contract_tc(x, 1, 0, 0, x, 1, nullptr, nullptr, 1, x->h, x->w, g, nullptr, x->c, 1, (long long)x->c * x->c,
-                       scale, 1, s);
-  if (rc) return rc;
-  const long long total = (long long)x->n * x->c * x->c;
-  long long blocks = (total + 255) / 256;
-  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  launch_k(mirror_upper_kernel, (int)blocks, 256, 0, s, g, x->c, total);
-  count_launch();
-  AST_CUDA_LAUNCH_CHECK();
-  return 0;
+// Gram (+ optional fused style-MSE / gradient seed).  With `counters` (zeroed by the caller, AST_GRAM_COUNTERS_PER_IMAGE
+// ints per image, like g itself) the finishing CTA of every block mirrors / reduces; without, g is zeroed here and a
+// separate kernel mirrors the upper triangle.
+int gram_tc(const ast_image* x, float* g, float scale, const float* target, long long target_img_stride, double* loss,
+            float loss_scale, float* dmat, float d_scale, int* counters, cudaStream_t s) {
+  if (!counters) {
+    cudaMemsetAsync(g, 0, sizeof(float) * (size_t)x->n * x->c * x->c, s);
+    int rc = contract_tc(x, 1, 0, 0, x, 1, nullptr, nullptr, 1, x->h, x->w, g, nullptr, x->c, 1, (long long)x->c * x->c,
+                         scale, 1, s, nullptr);
+    if (rc) return rc;
+    const long long total = (long long)x->n * x->c * x->c;
+    long long blocks = (total + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    launch_k(mirror_upper_kernel, (int)blocks, 256, 0, s, g, x->c, total);
+    count_launch();
+    AST_CUDA_LAUNCH_CHECK();
+    return 0;
+  }
+  GramFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.counters = counters; fin.target = target; fin.target_img_stride = target_img_stride;
+  fin.loss = loss; fin.loss_scale = loss_scale; fin.dmat = dmat; fin.d_scale = d_scale;
+  return contract_tc(x, 1, 0, 0, x, 1, nullptr, nullptr, 1, x->h, x->w, g, nullptr, x->c, 1, (long long)x->c * x->c,
+                     scale, 1, s, &fin);
 }
 
 }  // namespace ast

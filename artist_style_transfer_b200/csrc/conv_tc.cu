@@ -29,7 +29,6 @@ struct TcParams {
   int mi, mj, tw, th, tiles_i, tiles_j, n_img, n_tiles_n, bn;
   int ntaps, kchunks, kc;
   int si, so, oy0, ox0;
-  int cg, tiles_jp;                    // cta_group (1 or 2) and, for 2, the number of spatial tile PAIRS per image
   int cout, cout_valid, thin, flags;   // cout = weight rows per tap (multiple of 32); thin: cout_valid < cout or strided out
   int w_rows_per_img;
   int stages, a_bytes, stage_bytes, rowb;
@@ -40,73 +39,19 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------ kernel
-// ---- cta_group::2 helpers (PTX forms as in CUTLASS cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h)
-constexpr unsigned PEER_BIT_MASK = 0xFEFFFFFFu;       // clears the CTA-pair rank bit of a shared::cluster address -> leader CTA
-__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, unsigned long long* leader_bar, int c0,
-                                                int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, unsigned long long* leader_bar, int c0,
-                                                int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_2sm(unsigned long long* bar) {   // arrives on `bar` in BOTH CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
-}
+// (A cta_group::2 form - CTA pairs, M = 256, half of the weight tile per CTA - was measured to give no gain on this path
+//  and removed: scratch/dead_variants/conv_tc_r01.cu.txt, profiles/r01_summary.md finding 4.)
 template <int KIND>
-__device__ __forceinline__ void tc_mma_2sm(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
-                                           unsigned idesc, unsigned accumulate) {
-  if (KIND == 0)
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  else
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(unsigned long long* bar) {   // arrive on the LEADER CTA's copy of `bar`
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
-// CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2) works on two neighbouring 128-pixel tiles with
-// ONE tcgen05.mma.cta_group::2 (M = 256): each CTA loads its own A tile and HALF of the weight tile, so the shared-
-// memory operand traffic per SM drops from A+B to A+B/2 - the limiter of the N <= 128 layers (profiles/r01_summary.md).
-template <int KIND, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const TcParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
-               float* __restrict__ stats) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
+               double* __restrict__ stats) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ unsigned tmem_slot;
 
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#ifdef TC_PROFILE
-  long long prof_wait = 0, prof_wait2 = 0, prof_t0 = 0, prof_a = 0, prof_b = 0;
-  const long long prof_start = clock64();
-#define TC_PROF_T0() prof_t0 = clock64()
-#define TC_PROF_ADD(v) v += clock64() - prof_t0
-#else
-#define TC_PROF_T0()
-#define TC_PROF_ADD(v)
-#endif
   const int ksteps = p.ntaps * p.kchunks;
   const unsigned tmem_cols = (2 * p.bn <= 32) ? 32 : (2 * p.bn <= 64) ? 64 : (2 * p.bn <= 128) ? 128 : (2 * p.bn <= 256) ? 256 : 512;
 
@@ -114,23 +59,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256 * CG); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  const unsigned rank = CG == 2 ? cluster_ctarank() : 0u;
-  if (CG == 2) cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / TMA signal
   if (warp == 1) {
-    if (CG == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = tmem_slot;
 
@@ -143,90 +81,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     int s = 0, turn = 0; unsigned ph = 0;
     const int nprod = p.stages < TC_PRODUCERS ? p.stages : TC_PRODUCERS;
     if (lane < nprod)
-    for (long long tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
       const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
-      int tj, ti, img;
-      if (CG == 2) {          // the pair takes two consecutive spatial tiles of one image (row-major over ti, tj)
-        const int sp = 2 * (int)(r % p.tiles_jp) + (int)rank;
-        img = (int)(r / p.tiles_jp);
-        ti = sp / p.tiles_j; tj = sp - ti * p.tiles_j;      // sp past the last tile -> ti == tiles_i: all-OOB loads, no stores
-      } else {
-        tj = (int)(r % p.tiles_j); r /= p.tiles_j;
-        ti = (int)(r % p.tiles_i);
-        img = (int)(r / p.tiles_i);
-      }
+      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
+      const int ti = (int)(r % p.tiles_i);
+      const int img = (int)(r / p.tiles_i);
       const int x0 = p.si * tj * p.tw, y0 = p.si * ti * p.th;
-      const int wrow0 = img * p.w_rows_per_img + nt * p.bn + (CG == 2 ? (int)rank * (p.bn / 2) : 0);
+      const int wrow0 = img * p.w_rows_per_img + nt * p.bn;
       for (int t = 0; t < p.ntaps; ++t) {
         const int cx = x0 + p.dx[t], cy = y0 + p.dy[t];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           if (turn == lane) {
-            TC_PROF_T0();
             mbar_wait(&empty_bar[s], ph ^ 1);
-            TC_PROF_ADD(prof_wait);
             unsigned char* sa = smem + (size_t)s * p.stage_bytes;
-            if (CG == 1) {
-              TC_PROF_T0();
-              mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
-              TC_PROF_ADD(prof_wait2);
-              TC_PROF_T0();
-              tma_load_4d(sa, &tm_in, &full_bar[s], kc * p.kc, cx, cy, img);
-              TC_PROF_ADD(prof_a);
-              TC_PROF_T0();
-              tma_load_2d(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
-              TC_PROF_ADD(prof_b);
-            } else {     // both CTAs' bytes land on the LEADER's full barrier, which expects twice a stage
-              if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)p.stage_bytes);
-              tma_load_4d_2sm(sa, &tm_in, &full_bar[s], kc * p.kc, cx, cy, img);
-              tma_load_2d_2sm(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
-            }
+            mbar_expect_tx(&full_bar[s], (unsigned)p.stage_bytes);
+            tma_load_4d(sa, &tm_in, &full_bar[s], kc * p.kc, cx, cy, img);
+            tma_load_2d(sa + p.a_bytes, &tm_w, &full_bar[s], kc * p.kc, wrow0 + t * p.cout);
           }
           if (++turn == nprod) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && rank == 0) {
-    // ============================ MMA issuer (leader CTA only when CG == 2) ============================
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
     int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
     const int kmma = p.rowb / 32;   // UMMA_K spans 32 bytes for both bf16 (16 elems) and tf32 (8 elems)
     const unsigned desc_hi = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
-    for (long long tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
-      TC_PROF_T0();
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
-      TC_PROF_ADD(prof_wait2);
       tc_fence_after();
       const unsigned d_tmem = tmem_base + (unsigned)(as * p.bn);
       for (int ks = 0; ks < ksteps; ++ks) {
-        TC_PROF_T0();
         mbar_wait(&full_bar[s], ph);
-        TC_PROF_ADD(prof_wait);
         tc_fence_after();
         if (lane == 0) {
           // descriptor hi word is constant; lo word = (addr >> 4) | LBO, advanced by 32 B (= 2) per UMMA_K step
           const unsigned a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
           const unsigned a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
           const unsigned b_lo = (((a_addr + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          if (CG == 1) {
-            tc_mma<KIND>(d_tmem, pack_desc64(a_lo, desc_hi), pack_desc64(b_lo, desc_hi), p.idesc, ks > 0 ? 1u : 0u);
-            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 2, desc_hi), pack_desc64(b_lo + 2, desc_hi), p.idesc, 1u);
-            if (kmma == 4) {
-              tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 4, desc_hi), pack_desc64(b_lo + 4, desc_hi), p.idesc, 1u);
-              tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 6, desc_hi), pack_desc64(b_lo + 6, desc_hi), p.idesc, 1u);
-            }
-            tc_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
-            if (ks == ksteps - 1) tc_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
-          } else {
-            tc_mma_2sm<KIND>(d_tmem, pack_desc64(a_lo, desc_hi), pack_desc64(b_lo, desc_hi), p.idesc, ks > 0 ? 1u : 0u);
-            tc_mma_2sm<KIND>(d_tmem, pack_desc64(a_lo + 2, desc_hi), pack_desc64(b_lo + 2, desc_hi), p.idesc, 1u);
-            if (kmma == 4) {
-              tc_mma_2sm<KIND>(d_tmem, pack_desc64(a_lo + 4, desc_hi), pack_desc64(b_lo + 4, desc_hi), p.idesc, 1u);
-              tc_mma_2sm<KIND>(d_tmem, pack_desc64(a_lo + 6, desc_hi), pack_desc64(b_lo + 6, desc_hi), p.idesc, 1u);
-            }
-            tc_commit_2sm(&empty_bar[s]);             // frees this stage in BOTH CTAs
-            if (ks == ksteps - 1) tc_commit_2sm(&tfull_bar[as]);
+          tc_mma<KIND>(d_tmem, pack_desc64(a_lo, desc_hi), pack_desc64(b_lo, desc_hi), p.idesc, ks > 0 ? 1u : 0u);
+          tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 2, desc_hi), pack_desc64(b_lo + 2, desc_hi), p.idesc, 1u);
+          if (kmma == 4) {
+            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 4, desc_hi), pack_desc64(b_lo + 4, desc_hi), p.idesc, 1u);
+            tc_mma<KIND>(d_tmem, pack_desc64(a_lo + 6, desc_hi), pack_desc64(b_lo + 6, desc_hi), p.idesc, 1u);
           }
+          tc_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
+          if (ks == ksteps - 1) tc_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -241,25 +143,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const int row = q * 32 + lane;
     const int ty = row / p.tw, tx = row % p.tw;
     int as = 0; unsigned aph = 0;
-    for (long long tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
       const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
-      int tj, ti, img;
-      if (CG == 2) {          // the pair takes two consecutive spatial tiles of one image (row-major over ti, tj)
-        const int sp = 2 * (int)(r % p.tiles_jp) + (int)rank;
-        img = (int)(r / p.tiles_jp);
-        ti = sp / p.tiles_j; tj = sp - ti * p.tiles_j;      // sp past the last tile -> ti == tiles_i: all-OOB loads, no stores
-      } else {
-        tj = (int)(r % p.tiles_j); r /= p.tiles_j;
-        ti = (int)(r % p.tiles_i);
-        img = (int)(r / p.tiles_i);
-      }
+      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
+      const int ti = (int)(r % p.tiles_i);
+      const int img = (int)(r / p.tiles_i);
       const int i = ti * p.th + ty, j = tj * p.tw + tx;
       const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
       const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
-      TC_PROF_T0();
       mbar_wait(&tfull_bar[as], aph);
-      TC_PROF_ADD(prof_wait);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
       EpiRows rows;
@@ -279,22 +172,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
       }
       tc_fence_before();
-      if (CG == 1) mbar_arrive(&tempty_bar[as]); else mbar_arrive_leader(&tempty_bar[as]);
+      mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
 
-#ifdef TC_PROFILE
-  if (blockIdx.x == 3 && (threadIdx.x & 31) == 0 && warp <= 2)
-    printf("conv_tc prof: warp %d total %lld clk, wait %lld, wait2 %lld, tmaA %lld, tmaB %lld (stages/CTA ~%lld, bn %d kchunks %d taps %d)\n", warp,
-           clock64() - prof_start, prof_wait, prof_wait2, prof_a, prof_b, (p.total_tiles / gridDim.x) * p.ntaps * p.kchunks, p.bn, p.kchunks, p.ntaps);
-#endif
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -304,7 +191,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
                    cudaStream_t stream);   // conv_ws.cu: 1 = launched, 0 = not applicable
 int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
-                   bool resident_only, cudaStream_t stream);   // conv_px.cu: 1 = launched, 0 = not applicable
+                   cudaStream_t stream);   // conv_px.cu: 1 = launched, 0 = not applicable
 int tc_capabilities() { return 3; }   // 1 = conv_tc.cu, 2 = contract_tc.cu (both are always built together)
 
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
@@ -329,15 +216,11 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
-  // AST_CONV_PX: 0 = off, 1 (default) = pixels-as-N kernel for cout 64/128: its resident-weight form ahead of the
-  // weight-stationary kernel, its streaming form after it; 2 = always ahead of the weight-stationary kernel
-  static const int px_mode = [] { const char* e = getenv("AST_CONV_PX"); return e ? atoi(e) : 1; }();
-  if (px_mode >= 1)     // resident-weight form first (mode 2: any form)
-    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, px_mode == 1, stream)) return pr == 1 ? 0 : pr;
+  // dispatch: weight-stationary kernel (filter resident in smem, stride 1), then the pixels-as-N kernel (cout 64/128,
+  // long K loops), then the generic kernel below
   if (int wr = conv_gather_ws(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return wr == 1 ? 0 : wr;
   AST_CHECK_ARG(!g->pooled, "conv_tc: a pooled output needs the weight-stationary kernel (stride 1, filter resident in smem)");
-  if (px_mode == 1)
-    if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, false, stream)) return pr == 1 ? 0 : pr;
+  if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -358,23 +241,15 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
     AST_CHECK_ARG(g->w_img_stride == (int64_t)g->ntaps * cpad * in->c, "conv_tc: per-image weights must be densely packed");
     p.w_rows_per_img = g->ntaps * cpad;
   }
-  // AST_CONV_CG2=1: CTA pairs (tcgen05 cta_group::2, M = 256) - each CTA stages its own 128 pixels and half of the filter
-  // rows.  Off by default; see profiles/r01_summary.md for the A/B.
-  static const int cg2_env = [] { const char* e = getenv("AST_CONV_CG2"); return e ? atoi(e) : 0; }();
-  p.cg = (cg2_env && p.bn >= 64 && p.tiles_i * p.tiles_j >= 2) ? 2 : 1;
-  p.tiles_jp = (p.tiles_i * p.tiles_j + 1) / 2;       // spatial tile PAIRS per image
   p.a_bytes = 128 * p.rowb;
-  p.stage_bytes = p.a_bytes + (p.bn / p.cg) * p.rowb;
+  p.stage_bytes = p.a_bytes + p.bn * p.rowb;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  static const int dbg_stages = [] { const char* e = getenv("AST_TC_STAGES"); return e ? atoi(e) : 0; }();   // experiments only
-  static const int dbg_grid = [] { const char* e = getenv("AST_TC_GRID"); return e ? atoi(e) : 0; }();
-  if (dbg_stages > 1 && dbg_stages < p.stages) p.stages = dbg_stages;
   p.layout_type = p.rowb == 128 ? 2u : 4u;       // SWIZZLE_128B / SWIZZLE_64B
   p.sbo = 8u * p.rowb;
   const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;   // TF32 / BF16
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | (((128u * p.cg) >> 4) << 24);
-  p.total_tiles = (long long)p.n_img * (p.cg == 2 ? p.tiles_jp : p.tiles_i * p.tiles_j) * p.n_tiles_n;   // tile PAIRS when cg == 2
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j * p.n_tiles_n;
 
   // ---- tensor maps
   alignas(64) CUtensorMap tm_in, tm_w;
@@ -385,57 +260,30 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
     cuuint64_t strides[3] = {(cuuint64_t)in->sw * esz, (cuuint64_t)in->sh * esz, (cuuint64_t)in->sn * esz};
     cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.tw * p.si), (cuuint32_t)(p.th * p.si), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)p.si, (cuuint32_t)p.si, 1};
-    CUresult r = encode(&tm_in, dt, 4, in->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return (int)r; }
+    if (int r = cached_tensor_map(encode, &tm_in, dt, 4, in->ptr, dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
   }
   {
     const long long rows = (long long)g->ntaps * cpad * (g->w_img_stride ? in->n : 1);
     cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
-    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)(p.bn / p.cg)};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
+    if (int r = cached_tensor_map(encode, &tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 8192;   // + per-warp store-transpose stage
-  int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-  if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
+  const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   cudaError_t e;
-  if (p.cg == 2) {
-    const int pairs = (int)(p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
-    Img outi = to_img(out);
-    float* stats = g->stats;
-    if (in->dtype == AST_BF16) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 2>, tm_in, tm_w, p, bias, addi, maski, outi, stats);
-    } else {
-      e = cudaFuncSetAttribute(conv_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 2>, tm_in, tm_w, p, bias, addi, maski, outi, stats);
-    }
-    if (e != cudaSuccess) { set_error("conv_tc: cta_group::2 launch failed: %s", cudaGetErrorString(e)); return (int)e; }
-    count_launch();
-    AST_CUDA_LAUNCH_CHECK();
-    return 0;
-  }
   if (in->dtype == AST_BF16) {
-    e = cudaFuncSetAttribute(conv_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_k(conv_tc_kernel<0, 1>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
+    e = set_max_smem(conv_tc_kernel<0>, smem);
+    if (e == cudaSuccess) launch_k(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   } else {
-    e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_k(conv_tc_kernel<1, 1>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
+    e = set_max_smem(conv_tc_kernel<1>, smem);
+    if (e == cudaSuccess) launch_k(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   }
   if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  count_work(FAM_CONV_TC, conv_flops(in, out, g), conv_bytes(in, out, g, add, mask));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -14,7 +14,6 @@ namespace ast {
 
 constexpr int WS_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
 constexpr int WS_MAX_PBUF = 4;
-constexpr int WS_MAX_WBUF = 8;
 constexpr int WS_TH = 16, WS_TW = 8;
 
 struct WsParams {
@@ -24,25 +23,11 @@ struct WsParams {
   int so, oy0, ox0;
   int dy_min, dx_min, ph, pw;
   int patch_bytes, patch_tx, n_pbuf, w_tile_bytes, w_total_bytes;
-  int w_resident, n_wbuf, n_tiles_n;   // weights resident in smem, or streamed through an n_wbuf-deep ring
-  int th;                              // tile rows: WS_TH, or 32 for the pixels-as-N kernel (conv_wsx_kernel)
-  unsigned idesc, layout_type, sbo, base_mode;
+  unsigned idesc, layout_type, sbo;
   long long total_tiles;
   short tdy[AST_MAX_TAPS];
   short tdx[AST_MAX_TAPS];
 };
-
-__device__ __forceinline__ unsigned long long make_ws_desc(unsigned saddr, unsigned sbo_bytes, unsigned layout_type,
-                                                           unsigned base_mode) {
-  unsigned long long d = 0;
-  d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
-  d |= (unsigned long long)1 << 16;
-  d |= (unsigned long long)(sbo_bytes >> 4) << 32;
-  d |= (unsigned long long)1 << 46;
-  if (base_mode) d |= (unsigned long long)((saddr >> 7) & 7u) << 49;   // swizzle phase of an unaligned start
-  d |= (unsigned long long)layout_type << 61;
-  return d;
-}
 
 __device__ __forceinline__ unsigned long long pack_desc(unsigned lo, unsigned hi) {
   unsigned long long d;
@@ -56,12 +41,9 @@ template <int KIND, int MINB>
 __global__ void __launch_bounds__(WS_THREADS, MINB)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
-               float* __restrict__ stats, const Img pooled) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
+               double* __restrict__ stats, const Img pooled) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
-  __shared__ __align__(8) unsigned long long wfull[WS_MAX_WBUF], wempty[WS_MAX_WBUF];
   __shared__ unsigned tmem_slot;
   __shared__ unsigned s_tapoff[AST_MAX_TAPS];    // per-tap A start offset inside the patch, in 16-byte units
 
@@ -76,7 +58,6 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     for (int s = 0; s < p.n_pbuf; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
     mbar_init(&wbar, 1);
-    for (int s = 0; s < p.n_wbuf; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -95,17 +76,16 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0 && p.w_resident) {       // the whole filter, once
+    if (lane == 0) {       // the whole filter, once
       mbar_expect_tx(&wbar, (unsigned)p.w_total_bytes);
       for (int t = 0; t < p.ntaps; ++t)
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d(smem_w + (size_t)(t * p.kchunks + kc) * p.w_tile_bytes, &tm_w, &wbar, kc * p.kc, t * p.cout);
     }
     __syncwarp();
-    int s = 0; unsigned ph = 0; int ws = 0; unsigned wph = 0;
+    int s = 0; unsigned ph = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
-      const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
       const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
@@ -118,24 +98,13 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
         __syncwarp();
         if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
-        if (!p.w_resident) {           // stream this chunk's weights tap by tap, in the order the MMA warp consumes them
-          for (int t = 0; t < p.ntaps; ++t) {
-            mbar_wait(&wempty[ws], wph ^ 1);
-            if (lane == 0) {
-              mbar_expect_tx(&wfull[ws], (unsigned)p.w_tile_bytes);
-              tma_load_2d(smem_w + (size_t)ws * p.w_tile_bytes, &tm_w, &wfull[ws], kc * p.kc, t * p.cout + nt * p.bn);
-            }
-            __syncwarp();
-            if (++ws == p.n_wbuf) { ws = 0; wph ^= 1; }
-          }
-        }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0; int ws = 0; unsigned wph = 0;
+    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
     const int kmma = p.rowb / 32;
-    if (p.w_resident) mbar_wait(&wbar, 0);
+    mbar_wait(&wbar, 0);
     tc_fence_after();
     const unsigned w_addr0 = smem_u32(smem_w);
     const unsigned hi_a = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);
@@ -153,49 +122,20 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
           const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
           unsigned acc = kc > 0 ? 1u : 0u;
-          if (p.w_resident) {
 #pragma unroll 1
-            for (int t = 0; t < p.ntaps; ++t) {
-              const unsigned a_lo = p_lo + s_tapoff[t];
-              const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
-              if (kmma == 4) {
-                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
-                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
-              }
-              acc = 1u;
-            }
-            tc_commit(&pempty[s]);
-            if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
-          }
-        }
-        if (!p.w_resident) {
-          // streamed weights: one ring slot per tap; the whole warp waits, lane 0 issues
-          const unsigned p_lo = ((smem_u32(smem_p + (size_t)s * p.patch_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
-          const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
           for (int t = 0; t < p.ntaps; ++t) {
-            mbar_wait(&wfull[ws], wph);
-            tc_fence_after();
-            if (lane == 0) {
-              const unsigned a_lo = p_lo + s_tapoff[t];
-              const unsigned b_lo = w_lo + (unsigned)ws * w16;
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, (kc > 0 || t > 0) ? 1u : 0u);
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
-              if (kmma == 4) {
-                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
-                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
-              }
-              tc_commit(&wempty[ws]);
-              if (t == p.ntaps - 1) {
-                tc_commit(&pempty[s]);
-                if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
-              }
+            const unsigned a_lo = p_lo + s_tapoff[t];
+            const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
+            tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
+            tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
+            if (kmma == 4) {
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
             }
-            __syncwarp();
-            if (++ws == p.n_wbuf) { ws = 0; wph ^= 1; }
+            acc = 1u;
           }
+          tc_commit(&pempty[s]);
+          if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
         }
         __syncwarp();
         if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
@@ -212,7 +152,6 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     int as = 0; unsigned aph = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
-      const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
       const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
@@ -221,7 +160,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
       float pm[32];                                   // mask of this warp's first chunk, loaded while the MMAs still run
       const bool use_pm = MINB == 1 && mask.ptr && !p.thin && cpar * 32 < p.bn;   // (the 2-CTA build has no registers to spare)
-      if (use_pm) tc_epi_prefetch_mask(mask, img, oy, ox, nt * p.bn + cpar * 32, valid, pm);
+      if (use_pm) tc_epi_prefetch_mask(mask, img, oy, ox, cpar * 32, valid, pm);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
@@ -231,7 +170,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
         float v[32];
         tc_ld32(taddr0 + c0, v);
-        const int co = nt * p.bn + c0;
+        const int co = c0;
         if (p.thin) {
           if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
@@ -268,183 +207,14 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Pixels-as-N form of the weight-stationary kernel (resident weights, cout 32/64/128, full NHWC output): like conv_px.cu
-// the operands trade places - A = the resident weight tile of (tap, cin-chunk) (M = 128 rows: rows >= cout belong to the
-// next tile and only feed ignored accumulator lanes), B = a 32 x 8 = 256-pixel tile of the halo patch through the
-// shifted descriptor - so every MMA is N = 256 (128 cycles for 256 pixels instead of ~104 for 128).  A TMEM lane quarter
-// holds 32 output channels and only warps with warp % 4 == quarter may read it, so with cout = 32/64 just 1/2 quarters
-// carry data: SIXTEEN epilogue warps (four per quarter, 64 pixels each) keep the epilogue off the critical path.
-constexpr int WSX_EPI_WARPS = 16;
-constexpr int WSX_THREADS = (2 + WSX_EPI_WARPS) * 32;
-
-template <int KIND>
-__global__ void __launch_bounds__(WSX_THREADS, 1)
-conv_wsx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
-                const float* __restrict__ bias, const Img32 add, const Img32 mask, const Img32 out,
-                float* __restrict__ stats) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
-  __shared__ unsigned tmem_slot;
-  __shared__ unsigned s_tapoff[AST_MAX_TAPS];
-
-  unsigned char* smem_w = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* smem_p = smem_w + ((p.w_total_bytes + 1023) & ~1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
-    for (int s = 0; s < p.n_pbuf; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], WSX_EPI_WARPS * 32); }
-    mbar_init(&wbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (threadIdx.x >= 64 && threadIdx.x - 64 < p.ntaps) {
-    const int t = threadIdx.x - 64;
-    s_tapoff[t] = (unsigned)((p.tdy[t] * p.pw + p.tdx[t]) * p.rowb) >> 4;
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const unsigned tmem_base = tmem_slot;
-
-  if (warp == 0) {
-    // ============================ TMA producer ============================
-    if (lane == 0) {
-      mbar_expect_tx(&wbar, (unsigned)p.w_total_bytes);
-      for (int t = 0; t < p.ntaps; ++t)
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_2d(smem_w + (size_t)(t * p.kchunks + kc) * p.w_tile_bytes, &tm_w, &wbar, kc * p.kc, t * p.cout);
-      int s = 0; unsigned ph = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        long long r = tile;
-        const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
-        const int ti = (int)(r % p.tiles_i);
-        const int img = (int)(r / p.tiles_i);
-        const int x0 = tj * WS_TW + p.dx_min, y0 = ti * p.th + p.dy_min;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&pempty[s], ph ^ 1);
-          mbar_expect_tx(&pfull[s], (unsigned)p.patch_tx);
-          tma_load_4d(smem_p + (size_t)s * p.patch_bytes, &tm_in, &pfull[s], kc * p.kc, x0, y0, img);
-          if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    int s = 0; unsigned ph = 0; int as = 0; unsigned aph = 0;
-    const int kmma = p.rowb / 32;
-    mbar_wait(&wbar, 0);
-    tc_fence_after();
-    const unsigned w_addr0 = smem_u32(smem_w);
-    const unsigned hi_p = (p.sbo >> 4) | (1u << 14) | (p.layout_type << 29);            // patch: 8-pixel tile rows, SBO = patch row pitch
-    const unsigned hi_w = ((8u * p.rowb) >> 4) | (1u << 14) | (p.layout_type << 29);      // weights: dense rows
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[as], aph ^ 1);
-      tc_fence_after();
-      const unsigned d_tmem = tmem_base + (unsigned)(as * 256);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait(&pfull[s], ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const unsigned p_lo = ((smem_u32(smem_p + (size_t)s * p.patch_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
-          const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
-          unsigned acc = kc > 0 ? 1u : 0u;
-#pragma unroll 1
-          for (int t = 0; t < p.ntaps; ++t) {
-            const unsigned b_lo = p_lo + s_tapoff[t];                                     // N operand: shifted patch
-            const unsigned a_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;            // M operand: weights
-            tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_w), pack_desc(b_lo, hi_p), p.idesc, acc);
-            tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_w), pack_desc(b_lo + 2, hi_p), p.idesc, 1u);
-            if (kmma == 4) {
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_w), pack_desc(b_lo + 4, hi_p), p.idesc, 1u);
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_w), pack_desc(b_lo + 6, hi_p), p.idesc, 1u);
-            }
-            acc = 1u;
-          }
-          tc_commit(&pempty[s]);
-          if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
-        }
-        __syncwarp();
-        if (++s == p.n_pbuf) { s = 0; ph ^= 1; }
-      }
-      if (++as == 2) { as = 0; aph ^= 1; }
-    }
-  } else {
-    // ============================ epilogue: 16 warps, quarter q = warp % 4, pixel group pg = (warp - 2) / 4 ==========
-    const int q = warp & 3;
-    const int pg = (warp - 2) >> 2;                 // 64 pixel columns = tile rows pg*8 .. pg*8+7
-    const int ch = q * 32 + lane;
-    const float b = (bias && ch < p.cout) ? bias[ch] : 0.f;
-    PxStep st;
-    st.out_r = p.so * out.sh; st.out_c = p.so * out.sw;
-    st.add_r = p.so * add.sh; st.add_c = p.so * add.sw;
-    st.mask_r = p.so * mask.sh; st.mask_c = p.so * mask.sw;
-    const int jlim = min(p.mj, (out.w - p.ox0 + p.so - 1) / p.so), ilim = min(p.mi, (out.h - p.oy0 + p.so - 1) / p.so);
-    int as = 0; unsigned aph = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      long long r = tile;
-      const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
-      const int ti = (int)(r % p.tiles_i);
-      const int img = (int)(r / p.tiles_i);
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      if (q * 32 < p.cout) {
-        const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * 256 + pg * 64);
-        const int j0 = tj * WS_TW;
-        const int nvc = max(0, min(WS_TW, jlim - j0));
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          float v[32];
-          tc_ld32(taddr0 + c0, v);
-          const int i0 = ti * p.th + pg * 8 + (c0 >> 3);
-          const int nvr = max(0, min(4, ilim - i0));
-          const int oy = p.oy0 + p.so * i0, ox = p.ox0 + p.so * j0;
-          PxOff off;
-          off.out = img * out.sn + oy * out.sh + ox * out.sw;
-          off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
-          off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
-          if (nvr > 0 && nvc > 0)
-            px_chunk<8>(v, off, st, nvr, nvc, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
-        }
-        if (stats) {
-          float* srow = stats + ((long long)img * p.cout + ch) * 2;
-          atomicAdd(srow, s1);
-          atomicAdd(srow + 1, s2);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-// Returns 1 = launched, 0 = not applicable (caller uses conv_tc), other = error.
+// Returns 1 = launched, 0 = not applicable (caller uses conv_px / conv_tc), other = error.
+// Applies when the input stride is 1, the taps span <= 9 x 16 pixels and the whole packed filter plus two halo patches fit
+// in shared memory (VGG conv1_x and their dgrads, the 32-channel 256^2 layers, the vertical-tap forms of the 9x9 layers).
+// Variants measured slower and removed (scratch/dead_variants/conv_ws_r01.cu.txt, profiles/r01_summary.md finding 11):
+// streamed weights, a pixels-as-N form with 16 epilogue warps, base_offset descriptors.
 int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
                    cudaStream_t stream) {
-  const char* env = getenv("AST_CONV_WS");
-  const int mode = env ? atoi(env) : 1;   // 0 = off (A/B against conv_tc), 1 = resident weights only (default),
-                                          // 3 = also stream weights for big layers, 9 = base_offset experiment
-  if (mode == 0) return 0;
   if (g->si != 1 || g->w_img_stride != 0) return 0;
   if (g->pooled) {          // fused MaxPool2d(2,2) output: plain stride-1 launches with a full NHWC output only
     const ast_image* q = g->pooled;
@@ -460,51 +230,24 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
     dx_min = g->dx[t] < dx_min ? g->dx[t] : dx_min; dx_max = g->dx[t] > dx_max ? g->dx[t] : dx_max;
   }
   if (dx_max - dx_min > 8 || dy_max - dy_min > 15) return 0;
+  if (cpad > 256) return 0;
   WsParams p;
   memset(&p, 0, sizeof(p));
   p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
   p.kc = p.rowb / esz;
   p.kchunks = in->c / p.kc;
-  p.bn = cpad % 256 == 0 ? 256 : (cpad <= 256 ? cpad : (cpad % 128 == 0 ? 128 : (cpad % 64 == 0 ? 64 : 32)));
-  p.n_tiles_n = cpad / p.bn;
+  p.bn = cpad;
   p.w_tile_bytes = p.bn * p.rowb;
   p.w_total_bytes = g->ntaps * p.kchunks * p.w_tile_bytes;
   p.pw = (dx_max == dx_min) ? WS_TW : 16;
   const int avail = 232448 - 1024 - 1024 - 8192;        // align slack, static smem, store-transpose stage
-  int budget = avail - ((p.w_total_bytes + 1023) & ~1023);
-  // pixels-as-N kernel (opt-in, AST_WS_SWAP=1): 32 x 8 tiles; needs the resident weights + two of the taller patches
-  // (the M = 128 read of the last weight tile runs up to 128 - cout rows into the patch ring: finite data, ignored lanes).
-  // Measured (B=32, 256^2 step): conv1_1 0.43 -> 0.39 ms, but the 32-channel layers lose the two-CTAs-per-SM latency
-  // hiding (0.14 -> 0.22 ms) and the masked 64-channel VGG dgrad waits on its mask loads with only 8 of the 16 epilogue
-  // warps owning a TMEM lane quarter (0.38 -> 0.55 ms): 13.63 -> 13.76 ms per step, hence off by default.
-  static const int swap_env = [] { const char* e = getenv("AST_WS_SWAP"); return e ? atoi(e) : 0; }();
-  bool swap = false;
-  p.th = WS_TH;
-  if (swap_env && !g->pooled && !thin && p.n_tiles_n == 1 && (cpad == 32 || cpad == 64 || cpad == 128) && out->c == cpad &&
-      img32_ok(out) && img32_ok(add) && img32_ok(mask)) {
-    const int pb = (p.pw * (32 + (dy_max - dy_min)) * p.rowb + 1023) & ~1023;
-    if (budget >= 2 * pb) { swap = true; p.th = 32; }
-  }
-  p.ph = p.th + (dy_max - dy_min);
+  const int budget = avail - ((p.w_total_bytes + 1023) & ~1023);
+  p.ph = WS_TH + (dy_max - dy_min);
   p.patch_tx = p.pw * p.ph * p.rowb;
   p.patch_bytes = (p.patch_tx + 1023) & ~1023;
-  p.w_resident = (p.n_tiles_n == 1 && budget >= 2 * p.patch_bytes) ? 1 : 0;
-  if (p.w_resident) {
-    p.n_pbuf = budget / p.patch_bytes;
-    if (p.n_pbuf > WS_MAX_PBUF) p.n_pbuf = WS_MAX_PBUF;
-    p.n_wbuf = 0;
-  } else {
-    // streamed weights: 2-3 patches + a ring of per-tap weight tiles; only worth it for multi-tap filters
-    // Measured on B200 (profiles/r01_summary.md): NOT faster than conv_tc's per-tap streaming for the 128..512-channel
-    // layers (they are bound by shared-memory operand bandwidth of cta_group::1 MMAs, not by L2), so it is opt-in.
-    if (mode != 3 || g->ntaps < 4 || p.rowb != 128) return 0;
-    p.n_pbuf = 2;
-    p.n_wbuf = (avail - p.n_pbuf * p.patch_bytes) / p.w_tile_bytes;
-    if (p.n_wbuf > WS_MAX_WBUF) p.n_wbuf = WS_MAX_WBUF;
-    if (p.n_wbuf < 3) return 0;
-    if (avail - p.n_pbuf * p.patch_bytes - p.n_wbuf * p.w_tile_bytes >= p.patch_bytes) p.n_pbuf = 3;
-    p.w_total_bytes = p.n_wbuf * p.w_tile_bytes;       // ring size (smem layout below uses this)
-  }
+  if (budget < 2 * p.patch_bytes) return 0;              // the filter does not fit next to two patches
+  p.n_pbuf = budget / p.patch_bytes;
+  if (p.n_pbuf > WS_MAX_PBUF) p.n_pbuf = WS_MAX_PBUF;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_ws: cuTensorMapEncodeTiled entry point not available");
 
@@ -512,60 +255,38 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.cout_valid = out->c; p.thin = thin; p.n_img = in->n;
   p.dy_min = dy_min; p.dx_min = dx_min;
   for (int t = 0; t < g->ntaps; ++t) { p.tdy[t] = g->dy[t] - dy_min; p.tdx[t] = g->dx[t] - dx_min; }
-  p.tiles_i = (p.mi + p.th - 1) / p.th;
+  p.tiles_i = (p.mi + WS_TH - 1) / WS_TH;
   p.tiles_j = (p.mj + WS_TW - 1) / WS_TW;
-  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j * p.n_tiles_n;
+  p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j;
   p.layout_type = p.rowb == 128 ? 2u : 4u;
   p.sbo = (unsigned)(p.pw * p.rowb);
   // Measured on B200: the tensor core applies the 128B/64B swizzle XOR on ABSOLUTE shared-memory address bits, so a
   // start address shifted by whole pixels needs base_offset = 0 (setting it to (addr>>7)&7 gives wrong results).
-  p.base_mode = mode == 9 ? 1u : 0u;
   const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)((swap ? 256 : p.bn) >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
 
-  alignas(64) CUtensorMap tm_in, tm_w;
   const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  alignas(64) CUtensorMap tm_in, tm_w;
   {
     cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
     cuuint64_t strides[3] = {(cuuint64_t)in->sw * esz, (cuuint64_t)in->sh * esz, (cuuint64_t)in->sn * esz};
     cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)p.pw, (cuuint32_t)p.ph, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tm_in, dt, 4, in->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv_ws: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return (int)r; }
+    if (int r = cached_tensor_map(encode, &tm_in, dt, 4, in->ptr, dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)in->c, (cuuint64_t)((long long)g->ntaps * cpad)};
     cuuint64_t strides[1] = {(cuuint64_t)in->c * esz};
     cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv_ws: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return (int)r; }
+    if (int r = cached_tensor_map(encode, &tm_w, dt, 2, const_cast<void*>(weights), dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return r;
   }
-  if (swap) {
-    if (p.n_pbuf > 3) p.n_pbuf = 3;
-    const size_t smem_x = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)p.n_pbuf * p.patch_bytes;
-    const int grid_x = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-    cudaError_t ex;
-    if (in->dtype == AST_BF16) {
-      ex = cudaFuncSetAttribute(conv_wsx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
-      if (ex == cudaSuccess) launch_k(conv_wsx_kernel<0>, grid_x, WSX_THREADS, smem_x, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
-    } else {
-      ex = cudaFuncSetAttribute(conv_wsx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
-      if (ex == cudaSuccess) launch_k(conv_wsx_kernel<1>, grid_x, WSX_THREADS, smem_x, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
-    }
-    if (ex != cudaSuccess) { set_error("conv_wsx: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ex)); return (int)ex; }
-    count_launch();
-    AST_CUDA_LAUNCH_CHECK();
-    return 1;
-  }
-  // two CTAs per SM when both fit (AST_WS_2CTA=0 disables): trim the patch ring to 3 buffers first
-  static const int two_env = [] { const char* e = getenv("AST_WS_2CTA"); return e ? atoi(e) : 1; }();
+  // two CTAs per SM when both fit: layers whose weights + 3 patches need less than half of the shared memory (the
+  // 32-channel 256^2 layers, conv1_1) are latency bound with one persistent CTA per SM
   bool two = false;
-  if (two_env && p.w_resident) {
-    int nb = p.n_pbuf > 3 ? 3 : p.n_pbuf;
+  {
+    const int nb = p.n_pbuf > 3 ? 3 : p.n_pbuf;
     const size_t need = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)nb * p.patch_bytes + 8192;
     if (2 * (need + 1024) <= 227 * 1024) { two = true; p.n_pbuf = nb; }
   }
@@ -576,7 +297,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   Img pooli = g->pooled ? to_img(g->pooled) : null_img();
   cudaError_t e;
 #define WS_LAUNCH(K, B)                                                                                          \
-  e = cudaFuncSetAttribute(conv_ws_kernel<K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  e = set_max_smem(conv_ws_kernel<K, B>, smem);                                                                   \
   if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats, pooli)
   if (in->dtype == AST_BF16) {
     if (two) { WS_LAUNCH(0, 2); } else { WS_LAUNCH(0, 1); }
@@ -586,6 +307,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
 #undef WS_LAUNCH
   if (e != cudaSuccess) { set_error("conv_ws: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  count_work(FAM_CONV_WS, conv_flops(in, out, g), conv_bytes(in, out, g, add, mask));
   AST_CUDA_LAUNCH_CHECK();
   return 1;
 }

@@ -28,7 +28,6 @@ template <typename TI>
 __global__ void __launch_bounds__(256)
 conv_gather_simt_kernel(Img in, const TI* __restrict__ wts, const float* __restrict__ bias,
                         const float* __restrict__ in_shift, Img add, Img mask, Img out, GeomDev g) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
 
@@ -168,7 +167,6 @@ __global__ void __launch_bounds__(256)
 wgrad_gather_simt_kernel(Img x, Img gout, float* __restrict__ dw, const int* __restrict__ tap_off,
                          long long s_co, long long s_ci, GeomDev g, int nci_tiles, long long chunk,
                          long long dw_img_stride, int ksplit, float scale) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   __shared__ __align__(16) float Ys[BK][BN + 4];
   __shared__ __align__(16) float Xs[BK][BM + 4];
   const int tid = threadIdx.x;
@@ -275,7 +273,6 @@ wgrad_gather_simt_kernel(Img x, Img gout, float* __restrict__ dw, const int* __r
 template <typename TO, bool ROUND_TF32 = false>
 __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps,
                                     int a, int b, long long s_a, long long s_b, TO* __restrict__ dst) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)ntaps * a * b;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -291,9 +288,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
                    const ast_image* add, const ast_image* mask, const ast_image* out,
                    const ast_gather_geom* geom, cudaStream_t stream);  // conv_tc.cu
+struct GramFin;
 int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_image* cols, int c_s, const short* dy,
                 const short* dx, int ntaps, int mi, int mj, float* out, const int* tap_off, long long s_m,
-                long long s_n, long long out_img_stride, float scale, int upper_only, cudaStream_t stream);  // contract_tc.cu
+                long long s_n, long long out_img_stride, float scale, int upper_only, cudaStream_t stream,
+                const GramFin* finp);  // contract_tc.cu
 
 }  // namespace ast
 
@@ -325,6 +324,7 @@ extern "C" int ast_conv_gather(const ast_image* in, const void* weights, const f
     launch_k(conv_gather_simt_kernel<__nv_bfloat16>, grid, 256, 0, (cudaStream_t)stream, 
         to_img(in), (const __nv_bfloat16*)weights, bias, in_shift, addi, maski, to_img(out), g);
   count_launch();
+  count_work(FAM_CONV_SIMT, conv_flops(in, out, geom), conv_bytes(in, out, geom, add, mask));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -352,6 +352,10 @@ int launch_wgrad_simt(const ast_image* x, const ast_image* gout, float* dw, cons
   else LAUNCH(__nv_bfloat16, float);
 #undef LAUNCH
   count_launch();
+  if (dw_img_stride)
+    count_work(FAM_GRAM_SIMT, (double)x->n * x->c * (x->c + 1.0) * per_img, img_bytes(x) + 4.0 * x->n * x->c * x->c);
+  else
+    count_work(FAM_WGRAD_SIMT, 2.0 * x->n * per_img * geom->ntaps * x->c * gout->c, img_bytes(x) + img_bytes(gout));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -365,7 +369,7 @@ extern "C" int ast_wgrad_gather(const ast_image* x, const ast_image* gout, float
   if (x->n == 0) return 0;
   if (geom->flags & AST_CONV_TENSOR)
     return contract_tc(gout, geom->so, geom->oy0, geom->ox0, x, geom->si, geom->dy, geom->dx, geom->ntaps, geom->mi,
-                       geom->mj, dw, tap_off, s_co, s_ci, 0, 1.f, 0, (cudaStream_t)stream);
+                       geom->mj, dw, tap_off, s_co, s_ci, 0, 1.f, 0, (cudaStream_t)stream, nullptr);
   return launch_wgrad_simt(x, gout, dw, tap_off, s_co, s_ci, geom, 0, 1.f, (cudaStream_t)stream);
 }
 

@@ -14,7 +14,6 @@ namespace ast {
 __global__ void __launch_bounds__(256)
 row_im2col_kernel(Img src, Img out, const float* __restrict__ shift, int kw, int sign, int px, int py, int reflect,
                   int round_tf32) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int C = src.c;
   const long long total = (long long)out.n * out.h * out.w * out.c;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
@@ -47,7 +46,6 @@ template <int OUTC, int KW, int CC>
 __global__ void __launch_bounds__(256)
 row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw_rt, int sign, int px, int py, int reflect,
                       int round_tf32) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int C = CC > 0 ? CC : src.c;
   const int kw = KW > 0 ? KW : kw_rt;
   const long long total = (long long)out.n * out.h * out.w;
@@ -111,7 +109,6 @@ template <typename TO, bool ROUND_TF32>
 __global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int* __restrict__ tap_off, int ntaps, int a,
                                        int a_valid, int b, int b_valid, int b0, long long s_a, long long s_b1,
                                        long long s_b0, TO* __restrict__ dst) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)ntaps * a * b;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -125,50 +122,9 @@ __global__ void pack_weights_ex_kernel(const float* __restrict__ src, const int*
   }
 }
 
-// out[n, y, x, d*C + j] = src[n, y + sign*d - py, x, j]  (0 outside): folds kh vertical taps of an NHWC tensor into
-// channels with 16-byte copies, so a kh-tap filter-gradient contraction becomes ONE tap with kh*C channels.
-__global__ void __launch_bounds__(256) unfold_rows_kernel(Img src, Img out, int kh, int sign, int py, int esz) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  const int cpp = src.c * esz / 16;                 // 16-byte chunks per source pixel
-  const long long total = (long long)out.n * out.h * out.w * kh * cpp;
-  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const int ch = (int)(idx % cpp);
-    long long r = idx / cpp;
-    const int d = (int)(r % kh); r /= kh;
-    const int x = (int)(r % out.w); r /= out.w;
-    const int y = (int)(r % out.h);
-    const int n = (int)(r / out.h);
-    const int sy = y + sign * d - py;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (sy >= 0 && sy < src.h)
-      v = *reinterpret_cast<const uint4*>(src.ptr + (img_off(src, n, sy, x, 0) * esz + ch * 16));
-    *reinterpret_cast<uint4*>(out.ptr + ((img_off(out, n, y, x, 0) + (long long)d * src.c) * esz + ch * 16)) = v;
-  }
-}
-
 }  // namespace ast
 
-using namespace ast;
-
-extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32_t kh, int32_t sign, int32_t py,
-                               void* stream) {
-  AST_CHECK_ARG(src && out, "ast_unfold_rows: null argument");
-  const int esz = src->dtype == AST_F32 ? 4 : 2;
-  AST_CHECK_ARG(src->dtype == out->dtype && out->n == src->n && out->w == src->w && out->c == kh * src->c,
-                "ast_unfold_rows: out must be [n, *, w, kh*c] of the same dtype");
-  AST_CHECK_ARG(src->sc == 1 && out->sc == 1 && (src->c * esz) % 16 == 0 && (src->sw * esz) % 16 == 0 &&
-                (src->sh * esz) % 16 == 0 && (src->sn * esz) % 16 == 0 && (out->sw * esz) % 16 == 0 &&
-                (out->sh * esz) % 16 == 0 && (out->sn * esz) % 16 == 0 && (sign == 1 || sign == -1),
-                "ast_unfold_rows: NHWC tensors with 16-byte aligned pixels required");
-  const long long total = (long long)out->n * out->h * out->w * kh * (src->c * esz / 16);
-  if (total == 0) return 0;
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-  launch_k(unfold_rows_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, to_img(src), to_img(out), kh, sign, py, esz);
-  count_launch();
-  AST_CUDA_LAUNCH_CHECK();
-  return 0;
-}
+namespace ast {
 
 // Inverse companion of ast_row_im2col for a thin-OUTPUT k x k convolution (the 32->3 9x9 last layer, cnn.py:39):
 // the k vertical taps run as a tcgen05 conv whose output channel r = d*C + c holds, at pixel (y, x'), the partial sum
@@ -177,7 +133,6 @@ extern "C" int ast_unfold_rows(const ast_image* src, const ast_image* out, int32
 // One block per (n, y) row: the row of partial sums is staged in shared memory with coalesced 16-byte loads.
 __global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const float* __restrict__ bias, int kw, int relu,
                                                         int segw) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   extern __shared__ float row[];
   const int n = blockIdx.x / out.h, y = blockIdx.x % out.h;
   const int x0 = blockIdx.y * segw, nx = min(segw, out.w - x0);       // this block's output columns [x0, x0 + nx)
@@ -200,6 +155,10 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(Img part, Img out, const
   }
 }
 
+}  // namespace ast
+
+using namespace ast;
+
 extern "C" int ast_fold_rows(const ast_image* part, const ast_image* out, const float* bias, int32_t kw, int32_t relu,
                              void* stream) {
   AST_CHECK_ARG(part && out, "ast_fold_rows: null argument");
@@ -216,6 +175,7 @@ extern "C" int ast_fold_rows(const ast_image* part, const ast_image* out, const 
   dim3 grid((unsigned)(out->n * out->h), (unsigned)((out->w + segw - 1) / segw));
   launch_k(fold_rows_kernel, grid, 256, smem, (cudaStream_t)stream, to_img(part), to_img(out), bias, kw, relu, segw);
   count_launch();
+  count_work(FAM_POINTWISE, 0.0, img_bytes(part) + img_bytes(out));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -242,6 +202,7 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
     else RIK(16, 0, 0);
 #undef RIK
     count_launch();
+    count_work(FAM_POINTWISE, 0.0, img_bytes(src) + img_bytes(out));
     AST_CUDA_LAUNCH_CHECK();
     return 0;
   }
@@ -250,6 +211,7 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
   launch_k(row_im2col_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, to_img(src), to_img(out), shift, kw, sign, px, py,
                                                                    reflect, round_tf32);
   count_launch();
+  count_work(FAM_POINTWISE, 0.0, img_bytes(src) + img_bytes(out));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -271,6 +233,7 @@ extern "C" int ast_pack_weights_ex(const float* src, const int32_t* tap_off, int
   else AST_CHECK_ARG(false, "ast_pack_weights_ex: bad dtype %d", dst_dtype);
 #undef PK
   count_launch();
+  count_work(FAM_OPTIM, 0.0, 6.0 * total);
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }

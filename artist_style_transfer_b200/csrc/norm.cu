@@ -12,7 +12,6 @@ constexpr int NT = 256;
 template <typename T>
 __global__ void __launch_bounds__(NT)
 in_stats_partial_kernel(Img x, float* __restrict__ ws, int nblk, int chunk) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ float sm[];
   const int C = x.c, lanes = C / VEC, slots = NT / lanes;
@@ -72,7 +71,6 @@ in_stats_partial_kernel(Img x, float* __restrict__ ws, int nblk, int chunk) {
 
 __global__ void in_stats_final_kernel(const float* __restrict__ ws, int nblk, int C, int hw, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float na = 0.f, ma = 0.f, qa = 0.f;
@@ -95,7 +93,6 @@ template <typename TX, typename TO>
 __global__ void __launch_bounds__(NT)
 in_apply_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, Img res, Img out, int pad, int relu) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = 4;  // 4 channels per thread regardless of dtype (8B bf16 / 16B fp32 accesses)
   const int C = x.c, lanes = C / VEC;
   const long long total = (long long)out.n * out.h * out.w * lanes;
@@ -175,7 +172,6 @@ __global__ void __launch_bounds__(NT)
 in_bwd_stats_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
                     int relu, float* __restrict__ s1o, float* __restrict__ s2o, int chunk) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = 4;
   extern __shared__ float sm[];
   const int C = x.c, lanes = C / VEC, slots = NT / lanes;
@@ -224,7 +220,6 @@ __global__ void __launch_bounds__(NT)
 in_bwd_apply_kernel(Img x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, Img gpad, int pad, Img gextra,
                     int relu, const float* __restrict__ s1, const float* __restrict__ s2, Img dx, Img gtotal) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   constexpr int VEC = 4;
   const int C = x.c, lanes = C / VEC;
   const float inv_hw = 1.f / (float)(x.h * x.w);
@@ -258,15 +253,14 @@ in_bwd_apply_kernel(Img x, const float* __restrict__ mean, const float* __restri
   }
 }
 
-__global__ void in_finalize_kernel(const float* __restrict__ sums, int total, float inv_hw, float eps,
+__global__ void in_finalize_kernel(const double* __restrict__ sums, int total, double inv_hw, float eps,
                                    float* __restrict__ mean, float* __restrict__ rstd) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const float m = sums[2 * i] * inv_hw;
-  const float var = fmaxf(sums[2 * i + 1] * inv_hw - m * m, 0.f);
-  mean[i] = m;
-  rstd[i] = rsqrtf(var + eps);
+  const double m = sums[2 * i] * inv_hw;
+  const double var = fmax(sums[2 * i + 1] * inv_hw - m * m, 0.0);
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 static int stats_blocks(int n, int hw, int slots) {
@@ -283,16 +277,20 @@ static bool nhwc_ok(const ast_image* x, int vec) {
 
 }  // namespace ast
 
-namespace ast {   // norm_fast.cu: return 1 = launched, 0 = not applicable (use the generic kernel), other = error
-int instnorm_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                        const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s);
-int instnorm_bwd_stats_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
-                            const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
-                            float* s1, float* s2, cudaStream_t s);
-int instnorm_bwd_apply_fast(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
-                            const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
-                            const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
-                            cudaStream_t s);
+namespace ast {   // norm_staged.cu: return 1 = launched, 0 = not applicable (use the generic kernel), other = error
+int instnorm_apply_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s);
+int instnorm_bwd_stats_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                              float* s1, float* s2, cudaStream_t s);
+int instnorm_bwd_apply_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                              const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
+                              cudaStream_t s);
+int instnorm_bwd_fused_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                              float* s1, float* s2, int* arrive, const ast_image* dx, const ast_image* gtotal,
+                              cudaStream_t s);
 }  // namespace ast
 
 using namespace ast;
@@ -318,17 +316,19 @@ extern "C" int ast_instnorm_stats(const ast_image* x, float* mean, float* rstd, 
   else launch_k(in_stats_partial_kernel<__nv_bfloat16>, grid, NT, smem, s, to_img(x), (float*)workspace, nblk, chunk);
   launch_k(in_stats_final_kernel, x->n, 128, 0, s, (const float*)workspace, nblk, x->c, hw, eps, mean, rstd);
   count_launch(2);
+  count_work(FAM_IN_STATS, 0.0, img_bytes(x));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ast_instnorm_finalize(const float* sums, int32_t n, int32_t c, int32_t hw, float eps, float* mean,
+extern "C" int ast_instnorm_finalize(const double* sums, int32_t n, int32_t c, int32_t hw, float eps, float* mean,
                                      float* rstd, void* stream) {
   AST_CHECK_ARG(sums && mean && rstd && hw > 0, "ast_instnorm_finalize: bad argument");
   const int total = n * c;
   if (total == 0) return 0;
-  launch_k(in_finalize_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, sums, total, 1.f / (float)hw, eps, mean, rstd);
+  launch_k(in_finalize_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, sums, total, 1.0 / (double)hw, eps, mean, rstd);
   count_launch();
+  count_work(FAM_IN_STATS, 0.0, 0.0);
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -343,7 +343,7 @@ extern "C" int ast_instnorm_apply(const ast_image* x, const float* mean, const f
   AST_CHECK_ARG(pad < x->h && pad < x->w, "ast_instnorm_apply: pad too large for reflection");
   AST_CHECK_ARG(!residual || (same_shape(residual, x) && residual->sc == 1), "ast_instnorm_apply: residual shape");
   if (x->n == 0) return 0;
-  if (int fr = instnorm_apply_fast(x, mean, rstd, gamma, beta, residual, out, pad, relu, (cudaStream_t)stream))
+  if (int fr = instnorm_apply_staged(x, mean, rstd, gamma, beta, residual, out, pad, relu, (cudaStream_t)stream))
     return fr == 1 ? 0 : fr;
   const long long total = (long long)out->n * out->h * out->w * (x->c / 4);
   const int blocks = (int)min((total + NT - 1) / NT, (long long)num_sms() * 16);
@@ -356,6 +356,7 @@ extern "C" int ast_instnorm_apply(const ast_image* x, const float* mean, const f
   else LA(__nv_bfloat16, float);
 #undef LA
   count_launch();
+  count_work(FAM_IN_APPLY, 0.0, img_bytes(x) + img_bytes(out) + img_bytes(residual));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -377,9 +378,12 @@ extern "C" int ast_instnorm_bwd_stats(const ast_image* x, const float* mean, con
   if (int e = bwd_check("ast_instnorm_bwd_stats", x, gpad, pad, gextra)) return e;
   if (x->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(s1, 0, sizeof(float) * x->n * x->c, s);
-  cudaMemsetAsync(s2, 0, sizeof(float) * x->n * x->c, s);
-  if (int fr = instnorm_bwd_stats_fast(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, s))
+  if (!(relu & AST_IN_SUMS_ZEROED)) {
+    cudaMemsetAsync(s1, 0, sizeof(float) * x->n * x->c, s);
+    cudaMemsetAsync(s2, 0, sizeof(float) * x->n * x->c, s);
+  }
+  relu &= 1;
+  if (int fr = instnorm_bwd_stats_staged(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, s))
     return fr == 1 ? 0 : fr;
   const int lanes = x->c / 4, slots = NT / lanes, hw = x->h * x->w;
   const int nblk = stats_blocks(x->n, hw, slots);
@@ -392,6 +396,7 @@ extern "C" int ast_instnorm_bwd_stats(const ast_image* x, const float* mean, con
   else
     launch_k(in_bwd_stats_kernel<__nv_bfloat16>, grid, NT, smem, s, to_img(x), mean, rstd, gamma, beta, gp, pad, ge, relu, s1, s2, chunk);
   count_launch();
+  count_work(FAM_IN_BWD, 0.0, 0.0);
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -405,7 +410,8 @@ extern "C" int ast_instnorm_bwd_apply(const ast_image* x, const float* mean, con
   AST_CHECK_ARG(same_shape(dx, x) && dx->sc == 1, "ast_instnorm_bwd_apply: dx shape");
   AST_CHECK_ARG(!gtotal || (same_shape(gtotal, x) && gtotal->sc == 1), "ast_instnorm_bwd_apply: gtotal shape");
   if (x->n == 0) return 0;
-  if (int fr = instnorm_bwd_apply_fast(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, dx, gtotal,
+  relu &= 1;
+  if (int fr = instnorm_bwd_apply_staged(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, dx, gtotal,
                                        (cudaStream_t)stream))
     return fr == 1 ? 0 : fr;
   const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
@@ -420,6 +426,25 @@ extern "C" int ast_instnorm_bwd_apply(const ast_image* x, const float* mean, con
   else LB(__nv_bfloat16, float);
 #undef LB
   count_launch();
+  count_work(FAM_IN_BWD, 0.0, 2.0 * img_bytes(x) + img_bytes(dx) + img_bytes(gtotal));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ast_instnorm_bwd(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                                const float* beta, const ast_image* gpad, int32_t pad, const ast_image* gextra,
+                                int32_t relu, float* s1, float* s2, int32_t* arrive, const ast_image* dx,
+                                const ast_image* gtotal, void* stream) {
+  AST_CHECK_ARG(x && mean && rstd && gamma && beta && s1 && s2 && dx, "ast_instnorm_bwd: null argument");
+  if (int e = bwd_check("ast_instnorm_bwd", x, gpad, pad, gextra)) return e;
+  AST_CHECK_ARG(same_shape(dx, x) && dx->sc == 1, "ast_instnorm_bwd: dx shape");
+  AST_CHECK_ARG(!gtotal || (same_shape(gtotal, x) && gtotal->sc == 1), "ast_instnorm_bwd: gtotal shape");
+  if (x->n == 0) return 0;
+  if (arrive && (relu & AST_IN_SUMS_ZEROED)) {
+    if (int fr = instnorm_bwd_fused_staged(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu & 1, s1, s2, arrive, dx, gtotal,
+                                           (cudaStream_t)stream))
+      return fr == 1 ? 0 : fr;
+  }
+  if (int e = ast_instnorm_bwd_stats(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, stream)) return e;
+  return ast_instnorm_bwd_apply(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, s1, s2, dx, gtotal, stream);
 }

@@ -110,8 +110,6 @@ __global__ void __launch_bounds__(NS_THREADS, 2)
 in_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta, Rows res, Rows out, NsShape sh,
                        int relu) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -265,8 +263,6 @@ __global__ void __launch_bounds__(NS_THREADS, 2)
 in_bwd_stats_staged_kernel(Rows x, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, Rows gpad, Rows gextra,
                            NsShape sh, int relu, float* __restrict__ s1o, float* __restrict__ s2o) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -337,8 +333,6 @@ in_bwd_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
                            const float* __restrict__ gamma, const float* __restrict__ beta, Rows gpad, Rows gextra,
                            NsShape sh, int relu, const float* __restrict__ s1, const float* __restrict__ s2, Rows dx,
                            Rows gtotal) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
-  pdl_trigger();
   constexpr int VEC = NsVec<T>::N;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
@@ -396,6 +390,153 @@ in_bwd_apply_staged_kernel(Rows x, const float* __restrict__ mean, const float* 
   }
 }
 
+// ---------------------------------------------------------------- backward, both passes in ONE kernel
+// The two-kernel backward reads x and g' twice from HBM (7 physical passes for 5 algorithmic ones).  For layers whose
+// x + g' fit in the 126 MB L2 (the thirteen 64^2 x 128 layers of the B=32 step: 67-100 MB) this kernel runs the
+// statistics pass, meets the other blocks of the SAME image at a counter barrier (all blocks are co-resident: the grid is
+// one wave, launched cooperatively), and re-streams its own rows for the apply pass - which now hit L2.  The producer warp
+// does not wait at the barrier: it keeps prefetching the first apply units into the ring while the sums settle.
+template <typename T>
+__global__ void __launch_bounds__(NS_THREADS, 2)
+in_bwd_fused_staged_kernel(Rows x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, Rows gpad, Rows gextra,
+                           NsShape sh, int relu, float* __restrict__ s1o, float* __restrict__ s2o, int* __restrict__ arrive,
+                           Rows dx, Rows gtotal) {
+  constexpr int VEC = NsVec<T>::N;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full[NS_MAX_STAGES], empty[NS_MAX_STAGES];
+  const unsigned buf = (smem_u32(smem_raw) + 127u) & ~127u;
+  ns_init(full, empty, sh.stages);
+  const int n = blockIdx.y, C = sh.C;
+  const int rbeg = (int)((long long)blockIdx.x * sh.H / sh.nblk), rend = (int)((long long)(blockIdx.x + 1) * sh.H / sh.nblk);
+  const int nunits = (rend - rbeg) * sh.nseg;
+  const int nslabs = 1 + (gpad.ptr ? 1 : 0) + (gextra.ptr ? 1 : 0);
+  const int stage_bytes = nslabs * sh.slab_bytes;
+  const int lanes = C / VEC, slots = NS_CONSUMERS / lanes;
+
+  if (threadIdx.x >= NS_CONSUMERS) {
+    if (threadIdx.x == NS_CONSUMERS) {       // the same unit sequence twice (ring positions simply continue)
+      for (int k2 = 0; k2 < 2 * nunits; ++k2) {
+        const int k = k2 < nunits ? k2 : k2 - nunits;
+        const int s = k2 % sh.stages;
+        const unsigned ph = (unsigned)(k2 / sh.stages) & 1u;
+        const int i = rbeg + k / sh.nseg, sg = k % sh.nseg;
+        const int ja = sg * sh.seg, jb = min(sh.W, ja + sh.seg);
+        const unsigned bytes = (unsigned)((jb - ja) * C * (int)sizeof(T));
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], bytes * nslabs);
+        unsigned dst = buf + s * stage_bytes;
+        bulk_load(dst, rows_ptr<T>(x, n * x.sn + i * x.sh + ja * C), bytes, &full[s]);
+        dst += sh.slab_bytes;
+        if (gpad.ptr) {
+          bulk_load(dst, rows_ptr<T>(gpad, n * gpad.sn + (i + sh.pad) * gpad.sh + (ja + sh.pad) * C), bytes, &full[s]);
+          dst += sh.slab_bytes;
+        }
+        if (gextra.ptr) bulk_load(dst, rows_ptr<T>(gextra, n * gextra.sn + i * gextra.sh + ja * C), bytes, &full[s]);
+      }
+    }
+    return;
+  }
+  const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+  const int c = lane * VEC;
+  float A[VEC], D[VEC];
+  {
+    float mu[VEC];
+    ns_ldc<VEC>(gamma + c, A); ns_ldc<VEC>(rstd + n * C + c, D); ns_ldc<VEC>(mean + n * C + c, mu);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) A[e] *= D[e];
+    ns_ldc<VEC>(beta + c, D);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) D[e] -= A[e] * mu[e];
+  }
+  const int gb = n * gpad.sn + c;
+  // ---- pass 1: statistics
+  {
+    float t1[VEC], t2[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { t1[e] = 0.f; t2[e] = 0.f; }
+    for (int k = 0; k < nunits; ++k) {
+      const int s = k % sh.stages;
+      const unsigned ph = (unsigned)(k / sh.stages) & 1u;
+      const int i = rbeg + k / sh.nseg, sg = k % sh.nseg;
+      const int ja = sg * sh.seg, jb = min(sh.W, ja + sh.seg);
+      const bool brow = sh.pad > 0 && (i <= sh.pad || i >= sh.H - 1 - sh.pad);
+      const unsigned xs = buf + s * stage_bytes + (unsigned)(c * (int)sizeof(T));
+      const unsigned gs = xs + sh.slab_bytes;
+      const unsigned es = xs + (gpad.ptr ? 2 : 1) * sh.slab_bytes;
+      mbar_wait(&full[s], ph);
+      for (int j = ja + slot; j < jb; j += slots) {
+        const unsigned poff = (unsigned)((j - ja) * C * (int)sizeof(T));
+        NS_GPRIME()
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { t1[e] += g[e]; t2[e] = fmaf(g[e], xv[e], t2[e]); }
+      }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+    }
+    // block reduction in a scratch area BEHIND the ring (the producer is already refilling the ring for pass 2)
+    float* r1 = reinterpret_cast<float*>(smem_raw + (buf - smem_u32(smem_raw)) + (size_t)sh.stages * stage_bytes);
+    float* r2 = r1 + slots * C;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { r1[slot * C + c + e] = t1[e]; r2[slot * C + c + e] = t2[e]; }
+    asm volatile("bar.sync 1, %0;" ::"n"(NS_CONSUMERS) : "memory");
+    for (int cc = threadIdx.x; cc < C; cc += NS_CONSUMERS) {
+      float u1 = 0.f, u2 = 0.f;
+      for (int q = 0; q < slots; ++q) { u1 += r1[q * C + cc]; u2 += r2[q * C + cc]; }
+      atomicAdd(s1o + n * C + cc, u1);
+      atomicAdd(s2o + n * C + cc, rstd[n * C + cc] * (u2 - mean[n * C + cc] * u1));
+    }
+    // ---- all blocks of image n have added their sums: release / acquire through the fence + counter
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(NS_CONSUMERS) : "memory");
+    if (threadIdx.x == 0) {
+      atomicAdd(arrive + n, 1);
+      const volatile int* cnt = arrive + n;
+      for (unsigned spin = 0; *cnt < sh.nblk; ++spin)
+        if (spin > (1u << 28)) __trap();            // bounded: a scheduling surprise traps instead of hanging the GPU
+      __threadfence();
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NS_CONSUMERS) : "memory");
+  }
+  // ---- pass 2: apply (x and g' of this block's rows were just read: they are served from L2)
+  const float inv_hw = 1.f / (float)(sh.H * sh.W);
+  float B[VEC], Cc[VEC];
+  {
+    float mu[VEC], rs[VEC];
+    ns_ldc<VEC>(rstd + n * C + c, rs); ns_ldc<VEC>(mean + n * C + c, mu);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float S1 = __ldcg(s1o + n * C + c + e), S2 = __ldcg(s2o + n * C + c + e);
+      B[e] = -A[e] * rs[e] * S2 * inv_hw;
+      Cc[e] = -A[e] * S1 * inv_hw - B[e] * mu[e];
+    }
+  }
+  const int db = n * dx.sn + c, tb = n * gtotal.sn + c;
+  for (int k = 0; k < nunits; ++k) {
+    const int k2 = nunits + k;
+    const int s = k2 % sh.stages;
+    const unsigned ph = (unsigned)(k2 / sh.stages) & 1u;
+    const int i = rbeg + k / sh.nseg, sg = k % sh.nseg;
+    const int ja = sg * sh.seg, jb = min(sh.W, ja + sh.seg);
+    const bool brow = sh.pad > 0 && (i <= sh.pad || i >= sh.H - 1 - sh.pad);
+    const unsigned xs = buf + s * stage_bytes + (unsigned)(c * (int)sizeof(T));
+    const unsigned gs = xs + sh.slab_bytes;
+    const unsigned es = xs + (gpad.ptr ? 2 : 1) * sh.slab_bytes;
+    const int drow = db + i * dx.sh, trow = tb + i * gtotal.sh;
+    mbar_wait(&full[s], ph);
+    for (int j = ja + slot; j < jb; j += slots) {
+      const unsigned poff = (unsigned)((j - ja) * C * (int)sizeof(T));
+      NS_GPRIME()
+      if (gtotal.ptr) rows_store<T>(gtotal, trow + j * C, NsVec<T>::pack(g));
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) xv[e] = fmaf(A[e], g[e], fmaf(B[e], xv[e], Cc[e]));
+      rows_store<T>(dx, drow + j * C, NsVec<T>::pack(xv));
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 static bool rows_ok(const ast_image* im, int vec) {
   if (!im) return true;
@@ -409,10 +550,6 @@ static Rows to_rows(const ast_image* im) {
   if (!im) { r.ptr = nullptr; r.sn = r.sh = 0; return r; }
   r.ptr = (const char*)im->ptr; r.sn = (int)im->sn; r.sh = (int)im->sh;
   return r;
-}
-static bool staged_enabled() {
-  static const int on = [] { const char* e = getenv("AST_IN_STAGED"); return e ? atoi(e) : 1; }();
-  return on != 0;
 }
 // rows per block / segments / stages; false when the shape does not suit the staged kernels
 static bool ns_plan(NsShape* sh, int n, int C, int H, int W, int pad, int rows_total, int width, int esz, int nslabs, int* nblk) {
@@ -440,14 +577,14 @@ static bool ns_plan(NsShape* sh, int n, int C, int H, int W, int pad, int rows_t
 
 template <typename K>
 static cudaError_t ns_attr(K kernel, size_t smem) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return set_max_smem(kernel, smem);
 }
 
 // Each returns 1 if the staged kernel was launched, 0 if the caller should use the register kernels.
 int instnorm_apply_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           const ast_image* residual, const ast_image* out, int pad, int relu, cudaStream_t s) {
   const int vec = x->dtype == AST_F32 ? 4 : 8, esz = x->dtype == AST_F32 ? 4 : 2;
-  if (!staged_enabled() || x->dtype != out->dtype || !rows_ok(x, vec) || !rows_ok(out, vec)) return 0;
+  if (x->dtype != out->dtype || !rows_ok(x, vec) || !rows_ok(out, vec)) return 0;
   if (residual && (residual->dtype != x->dtype || !rows_ok(residual, vec))) return 0;
   if (pad >= x->h || pad >= x->w) return 0;
   NsShape sh;
@@ -466,6 +603,7 @@ int instnorm_apply_staged(const ast_image* x, const float* mean, const float* rs
   }
   if (e != cudaSuccess) { set_error("instnorm_apply_staged: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  count_work(FAM_IN_APPLY, 0.0, img_bytes(x) + img_bytes(out) + img_bytes(residual));
   AST_CUDA_LAUNCH_CHECK();
   return 1;
 }
@@ -481,7 +619,7 @@ int instnorm_bwd_stats_staged(const ast_image* x, const float* mean, const float
                               const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
                               float* s1, float* s2, cudaStream_t s) {
   const int vec = x->dtype == AST_F32 ? 4 : 8, esz = x->dtype == AST_F32 ? 4 : 2;
-  if (!staged_enabled() || !bwd_rows_ok(x, gpad, gextra, vec)) return 0;
+  if (!bwd_rows_ok(x, gpad, gextra, vec)) return 0;
   NsShape sh;
   int nblk;
   const int nslabs = 1 + (gpad ? 1 : 0) + (gextra ? 1 : 0);
@@ -501,6 +639,7 @@ int instnorm_bwd_stats_staged(const ast_image* x, const float* mean, const float
   }
   if (e != cudaSuccess) { set_error("instnorm_bwd_stats_staged: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  count_work(FAM_IN_BWD, 0.0, 0.0);     // algorithmic bytes of the backward pair are booked by the apply launch
   AST_CUDA_LAUNCH_CHECK();
   return 1;
 }
@@ -510,7 +649,7 @@ int instnorm_bwd_apply_staged(const ast_image* x, const float* mean, const float
                               const float* s1, const float* s2, const ast_image* dx, const ast_image* gtotal,
                               cudaStream_t s) {
   const int vec = x->dtype == AST_F32 ? 4 : 8, esz = x->dtype == AST_F32 ? 4 : 2;
-  if (!staged_enabled() || x->dtype != dx->dtype || !bwd_rows_ok(x, gpad, gextra, vec) || !rows_ok(dx, vec)) return 0;
+  if (x->dtype != dx->dtype || !bwd_rows_ok(x, gpad, gextra, vec) || !rows_ok(dx, vec)) return 0;
   if (gtotal && (gtotal->dtype != x->dtype || !rows_ok(gtotal, vec))) return 0;
   NsShape sh;
   int nblk;
@@ -528,6 +667,52 @@ int instnorm_bwd_apply_staged(const ast_image* x, const float* mean, const float
   }
   if (e != cudaSuccess) { set_error("instnorm_bwd_apply_staged: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  // algorithmic traffic of the InstanceNorm backward: read x and g' once, write dx (+ the skip gradient)
+  count_work(FAM_IN_BWD, 0.0, 2.0 * img_bytes(x) + img_bytes(dx) + img_bytes(gtotal));
+  AST_CUDA_LAUNCH_CHECK();
+  return 1;
+}
+
+// Both backward passes in one cooperative launch when x + g' can stay in L2 between them.  `arrive`: n ints, zero on entry.
+// Returns 1 = launched, 0 = not applicable (caller runs the two-kernel path), other = error.
+int instnorm_bwd_fused_staged(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const ast_image* gpad, int pad, const ast_image* gextra, int relu,
+                              float* s1, float* s2, int* arrive, const ast_image* dx, const ast_image* gtotal,
+                              cudaStream_t s) {
+  const int vec = x->dtype == AST_F32 ? 4 : 8, esz = x->dtype == AST_F32 ? 4 : 2;
+  if (x->dtype != dx->dtype || !bwd_rows_ok(x, gpad, gextra, vec) || !rows_ok(dx, vec)) return 0;
+  if (gtotal && (gtotal->dtype != x->dtype || !rows_ok(gtotal, vec))) return 0;
+  const int nslabs = 1 + (gpad ? 1 : 0) + (gextra ? 1 : 0);
+  const double resident = (double)nslabs * x->n * x->h * x->w * x->c * esz;      // bytes re-read by the second pass
+  if (resident > 104e6) return 0;                    // would not survive in the 126 MB L2 next to the dx / skip-gradient writes
+  NsShape sh;
+  int nblk;
+  if (!ns_plan(&sh, x->n, x->c, x->h, x->w, pad, x->h, x->w, esz, nslabs, &nblk)) return 0;
+  if ((long long)nblk * x->n > 2ll * num_sms()) return 0;          // the counter barrier needs every block resident
+  const size_t scratch = 2 * (size_t)(NS_CONSUMERS / (x->c / vec)) * x->c * sizeof(float);
+  while (sh.stages > 2 && (size_t)sh.stages * nslabs * sh.slab_bytes + scratch + 128 > (size_t)NS_SMEM_BUDGET + 8192) --sh.stages;
+  const size_t smem = (size_t)sh.stages * nslabs * sh.slab_bytes + scratch + 128;
+  if (smem > 110 * 1024) return 0;
+  dim3 grid(nblk, x->n);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(NS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative;
+  attr.val.cooperative = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaError_t e;
+  Rows xr = to_rows(x), gp = to_rows(gpad), ge = to_rows(gextra), dxr = to_rows(dx), gt = to_rows(gtotal);
+  if (x->dtype == AST_F32) {
+    e = ns_attr(in_bwd_fused_staged_kernel<float>, smem);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, in_bwd_fused_staged_kernel<float>, xr, mean, rstd, gamma, beta, gp, ge, sh, relu, s1, s2, arrive, dxr, gt);
+  } else {
+    e = ns_attr(in_bwd_fused_staged_kernel<__nv_bfloat16>, smem);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, in_bwd_fused_staged_kernel<__nv_bfloat16>, xr, mean, rstd, gamma, beta, gp, ge, sh, relu, s1, s2, arrive, dxr, gt);
+  }
+  if (e != cudaSuccess) { set_error("instnorm_bwd_fused_staged: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  count_work(FAM_IN_BWD, 0.0, 2.0 * img_bytes(x) + img_bytes(dx) + img_bytes(gtotal));
   AST_CUDA_LAUNCH_CHECK();
   return 1;
 }

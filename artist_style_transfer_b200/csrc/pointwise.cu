@@ -9,7 +9,6 @@ namespace ast {
 constexpr int NT = 256;
 
 __global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = x.c / 4;
   const long long total = (long long)y.n * y.h * y.w * lanes;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -35,7 +34,6 @@ __global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y) {
 
 // one thread per 2x2 window (ceil-div grid so odd trailing rows/cols of x still get gadd*mask)
 __global__ void __launch_bounds__(NT) maxpool2_bwd_kernel(Img x, Img gy, Img gadd, Img gx) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = x.c / 4;
   const int wh = (x.h + 1) / 2, ww = (x.w + 1) / 2;
   const long long total = (long long)x.n * wh * ww * lanes;
@@ -78,7 +76,6 @@ __global__ void __launch_bounds__(NT) maxpool2_bwd_kernel(Img x, Img gy, Img gad
 }
 
 __global__ void __launch_bounds__(NT) mse_kernel(Img a, Img b, float* loss, float scale, Img grad, float gscale) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)a.n * a.h * a.w * a.c;
   float part = 0.f;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -104,7 +101,6 @@ __global__ void __launch_bounds__(NT) mse_kernel(Img a, Img b, float* loss, floa
 
 // vectorised NHWC variant of the same thing (all images sc == 1, c % 4 == 0)
 __global__ void __launch_bounds__(NT) mse_vec_kernel(Img a, Img b, float* loss, float scale, Img grad, float gscale) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = a.c / 4;
   const long long total = (long long)a.n * a.h * a.w * lanes;
   float part = 0.f;
@@ -133,7 +129,6 @@ __global__ void __launch_bounds__(NT) mse_vec_kernel(Img a, Img b, float* loss, 
 }
 
 __global__ void __launch_bounds__(NT) copy_image_kernel(Img src, Img dst, const float* __restrict__ shift, int pad) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)dst.n * dst.h * dst.w * dst.c;
   // iterate in the destination's fastest-varying order for coalesced writes
   const bool chan_fast = dst.sc == 1;
@@ -153,7 +148,6 @@ __global__ void __launch_bounds__(NT) copy_image_kernel(Img src, Img dst, const 
 }
 
 __global__ void __launch_bounds__(NT) accumulate_kernel(Img x, Img acc) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)x.n * x.h * x.w * x.c;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
     const int c = (int)(idx % x.c);
@@ -167,7 +161,6 @@ __global__ void __launch_bounds__(NT) accumulate_kernel(Img x, Img acc) {
 }
 
 __global__ void __launch_bounds__(NT) mask_add_kernel(Img a, Img b, Img mask, Img out) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const long long total = (long long)a.n * a.h * a.w * a.c;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
     const int c = (int)(idx % a.c);
@@ -184,7 +177,6 @@ __global__ void __launch_bounds__(NT) mask_add_kernel(Img a, Img b, Img mask, Im
 
 // 4 channels per thread (16 B fp32 / 8 B bf16 accesses); mixed dtypes allowed
 __global__ void __launch_bounds__(NT) mask_add_vec_kernel(Img a, Img b, Img mask, Img out) {
-  pdl_sync();   // programmatic dependent launch: see common.cuh
   const int lanes = a.c / 4;
   const long long total = (long long)a.n * a.h * a.w * lanes;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -221,7 +213,30 @@ static int blocks_for(long long total) {
 int launch_wgrad_simt(const ast_image* x, const ast_image* gout, float* dw, const int32_t* tap_off,
                       int64_t s_co, int64_t s_ci, const ast_gather_geom* geom, int64_t dw_img_stride, float scale,
                       cudaStream_t s);  // gather_simt.cu
-int gram_tc(const ast_image* x, float* g, float scale, cudaStream_t s);  // gram_tc.cu
+int gram_tc(const ast_image* x, float* g, float scale, const float* target, long long target_img_stride, double* loss,
+            float loss_scale, float* dmat, float d_scale, int* counters, cudaStream_t s);  // contract_tc.cu
+
+// strict-mode finish of ast_gram_mse after the FFMA Gram: loss += loss_scale * sum (G - S)^2 ; D = d_scale * (G - S)
+__global__ void __launch_bounds__(NT) gram_finish_kernel(const float* __restrict__ g, const float* __restrict__ target,
+                                                          long long target_img_stride, long long cc, long long total,
+                                                          double* loss, float loss_scale, float* __restrict__ dmat, float d_scale) {
+  float part = 0.f;
+  for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+    const long long img = idx / cc, r = idx - img * cc;
+    const float d = g[idx] - target[img * target_img_stride + r];
+    part = fmaf(d, d, part);
+    if (dmat) dmat[idx] = d_scale * d;
+  }
+  __shared__ float red[NT / 32];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < NT / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, (double)v * (double)loss_scale);
+  }
+}
 
 }  // namespace ast
 
@@ -235,6 +250,7 @@ extern "C" int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, void* st
   if (total == 0) return 0;
   launch_k(maxpool2_fwd_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(y));
   count_launch();
+  count_work(FAM_POOL, 0.0, img_bytes(x) + img_bytes(y));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -250,6 +266,7 @@ extern "C" int ast_maxpool2_bwd(const ast_image* x, const ast_image* y, const as
   if (total == 0) return 0;
   launch_k(maxpool2_bwd_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(gy), gadd ? to_img(gadd) : null_img(), to_img(gx));
   count_launch();
+  count_work(FAM_POOL, 0.0, img_bytes(x) + img_bytes(gy) + img_bytes(gadd) + img_bytes(gx));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -266,6 +283,7 @@ extern "C" int ast_mse(const ast_image* a, const ast_image* b, float* loss, floa
   else
     launch_k(mse_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(a), to_img(b), loss, scale, gi, gscale);
   count_launch();
+  count_work(FAM_MSE, 0.0, img_bytes(a) + img_bytes(b) + img_bytes(grad));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -279,6 +297,7 @@ extern "C" int ast_copy_image(const ast_image* src, const ast_image* dst, const 
   if (total == 0) return 0;
   launch_k(copy_image_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(src), to_img(dst), shift, pad);
   count_launch();
+  count_work(FAM_POINTWISE, 0.0, img_bytes(src) + img_bytes(dst));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -290,6 +309,7 @@ extern "C" int ast_accumulate(const ast_image* x, const ast_image* acc, void* st
   if (total == 0) return 0;
   launch_k(accumulate_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(acc));
   count_launch();
+  count_work(FAM_POINTWISE, 0.0, img_bytes(x) + 2.0 * img_bytes(acc));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -304,6 +324,7 @@ extern "C" int ast_mask_add(const ast_image* a, const ast_image* b, const ast_im
   else
     launch_k(mask_add_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(a), b ? to_img(b) : null_img(), mask ? to_img(mask) : null_img(), to_img(out));
   count_launch();
+  count_work(FAM_POINTWISE, 0.0, img_bytes(a) + img_bytes(b) + img_bytes(mask) + img_bytes(out));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -312,10 +333,31 @@ extern "C" int ast_gram(const ast_image* x, float* g, float scale, int32_t flags
   AST_CHECK_ARG(x && g, "ast_gram: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   if (x->n == 0 || x->c == 0) return 0;
-  if (flags & AST_CONV_TENSOR) return gram_tc(x, g, scale, s);
+  if (flags & AST_CONV_TENSOR) return gram_tc(x, g, scale, nullptr, 0, nullptr, 0.f, nullptr, 0.f, nullptr, s);
   cudaMemsetAsync(g, 0, sizeof(float) * (size_t)x->n * x->c * x->c, s);
   ast_gather_geom geom;
   memset(&geom, 0, sizeof(geom));
   geom.mi = x->h; geom.mj = x->w; geom.si = 1; geom.so = 1; geom.ntaps = 1;
   return launch_wgrad_simt(x, x, g, nullptr, x->c, 1, &geom, (int64_t)x->c * x->c, scale, s);
+}
+
+extern "C" int ast_gram_mse(const ast_image* x, float* g, float scale, const float* target, int64_t target_img_stride,
+                            double* loss, float loss_scale, float* d, float d_scale, int32_t* counters, int32_t flags,
+                            void* stream) {
+  AST_CHECK_ARG(x && g && target && counters, "ast_gram_mse: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x->n == 0 || x->c == 0) return 0;
+  if (flags & AST_CONV_TENSOR)
+    return gram_tc(x, g, scale, target, target_img_stride, loss, loss_scale, d, d_scale, counters, s);
+  ast_gather_geom geom;
+  memset(&geom, 0, sizeof(geom));
+  geom.mi = x->h; geom.mj = x->w; geom.si = 1; geom.so = 1; geom.ntaps = 1;
+  if (int rc = launch_wgrad_simt(x, x, g, nullptr, x->c, 1, &geom, (int64_t)x->c * x->c, scale, s)) return rc;
+  const long long cc = (long long)x->c * x->c, total = cc * x->n;
+  launch_k(gram_finish_kernel, blocks_for(total), NT, 0, s, (const float*)g, target, (long long)target_img_stride, cc, total,
+           loss, loss_scale, d, d_scale);
+  count_launch();
+  count_work(FAM_MSE, 0.0, 12.0 * total);
+  AST_CUDA_LAUNCH_CHECK();
+  return 0;
 }

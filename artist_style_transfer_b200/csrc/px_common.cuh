@@ -29,16 +29,27 @@ struct PxStep { int out_r, out_c, add_r, add_c, mask_r, mask_c; };
 template <int CW>
 __device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxStep& st, int nvr, int nvc, int ch, int lane,
                                          float b, int flags, const Img32& add, const Img32& mask, const Img32& out,
-                                         bool want_stats, float& s1, float& s2) {
+                                         bool want_stats, double& s1, double& s2) {
   constexpr int W = CW ? CW : 1;
   // idx may depend on the lane (bf16 store path): ONE shuffle / one affine evaluation per use
 #define PX_OFF(f, idx) (CW ? off.f + ((idx) / W) * st.f##_r + ((idx) % W) * st.f##_c : __shfl_sync(0xffffffffu, off.f, (idx)))
 #define PX_VALID(idx) (CW ? ((idx) / W < nvr && (idx) % W < nvc) : __shfl_sync(0xffffffffu, off.out, (idx)) >= 0)
   if (want_stats) {
+    // InstanceNorm sums of this thread's channel over the chunk: centred on the chunk mean in fp32 (no cancellation),
+    // merged into double running sums (sum x, sum x^2 = M2 + cnt * mean^2)
+    float sum = 0.f;
+    int cnt = 0;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const float x = PX_VALID(e) ? v[e] : 0.f;
-      s1 += x; s2 = fmaf(x, x, s2);
+    for (int e = 0; e < 32; ++e)
+      if (PX_VALID(e)) { sum += v[e]; ++cnt; }
+    if (cnt > 0) {
+      const float mu = sum / (float)cnt;
+      float m2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (PX_VALID(e)) { const float dlt = v[e] - mu; m2 = fmaf(dlt, dlt, m2); }
+      s1 += (double)sum;
+      s2 += (double)m2 + (double)cnt * ((double)mu * (double)mu);
     }
   }
   // the add / mask operands of all 32 pixels are loaded up front (independent loads in flight), never interleaved

@@ -173,8 +173,11 @@ struct EpiRows { long long off[8]; };
 
 // InstanceNorm statistics fused into the conv epilogue: each lane holds 32 channels of one pixel row; a reduce-scatter
 // butterfly (16+8+4+2+1 shuffles per quantity) leaves lane L with the sum over the warp's 32 rows of channel co+L,
-// which is added to stats[(img*C + co+L)*2 + {0,1}] with one fire-and-forget atomic each.
-__device__ __forceinline__ void tc_epi_stats(const float* v, bool valid, float* __restrict__ stats_row, int lane) {
+// which is added to stats[(img*C + co+L)*2 + {0,1}] (double) with one fire-and-forget atomic each.
+// The two partial sums cover only this warp's 32 pixels (fp32 is accurate enough there); the accumulation across the
+// plane runs in DOUBLE (atomicAdd on doubles, finalize in double), so E[x^2] - mean^2 does not cancel catastrophically
+// for planes with |mean| >> std (SURVEY section 7 "shifted sums or Welford-merge").
+__device__ __forceinline__ void tc_epi_stats(const float* v, bool valid, double* __restrict__ stats_row, int lane) {
   float a[32], b[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) { a[e] = valid ? v[e] : 0.f; b[e] = a[e] * a[e]; }
@@ -189,8 +192,8 @@ __device__ __forceinline__ void tc_epi_stats(const float* v, bool valid, float* 
       b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, half);
     }
   }
-  atomicAdd(stats_row + 2 * lane, a[0]);
-  atomicAdd(stats_row + 2 * lane + 1, b[0]);
+  atomicAdd(stats_row + 2 * lane, (double)a[0]);
+  atomicAdd(stats_row + 2 * lane + 1, (double)b[0]);
 }
 
 __device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
@@ -322,6 +325,16 @@ inline EncodeTiledFn get_encode() {
   }
   return fn;
 }
+
+// cuTensorMapEncodeTiled costs a few microseconds on the host and ran twice per launch; the maps only depend on
+// (pointer, shape, strides, box), which repeat from step to step (PyTorch's caching allocator hands the same blocks
+// out again), so they are cached.  The map is copied out by value (128 bytes): no pointer into the cache escapes.
+int cached_tensor_map(EncodeTiledFn encode, CUtensorMap* out, CUtensorMapDataType dt, int rank, void* ptr,
+                      const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion l2);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the request grows (per device and kernel)
+cudaError_t set_max_smem_impl(const void* kernel, size_t smem);
+template <typename K> inline cudaError_t set_max_smem(K kernel, size_t smem) { return set_max_smem_impl((const void*)kernel, smem); }
 
 // power-of-two (w x h = area) pixel box that wastes the fewest positions of an mi x mj grid
 inline void pick_tile(int mi, int mj, int area, int* tw, int* th) {

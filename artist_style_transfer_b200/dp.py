@@ -47,6 +47,34 @@ class GradBucket:
         torch._foreach_copy_(grads, [c.view_as(g) for g, c in zip(grads, chunks)])
 
 
+def allreduce_mean_flat(flat, group=None):
+    """In-place mean all-reduce of ONE flat fp32 buffer (the TransformerNet gradient arena: no pack / unpack copies)."""
+    ws, _ = world(group)
+    if ws == 1:
+        return
+    if flat.is_cuda:
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:                                       # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= ws
+
+
+def broadcast_parameters(params, group=None, src=0):
+    """Make every rank start from rank `src`'s parameters (one flat broadcast).  Data-parallel training only averages
+    gradients; without this a differing seed or a checkpoint loaded on one rank gives silently diverging replicas."""
+    ws, _ = world(group)
+    if ws == 1:
+        return
+    with torch.no_grad():
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        dist.broadcast(flat, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+
 def allreduce_sums(tensors, group=None):
     """In-place SUM all-reduce of a list of tensors (smartaverage feature / Gram sums and the painting count)."""
     ws, _ = world(group)

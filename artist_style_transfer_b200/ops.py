@@ -116,18 +116,21 @@ def row_im2col(src, out, kw, sign, px, py, reflect, shift=None, round_tf32=False
         return out
 
 
-def unfold_rows(src, out, kh, sign, py=0):
-    """out[n,y,x,d*C+j] = src[n, y+sign*d-py, x, j] (0 outside); see include/ast.h ast_unfold_rows."""
-    with _timed(_pw("unfold_rows", out)):
-        si, oi = image(src), image(out)
-        check(_lib.load().ast_unfold_rows(ref(si), ref(oi), kh, sign, py, stream_ptr()), "ast_unfold_rows")
-        return out
+def _flip(img):
+    """Channel-reversed alias of an ast_image (BGR <-> RGB, inference.py:116 `[[2, 1, 0]]`): same pixels, channel c of the
+    view is channel C-1-c of the tensor - expressed with a negative channel stride, no kernel support needed."""
+    esz = {_lib.AST_F32: 4, _lib.AST_BF16: 2, _lib.AST_U8: 1}[img.dtype]
+    img.ptr = img.ptr + (img.c - 1) * img.sc * esz
+    img.sc = -img.sc
+    return img
 
 
-def fold_rows(part, out, kw, bias=None, relu=False):
+def fold_rows(part, out, kw, bias=None, relu=False, flip_channels=False):
     """out[n,y,x,c] = bias[c] + sum_d part[n,y,x+d,d*C+c]; see include/ast.h ast_fold_rows."""
     with _timed(_pw("fold_rows", part)):
         pi, oi = image(part), image(out)
+        if flip_channels:
+            oi = _flip(oi)
         check(_lib.load().ast_fold_rows(ref(pi), ref(oi), ptr(bias), kw, int(relu), stream_ptr()), "ast_fold_rows")
         return out
 
@@ -219,7 +222,8 @@ def _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=No
     return out
 
 
-def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None, s12=None):
+def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None, s12=None, zeroed=False,
+                       arrive=None):
     """Returns s12 of shape (2, N*C): dbeta = s12[0].view(N,C).sum(0), dgamma = s12[1].view(N,C).sum(0); fills dx
     (and gtotal).  `s12` may be a caller-provided (2, N*C) fp32 view (e.g. a slice of one buffer shared by layers)."""
     n, _, _, c = x.shape
@@ -228,11 +232,9 @@ def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, 
     s1, s2 = s12[0], s12[1]                                                  # over the batch with one kernel
     lib = _lib.load()
     xi, gp, ge, dxi, gt = image(x), image(gpad), image(gextra), image(dx), image(gtotal)
-    check(lib.ast_instnorm_bwd_stats(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge),
-                                     int(relu), ptr(s1), ptr(s2), stream_ptr()), "ast_instnorm_bwd_stats")
-    check(lib.ast_instnorm_bwd_apply(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge),
-                                     int(relu), ptr(s1), ptr(s2), ref(dxi), ref(gt), stream_ptr()),
-          "ast_instnorm_bwd_apply")
+    flags = int(relu) | (_lib.IN_SUMS_ZEROED if zeroed else 0)
+    check(lib.ast_instnorm_bwd(ref(xi), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ref(gp), pad, ref(ge), flags, ptr(s1),
+                               ptr(s2), ptr(arrive) if zeroed else None, ref(dxi), ref(gt), stream_ptr()), "ast_instnorm_bwd")
     return s12
 
 
@@ -267,8 +269,10 @@ def _mse_impl(a, b, loss, scale, grad=None, gscale=0.0):
     return loss
 
 
-def _copy_image_impl(src, dst, shift=None, pad=0):
+def _copy_image_impl(src, dst, shift=None, pad=0, flip_channels=False):
     si, di = image(src), image(dst)
+    if flip_channels:
+        di = _flip(di)
     check(_lib.load().ast_copy_image(ref(si), ref(di), ptr(shift), pad, stream_ptr()), "ast_copy_image")
     return dst
 
@@ -319,9 +323,13 @@ def instnorm_apply(x, mean, rstd, gamma, beta, out, pad, relu, residual=None):
         return _instnorm_apply_impl(x, mean, rstd, gamma, beta, out, pad, relu, residual=residual)
 
 
-def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None, s12=None):
+def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=None, s12=None, zeroed=False, arrive=None):
+    """zeroed=True: `s12` (and `arrive`, n int32 barrier counters) were zero-filled by the caller: one fill for all layers
+    instead of two memsets per call, and the single-kernel backward (statistics + apply with the second read served from
+    L2) becomes available."""
     with _timed("instnorm" + (f"|bwd{tuple(x.shape)}" if PROFILE_DETAIL and _prof is not None else "")):
-        return _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=gtotal, s12=s12)
+        return _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal=gtotal, s12=s12,
+                                  zeroed=zeroed, arrive=arrive)
 
 
 def maxpool2_fwd(x):
@@ -339,14 +347,50 @@ def gram(x, scale, tensor=False):
         return _gram_impl(x, scale, tensor=tensor)
 
 
+def gram_mse(x, target, g, counters, loss=None, loss_scale=0.0, d=None, d_scale=0.0, tensor=False):
+    """Fused style term of one tap (include/ast.h ast_gram_mse): fills g = Gram(x) * 1/(CHW) (g and counters must be
+    zero on entry), loss (an fp64 accumulator) += loss_scale * sum (g - target)^2, d = d_scale * (g - target).
+    target: [C,C] (shared by the batch) or [N,C,C]."""
+    if loss is not None and loss.dtype != torch.float64:
+        raise RuntimeError("gram_mse: the loss accumulator must be float64")
+    n, h, w, c = x.shape
+    if n == 0 or c == 0:
+        return g
+    tstride = 0 if target.dim() == 2 or target.stride(0) == 0 else target.stride(0)
+    if target.stride(-1) != 1 or target.stride(-2) != c:
+        raise RuntimeError("gram_mse: target rows must be dense")
+    with _timed("gram"):
+        xi = image(x)
+        check(_lib.load().ast_gram_mse(ref(xi), ptr(g), 1.0 / (c * h * w), ptr(target), tstride, ptr(loss), loss_scale,
+                                       ptr(d), d_scale, ptr(counters), CONV_TENSOR if tensor else 0, stream_ptr()),
+              "ast_gram_mse")
+    return g
+
+
+def channel_sum(x, out):
+    """out[c] += sum_{n,h,w} x[n,h,w,c] (include/ast.h ast_channel_sum)."""
+    with _timed(_pw("channel_sum", x)):
+        xi = image(x)
+        check(_lib.load().ast_channel_sum(ref(xi), ptr(out), stream_ptr()), "ast_channel_sum")
+    return out
+
+
+def batch_reduce(src, dst, descs_dev, n_desc, max_cols):
+    """dst[dst_off + c] = sum_r src[src_off + r*row_stride + c] for a device table of descriptors (ast_batch_reduce)."""
+    with _timed("pointwise"):
+        check(_lib.load().ast_batch_reduce(ptr(src), ptr(dst), ptr(descs_dev), n_desc, max_cols, stream_ptr()),
+              "ast_batch_reduce")
+    return dst
+
+
 def mse(a, b, loss, scale, grad=None, gscale=0.0):
     with _timed(_pw("mse", a)):
         return _mse_impl(a, b, loss, scale, grad=grad, gscale=gscale)
 
 
-def copy_image(src, dst, shift=None, pad=0):
+def copy_image(src, dst, shift=None, pad=0, flip_channels=False):
     with _timed(_pw("copy_image", dst)):
-        return _copy_image_impl(src, dst, shift=shift, pad=pad)
+        return _copy_image_impl(src, dst, shift=shift, pad=pad, flip_channels=flip_channels)
 
 
 def accumulate(x, acc):

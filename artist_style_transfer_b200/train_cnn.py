@@ -6,8 +6,9 @@ Drop-in pieces (same names / signatures / return types as the reference):
 and the loop body / style-setup blocks restated as functions:
   style_grams_single(...)                             train_cnn.py:184-190 ('random'), :199-204 ('average')
   style_grams_smartaverage(...)                       train_cnn.py:224-244
+  StyleGramBank                                       train_cnn.py:206-223,316-320 ('cycle': per-painting Grams on device)
   perceptual_step(...)                                train_cnn.py:295-333
-  PerceptualTrainer                                   train_cnn.py:247-248,295-334 (+ data-parallel allreduce)
+  PerceptualTrainer                                   train_cnn.py:247-248,295-334,375 (+ data-parallel allreduce)
 All arithmetic runs in libast_b200.so; `nn.MSELoss` on the returned tensors still works and differentiates.
 """
 import math
@@ -44,18 +45,6 @@ def _vgg_layout():
     return layers
 
 
-def _conv11_fold():
-    return os.environ.get("AST_CONV11_FOLD", "1") == "1"
-
-
-def _fuse_pool():
-    return os.environ.get("AST_FUSE_POOL", "1") == "1"
-
-
-def _vgg_bwd_bf16():
-    return os.environ.get("AST_VGG_BWD", "bf16") != "tf32"
-
-
 class _VGGFunction(torch.autograd.Function):
     """conv3x3(pad 1)+ReLU / maxpool chain up to `upto`, returning the tapped activations (NCHW views)."""
 
@@ -64,7 +53,9 @@ class _VGGFunction(torch.autograd.Function):
         if not x.is_cuda:
             raise RuntimeError("VGG16 kernels run on CUDA only (no CPU fallback)")
         tensor = module._mode() == "fast" and _lib.has_tc_conv()
-        x32 = x.detach().to(torch.float32)
+        x32 = x.detach()
+        if x32.dtype not in (torch.float32, torch.uint8):      # uint8 images are widened inside conv1_1's loader
+            x32 = x32.to(torch.float32)
         n, _, h, w = x32.shape
         dev = x32.device
         cur = x32.permute(0, 2, 3, 1)            # NCHW tensor described as an (N,H,W,C) view; conv1_1 reads it directly
@@ -86,6 +77,10 @@ class _VGGFunction(torch.autograd.Function):
                 plan.append((idx, "conv", cur, out))
                 cur = out
             elif kind == "conv":
+                if cur.dtype == torch.uint8:        # strict mode: the FFMA conv reads fp32
+                    f32 = torch.empty(cur.shape, dtype=torch.float32, device=dev)
+                    ops.copy_image(cur, f32)
+                    cur = f32
                 launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
                 out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
                 wp, bias = packed[idx]
@@ -93,7 +88,7 @@ class _VGGFunction(torch.autograd.Function):
                 # conv1_2 -> ReLU -> MaxPool2d: the weight-stationary kernel also writes the pooled tensor (saves the pool
                 # kernel's 537 MB read at B=32); when nothing needs the full-resolution relu1_2 (no-grad content branch
                 # asking only for its last tap) it is not even stored
-                fuse_pool = (use_tc and _fuse_pool() and cin == 64 and cout == 64 and idx + 2 <= upto
+                fuse_pool = (use_tc and cin == 64 and cout == 64 and idx + 2 <= upto
                              and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0)
                 if fuse_pool:
                     pooled_next = torch.empty((n, cur.shape[1] // 2, cur.shape[2] // 2, cout), dtype=torch.float32, device=dev)
@@ -137,9 +132,8 @@ class _VGGFunction(torch.autograd.Function):
                     g = gc
                 tapg[idx] = g
         # fast mode: the gradient chain through the frozen VGG runs in bf16 (fp32 accumulation), like the transform
-        # net's backward; the forward taps, Grams and losses keep TF32 (parity is stated on those).  AST_VGG_BWD=tf32
-        # restores a TF32 backward.
-        bf16_bwd = tensor and _vgg_bwd_bf16()
+        # net's backward; the forward taps, Grams and losses keep TF32 (parity is stated on those).
+        bf16_bwd = tensor
         gdt = torch.bfloat16 if bf16_bwd else torch.float32
         packed = module._packed_dgrad(tensor, bf16_bwd)
         g = None            # gradient w.r.t. the OUTPUT of the current plan entry (already ReLU-masked for convs)
@@ -164,7 +158,7 @@ class _VGGFunction(torch.autograd.Function):
             # g is d/d(relu out) masked == d/d(conv out).  dgrad to the conv input:
             if idx == 0:
                 gx = torch.empty((out.shape[0], 3, out.shape[1], out.shape[2]), dtype=torch.float32, device=g.device)
-                if tensor and _conv11_fold() and g.dtype == torch.bfloat16:
+                if tensor and g.dtype == torch.bfloat16:
                     # d(image) of conv1_1 as 3 VERTICAL taps whose 9 (of 32) output channels are the partial sums of the
                     # 3 horizontal taps x 3 image channels, finished by ast_fold_rows - 12 instead of 36 N=32 MMAs per
                     # 128 pixels and no strided 3-channel epilogue:
@@ -218,7 +212,11 @@ class VGG16(nn.Module, _cnn._Precision):
                 m = nn.MaxPool2d(2, 2)
             mods.append(m)
         self.features = nn.Sequential(*mods)
-        if vgg_path is not None and os.path.exists(vgg_path):
+        if vgg_path is not None:
+            # like the reference (train_cnn.py:55) a missing weight file is an error, not a silently random VGG;
+            # vgg_path=None is the explicit way to ask for random-init weights (tests, bench)
+            if not os.path.exists(vgg_path):
+                raise FileNotFoundError(f"VGG16 weights not found at {vgg_path!r} (pass vgg_path=None for random-init weights)")
             self.load_state_dict(torch.load(vgg_path, map_location="cpu"), strict=False)   # train_cnn.py:55
         self.just_content = just_content
         for p in self.features.parameters():    # train_cnn.py:60-61
@@ -352,7 +350,8 @@ def style_grams_single(vgg, style_tensor, batch_size):
     with torch.no_grad():
         feats = vgg(style_tensor.float().unsqueeze(0) if style_tensor.dim() == 3 else style_tensor.float(),
                     shift=neg_mean(style_tensor.device))
-        return {k: gram(v).expand(batch_size, -1, -1).contiguous() for k, v in feats.items()}
+        # B identical rows in the reference: a stride-0 expand (no copies); the fused loss kernel reads one C x C target
+        return {k: gram(v).expand(batch_size, -1, -1) for k, v in feats.items()}
 
 
 def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group=None):
@@ -390,106 +389,166 @@ def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group
                 g = gram(v.permute(0, 3, 1, 2)) / (length * length)
             else:
                 g = v / length
-            out[k] = g.expand(batch_size, -1, -1).contiguous()
+            out[k] = g.expand(batch_size, -1, -1)
         return out
 
 
 class _MSEFunction(torch.autograd.Function):
-    """weight * mean((a-b)^2) with the gradient w.r.t. `a` produced in the same pass (nn.MSELoss, train_cnn.py:249,307).
-
-    unit_grad=True promises that the upstream gradient of this loss is exactly 1 (perceptual_step calls
-    total.backward() itself with total = content + style): backward then returns the stored gradient as is instead of
-    multiplying a feature-map-sized tensor by a device scalar (0.19 ms per step at B=32 for the relu2_2 content term).
-    """
+    """weight * mean((a-b)^2) with the gradient w.r.t. `a` produced in the same pass (nn.MSELoss, train_cnn.py:249,307)."""
 
     @staticmethod
-    def forward(ctx, a, b, weight=1.0, unit_grad=False):
+    def forward(ctx, a, b, weight=1.0):
         av = a.detach().permute(0, 2, 3, 1)
         bv = b.detach().permute(0, 2, 3, 1)
         loss = torch.zeros(1, dtype=torch.float32, device=a.device)
         grad = torch.empty(av.shape, dtype=torch.float32, device=a.device) if a.requires_grad else None
         numel = a.numel()
         ops.mse(av, bv, loss, float(weight) / numel, grad, 2.0 * float(weight) / numel)
-        ctx.grad, ctx.unit_grad = grad, unit_grad
+        ctx.grad = grad
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         if ctx.grad is None:
-            return None, None, None, None
-        ga = ctx.grad if ctx.unit_grad else ctx.grad * g
-        return ga.permute(0, 3, 1, 2), None, None, None
-
-
-class _ContentGramFunction(torch.autograd.Function):
-    """relu2_2 feeds BOTH the content loss (train_cnn.py:307) and a style Gram (:321-325).  As two autograd nodes their
-    gradients meet in an autograd add over two feature-map-sized tensors (0.12 ms per step at B=32); here one node
-    returns (weighted content loss, Gram) and its backward adds the stored content gradient inside the epilogue of the
-    Gram-backward convolution (`add` operand of ast_conv_gather).  unit_grad as in _MSEFunction."""
-
-    @staticmethod
-    def forward(ctx, f, content_feat, weight, fast, unit_grad):
-        b, c, h, w = f.shape
-        fv = f.detach()
-        if fv.dtype not in (torch.float32, torch.bfloat16):
-            fv = fv.float()
-        xv = fv.permute(0, 2, 3, 1)
-        loss = torch.zeros(1, dtype=torch.float32, device=f.device)
-        grad = torch.empty(xv.shape, dtype=torch.float32, device=f.device)
-        numel = f.numel()
-        ops.mse(xv, content_feat.detach().permute(0, 2, 3, 1), loss, float(weight) / numel, grad, 2.0 * float(weight) / numel)
-        g = ops.gram(xv, 1.0 / (c * h * w), tensor=fast and b > 0 and ops.tc_contract_eligible(xv, xv))
-        ctx.save_for_backward(fv)
-        ctx.grad, ctx.fast, ctx.unit_grad = grad, fast, unit_grad
-        return loss[0], g
-
-    @staticmethod
-    def backward(ctx, g_loss, dg):
-        (fv,) = ctx.saved_tensors
-        b, c, h, w = fv.shape
-        cgrad = ctx.grad if ctx.unit_grad else ctx.grad * g_loss
-        x = fv.permute(0, 2, 3, 1)
-        if dg is None:
-            return cgrad.permute(0, 3, 1, 2), None, None, None, None
-        d = ((dg + dg.transpose(1, 2)) * (1.0 / (c * h * w))).to(fv.dtype).contiguous()
-        out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
-        fast = ctx.fast
-        ops.conv_gather(x, d.view(b, 1, c, c), cg.conv_fwd(1, 1, 0, h, w), out, add=cgrad, w_img_stride=c * c,
-                        tensor=fast and x.is_contiguous() and ops.tc_eligible(x, c), round_tf32=fast)
-        return out.permute(0, 3, 1, 2), None, None, None, None
+            return None, None, None
+        return (ctx.grad * g).permute(0, 3, 1, 2), None, None
 
 
 def mse_loss(a, b, weight=1.0):
     """Fused (weighted) MSE forward+gradient for two [B,C,H,W] tensors (b is treated as a constant)."""
-    return _MSEFunction.apply(a, b, weight, False)
+    return _MSEFunction.apply(a, b, weight)
+
+
+class _PerceptualLossFunction(torch.autograd.Function):
+    """The whole loss side of train_cnn.py:307-329 as ONE autograd node over the four VGG taps of the generated batch.
+
+    Per tap, ONE kernel (ast_gram_mse) computes the upper triangle of the Gram on the tensor cores and - in the finishing
+    CTA of every block - the style-MSE contribution and D = 4 w_s (G - S) / (B C^2 CHW), the symmetric per-image 1x1
+    weights of the Gram backward dF = D F.  The content term on relu2_2 (train_cnn.py:307-308) is one
+    MSE pass producing loss and gradient; the backward adds that gradient inside the epilogue of relu2_2's Gram-backward
+    convolution.  unit_grad=True promises that the upstream gradients of both losses are exactly 1 (perceptual_step calls
+    total.backward() itself with total = content + style): nothing is rescaled.
+    Returns (content_loss, style_loss, grams...) - the Grams are exposed for inspection / tests (no gradient).
+    """
+
+    @staticmethod
+    def forward(ctx, content_feat, content_weight, style_weight, fast, unit_grad, n_taps, *rest):
+        feats, targets = rest[:n_taps], rest[n_taps:2 * n_taps]
+        names = rest[2 * n_taps]
+        dev = feats[0].device
+        b = feats[0].shape[0]
+        sizes = [b * f.shape[1] * f.shape[1] for f in feats]
+        cnt = b * _lib.GRAM_COUNTERS_PER_IMAGE
+        # one zero fill: [style loss (one fp64), content loss, pad | Gram 0..n | ticket counters 0..n (int32 views)]
+        zeros = torch.zeros(4 + sum(sizes) + n_taps * cnt, dtype=torch.float32, device=dev)
+        style_acc, content_acc = zeros[:2].view(torch.float64), zeros[2:3]
+        off = 4
+        grams, dmats, saved = [], [], []
+        need_grad = any(ctx.needs_input_grad[6:6 + n_taps])
+        content_grad = None
+        for i, f in enumerate(feats):
+            _, c, h, w = f.shape
+            fv = f.detach()
+            if fv.dtype not in (torch.float32, torch.bfloat16):
+                fv = fv.float()
+            xv = fv.permute(0, 2, 3, 1)
+            g = zeros[off:off + sizes[i]].view(b, c, c)
+            off += sizes[i]
+            counters = zeros[4 + sum(sizes) + i * cnt:4 + sum(sizes) + (i + 1) * cnt].view(torch.int32)
+            d = torch.empty((b, c, c), dtype=torch.float32, device=dev) if need_grad else None
+            tgt = targets[i].detach()
+            if tgt.dtype != torch.float32:
+                tgt = tgt.float()
+            ops.gram_mse(xv, tgt, g, counters, loss=style_acc, loss_scale=float(style_weight) / (b * c * c), d=d,
+                         d_scale=4.0 * float(style_weight) / (float(b) * c * c * c * h * w),
+                         tensor=fast and b > 0 and ops.tc_contract_eligible(xv, xv))
+            if names[i] == "relu2_2" and content_feat is not None:                       # train_cnn.py:307-308
+                numel = f.numel()
+                content_grad = torch.empty(xv.shape, dtype=torch.float32, device=dev) if need_grad else None
+                ops.mse(xv, content_feat.detach().permute(0, 2, 3, 1), content_acc, float(content_weight) / numel,
+                        content_grad, 2.0 * float(content_weight) / numel)
+            grams.append(g)
+            dmats.append(d)
+            saved.append(fv)
+        ctx.feats, ctx.dmats, ctx.content_grad, ctx.names = saved, dmats, content_grad, names
+        ctx.fast, ctx.unit_grad, ctx.n_taps = fast, unit_grad, n_taps
+        ctx.mark_non_differentiable(*grams)
+        return (content_acc[0], style_acc[0].to(torch.float32), *grams)
+
+    @staticmethod
+    def backward(ctx, g_content, g_style, *_):
+        outs = []
+        for i, fv in enumerate(ctx.feats):
+            b, c, h, w = fv.shape
+            x = fv.permute(0, 2, 3, 1)
+            d = ctx.dmats[i]
+            cgrad = ctx.content_grad if ctx.names[i] == "relu2_2" else None
+            if not ctx.unit_grad:
+                d = d * g_style
+                cgrad = None if cgrad is None else cgrad * g_content
+            if d.dtype != fv.dtype:
+                d = d.to(fv.dtype)
+            out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
+            # dF = D F: a 1x1 gather-conv with per-image C x C weights (+ the content gradient in its epilogue)
+            ops.conv_gather(x, d.view(b, 1, c, c), cg.conv_fwd(1, 1, 0, h, w), out, add=cgrad, w_img_stride=c * c,
+                            tensor=ctx.fast and x.is_contiguous() and ops.tc_eligible(x, c), round_tf32=ctx.fast)
+            outs.append(out.permute(0, 3, 1, 2))
+        ctx.feats = ctx.dmats = ctx.content_grad = None
+        return (None, None, None, None, None, None, *outs, *([None] * (ctx.n_taps + 1)))
+
+
+def perceptual_losses(gen_feats, content_feat, style_gram, content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT,
+                      fast=None, unit_grad=False):
+    """(content_loss, style_loss, {tap: Gram}) of train_cnn.py:307-325 for the generated batch's VGG taps."""
+    names = tuple(gen_feats.keys())
+    feats = [gen_feats[k] for k in names]
+    targets = [style_gram[k] for k in names]
+    if fast is None:
+        fast = _cnn.get_default_precision() == "fast"
+    out = _PerceptualLossFunction.apply(content_feat, content_weight, style_weight, bool(fast), bool(unit_grad), len(names),
+                                        *feats, *targets, names)
+    return out[0], out[1], dict(zip(names, out[2:]))
 
 
 def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CONTENT_WEIGHT,
                     style_weight=STYLE_WEIGHT, backward=True):
-    """The loop body of train_cnn.py:295-333 (methods 'random'/'average'/'smartaverage'), without the optimizer.
+    """The loop body of train_cnn.py:295-333 (methods 'random'/'average'/'cycle'/'smartaverage'), without the optimizer.
 
-    Returns (content_loss, style_loss, total_loss) as 0-d device tensors (no host sync).
-    Differences from the reference that do not change results: the mean shift is fused into conv1_1's loader,
-    and the content branch stops at relu2_2 (the reference computes relu3_3/relu4_3 and discards them).
+    content_batch: [B,3,H,W] BGR 0-255, fp32 or uint8.  Returns (content_loss, style_loss, total_loss) as 0-d device
+    tensors (no host sync).  Differences from the reference that do not change results: the mean shift is fused into
+    conv1_1's loader, and the content branch stops at relu2_2 (the reference computes relu3_3/relu4_3 and discards them).
     """
     shift = neg_mean(content_batch.device)
     generated = transfer(content_batch)                                        # :299
     with torch.no_grad():
         content_feat = vgg(content_batch, shift=shift, upto="relu2_2", only_last=True)["relu2_2"]   # :300
     gen_feats = vgg(generated, shift=shift)                                    # :301
-    # :307-308 and the relu2_2 Gram of :321-325 as ONE autograd node (the weight is folded into the kernel; with
-    # backward=True the upstream gradient of the content term is exactly 1)
-    content_loss, gram22 = _ContentGramFunction.apply(gen_feats["relu2_2"], content_feat, content_weight,
-                                                      vgg._mode() == "fast", bool(backward))
-    style_loss = 0
-    for key, value in gen_feats.items():                                       # :321-325
-        g = gram22 if key == "relu2_2" else gram(value, precision=vgg._mode())
-        style_loss = style_loss + mse_loss(g.unsqueeze(1), style_gram[key].unsqueeze(1))
-    style_loss = style_loss * style_weight
+    content_loss, style_loss, _ = perceptual_losses(gen_feats, content_feat, style_gram, content_weight, style_weight,
+                                                    fast=vgg._mode() == "fast", unit_grad=bool(backward))   # :307-325
     total = content_loss + style_loss                                          # :329
     if backward:
         total.backward()                                                       # :333
     return content_loss.detach(), style_loss.detach(), total.detach()
+
+
+class StyleGramBank:
+    """'cycle' style method (train_cnn.py:206-223, 316-320): the Grams of every painting of the artist stay resident on
+    the device ([P,C,C] per tap, 1.4 MB per painting) instead of being shuttled to the CPU and back every step
+    (`.cpu()` at :218, `.to(device)` at :323); step t uses painting t % P.  Each painting's Gram is shared by the batch
+    (the reference stores B identical rows), so targets are [C,C] views."""
+
+    def __init__(self, vgg, paintings):
+        per = [style_grams_single(vgg, p, 1) for p in paintings]
+        self.keys = list(per[0].keys())
+        self.bank = {k: torch.cat([g[k] for g in per], dim=0).contiguous() for k in self.keys}    # [P, C, C]
+        self.length = len(per)
+
+    def __len__(self):
+        return self.length
+
+    def target(self, index):
+        i = index % self.length                                               # :317
+        return {k: v[i] for k, v in self.bank.items()}
 
 
 class _Prefetched:
@@ -503,36 +562,61 @@ class _Prefetched:
 class PerceptualTrainer:
     """Optimizer side of train() (train_cnn.py:247-248,295,334,375) plus data-parallel gradient averaging.
 
-    One process per GPU; when torch.distributed is initialised the TransformerNet gradients are flattened
-    into one 1,712,771-float bucket and averaged with a single NCCL all-reduce per step.
+    optimizer="fused" (default): the TransformerNet gradients land in one flat arena (arena.py) that is all-reduced as it
+    is (one NCCL call) and consumed by ONE Adam(L2) kernel which also refreshes the packed bf16 weights of
+    the next step; lr and the step count live in device memory, so StepLR (end_epoch) also acts on CUDA-graph replays.
+    optimizer="torch": torch.optim.Adam + StepLR on the parameters' .grad (the reference's objects, :247-248).
+    One process per GPU; with torch.distributed initialised, rank 0's parameters are broadcast at construction so that
+    replicas start identical, and every step averages the gradients.
     """
 
     def __init__(self, transfer, vgg, style_gram, lr=LR, weight_decay=1e-4, num_epochs=200, num_steps=2,
-                 content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT, group=None, cuda_graph=False):
+                 content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT, group=None, cuda_graph=False,
+                 optimizer="fused"):
         self.transfer, self.vgg, self.style_gram = transfer, vgg, style_gram
         self.content_weight, self.style_weight = content_weight, style_weight
         self.params = [p for p in transfer.parameters()]
         on_cuda = self.params[0].is_cuda
-        # fused=True: torch's single-kernel Adam (same update rule, L2 weight decay) instead of ~15 foreach kernels per step
-        self.optimizer = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay, fused=bool(on_cuda),
-                                          capturable=bool(cuda_graph and on_cuda))                 # :247
-        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=max(1, num_epochs // num_steps),
-                                                         gamma=0.5)                                # :248
         self.group = group
-        self._flat = None
-        # cuda_graph=True: after 3 eager warm-up steps the whole step (fwd, bwd, all-reduce, Adam: ~350 launches) is
-        # captured once per input shape and replayed, removing host launch overhead and inter-kernel gaps.
+        self.world, self.rank = dp.world(group)
+        if self.world > 1:
+            dp.broadcast_parameters(self.params, group)          # replicas must start identical (one flat call)
+        self.base_lr, self.lr, self.gamma, self.epoch = float(lr), float(lr), 0.5, 0
+        self.step_size = max(1, num_epochs // num_steps)                                           # :248
         self.cuda_graph = bool(cuda_graph and on_cuda)
+        self.fused = optimizer == "fused" and on_cuda
+        if optimizer not in ("fused", "torch"):
+            raise ValueError("optimizer must be 'fused' or 'torch'")
+        self._flat = None
+        if self.fused:
+            self.arena = transfer._arena_for(self.params[0].device)
+            self.arena.enable_optimizer(lr, weight_decay=weight_decay)
+            self.gbuf = self.arena.new_grad_buffer()
+            self.arena.grad_sink = self.gbuf
+            for p, g in zip(self.arena.params(), self.arena.grad_views(self.gbuf)):
+                p.grad = g                                       # views of the arena (strided for conv weights)
+            self.optimizer = self.scheduler = None
+        else:
+            # lr as a device tensor under graph capture: torch's fused Adam then reads it at replay time, so StepLR's
+            # in-place update is seen by the captured graph (a Python float would be frozen into it)
+            lr_arg = torch.tensor(lr, dtype=torch.float32, device=self.params[0].device) if self.cuda_graph else lr
+            self.optimizer = torch.optim.Adam(self.params, lr=lr_arg, weight_decay=weight_decay, fused=bool(on_cuda),
+                                              capturable=self.cuda_graph)                         # :247
+            self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=self.step_size, gamma=0.5)
+        # cuda_graph=True: after 3 eager warm-up steps the whole step (fwd, bwd, all-reduce, Adam: ~300 launches) is
+        # captured once per input shape and replayed, removing host launch overhead and inter-kernel gaps.
         self._graph, self._static_in, self._static_losses, self._eager_steps = None, None, None, 0
+        self._static_style = None
         self._copy_stream = None
 
     # ---- host -> device input pipeline --------------------------------------------------------------------------
     def prefetch(self, host_batch):
         """Start copying a (pinned) host batch to the device on a side stream and return a handle that `step()` accepts.
 
-        Called for batch i+1 before `step(batch i)` is waited on, the PCIe copy (25 MB at B=32, 256^2) overlaps the
-        compute of step i instead of preceding step i+1.  Two device staging buffers alternate; a buffer is only
-        overwritten after the step that consumed it has copied it into the step's input.
+        host_batch: [B,3,H,W] fp32 or uint8 (uint8 moves 4x fewer bytes over PCIe; values are widened in the first
+        layers' loaders).  Called for batch i+1 before `step(batch i)` is waited on, the copy overlaps the compute of
+        step i.  Two device staging buffers alternate; a buffer is only overwritten after the step that consumed it has
+        copied it into the step's input.
         """
         dev = self.params[0].device
         if self._copy_stream is None:
@@ -540,14 +624,20 @@ class PerceptualTrainer:
             self._stage, self._stage_free, self._stage_i = [None, None], [None, None], 0
         i = self._stage_i
         self._stage_i ^= 1
-        if self._stage[i] is None or self._stage[i].shape != host_batch.shape:
-            self._stage[i] = torch.empty(host_batch.shape, dtype=torch.float32, device=dev)
-        with torch.cuda.stream(self._copy_stream):
+        cs = self._copy_stream
+        if self._stage[i] is None or self._stage[i].shape != host_batch.shape or self._stage[i].dtype != host_batch.dtype:
+            # allocate ON the copy stream: the caching allocator may hand out a block whose previous user still has
+            # kernels queued on the compute stream, so order the copy stream behind it first
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cs):
+                self._stage[i] = torch.empty(host_batch.shape, dtype=host_batch.dtype, device=dev)
+            self._stage_free[i] = None
+        with torch.cuda.stream(cs):
             if self._stage_free[i] is not None:
-                self._copy_stream.wait_event(self._stage_free[i])
+                cs.wait_event(self._stage_free[i])
             self._stage[i].copy_(host_batch, non_blocking=True)
             ready = torch.cuda.Event()
-            ready.record(self._copy_stream)
+            ready.record(cs)
         return _Prefetched(self._stage[i], ready, i)
 
     def _consume(self, batch):
@@ -564,36 +654,62 @@ class PerceptualTrainer:
             self._stage_free[slot] = ev
 
     def _allreduce_grads(self):
-        if self._flat is None:
-            self._flat = dp.GradBucket()
-        self._flat.allreduce_mean(self.params, self.group)
+        if self.world == 1:
+            return
+        if self.fused:
+            dp.allreduce_mean_flat(self.gbuf, self.group)         # the arena IS the bucket
+        else:
+            if self._flat is None:
+                self._flat = dp.GradBucket()
+            self._flat.allreduce_mean(self.params, self.group)
 
-    def _eager_step(self, content_batch):
-        self.optimizer.zero_grad(set_to_none=True)                                                 # :295
-        losses = perceptual_step(self.transfer, self.vgg, content_batch, self.style_gram,
+    def _eager_step(self, content_batch, style_gram):
+        if self.fused:
+            self.gbuf.zero_()                                                                      # :295
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+        losses = perceptual_step(self.transfer, self.vgg, content_batch, style_gram,
                                  self.content_weight, self.style_weight, backward=True)
         self._allreduce_grads()
-        self.optimizer.step()                                                                      # :334
+        if self.fused:
+            self.arena.adam_step(self.gbuf)                                                        # :334
+        else:
+            self.optimizer.step()
         return losses
 
-    def _capture(self, content_batch):
+    def _capture(self, content_batch, style_gram):
         self._static_in = content_batch.clone()
+        # static copies of the style targets: 'cycle' switches the target per step by copying 1.4 MB into them
+        self._static_style = {k: (v[0:1].clone().expand_as(v) if v.dim() == 3 and v.stride(0) == 0 else v.clone())
+                              for k, v in style_gram.items()}
         self._graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if not self.fused:
+            self.optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(self._graph):
-            self._static_losses = self._eager_step(self._static_in)
+            self._static_losses = self._eager_step(self._static_in, self._static_style)
 
-    def step(self, content_batch):
-        """One optimisation step on `content_batch`: a device tensor, a host tensor, or a handle from `prefetch()`."""
+    def step(self, content_batch, style_gram=None):
+        """One optimisation step on `content_batch`: a device tensor, a host tensor, or a handle from `prefetch()`.
+        style_gram: optional per-step style targets ('cycle': `bank.target(t)`); default: the trainer's own."""
         content_batch, slot = self._consume(content_batch)
+        sg = self.style_gram if style_gram is None else style_gram
         if not self.cuda_graph:
             if not content_batch.is_cuda:
                 content_batch = content_batch.to(self.params[0].device, non_blocking=True)
-            losses = self._eager_step(content_batch)
+            losses = self._eager_step(content_batch, sg)
             self._release(slot)
             return losses
-        if self._graph is not None and self._static_in.shape == content_batch.shape:
+        if (self._graph is not None and self._static_in.shape == content_batch.shape
+                and self._static_in.dtype == content_batch.dtype
+                and all(self._static_style[k].shape == sg[k].shape for k in sg)):
             self._static_in.copy_(content_batch, non_blocking=True)
+            if style_gram is not None:
+                for k, v in sg.items():
+                    dst = self._static_style[k]
+                    if dst.dim() == 3 and dst.stride(0) == 0:          # one shared target behind a stride-0 expand
+                        dst[0].copy_(v[0] if v.dim() == 3 else v, non_blocking=True)
+                    else:
+                        dst.copy_(v, non_blocking=True)
             self._release(slot)
             self._graph.replay()
             return self._static_losses
@@ -601,13 +717,37 @@ class PerceptualTrainer:
             content_batch = content_batch.to(self.params[0].device, non_blocking=True)
         if self._eager_steps < 3:                       # warm up caches (packed weights, tap tables, allocator)
             self._eager_steps += 1
-            losses = self._eager_step(content_batch)
+            losses = self._eager_step(content_batch, sg)
             self._release(slot)
             return losses
-        self._capture(content_batch)                    # capture does not execute: run the graph once for this batch
+        self._graph = None
+        self._capture(content_batch, sg)                # capture does not execute: run the graph once for this batch
         self._release(slot)
         self._graph.replay()
         return self._static_losses
 
     def end_epoch(self):
-        self.scheduler.step()                                                                      # :375
+        """StepLR(step_size=num_epochs // num_steps, gamma=0.5).step() (train_cnn.py:248,375)."""
+        self.epoch += 1
+        if self.fused:
+            self.lr = self.base_lr * self.gamma ** (self.epoch // self.step_size)
+            self.arena.set_lr(self.lr)                  # device scalar: graph replays pick it up
+        else:
+            self.scheduler.step()
+            self.lr = float(self.scheduler.get_last_lr()[0])
+
+    def close(self):
+        """Drop the captured graph (and its NCCL work) BEFORE the process group is destroyed: tearing down a communicator
+        that a live CUDA graph still references blocked interpreter exit on the B200 boxes."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._static_losses = None
+        if self.fused:
+            self.arena.grad_sink = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

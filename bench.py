@@ -9,8 +9,14 @@ A "step" is one full optimisation step of train_cnn.py:295-334 (TransformerNet f
 style/content MSE, gradient all-reduce, Adam) on one synthetic batch.  Workload at every N: BASELINE
 configs[1] - batch 32 per GPU at 256x256, bf16-in/fp32-accumulate ("fast" precision) - weak scaling.
 Prints ONE JSON line (rank 0).
+
+Roofline numbers: per-kernel device durations come from the CUDA-GRAPH REPLAY of the step (CUPTI through
+torch.profiler over 3 replays, taken AFTER the timed region - the headline value is never measured under a
+profiler), so the family times sum to the step time; algorithmic flops / bytes per family come from the
+library's own launch accounting (ast_family_stats) over one eager step of the same workload.
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -24,6 +30,7 @@ sys.path.insert(0, ROOT)
 GF_PER_IMG = {"total": 137.86, "conv_gather": 16.803 + 15.784 + 36.465 + 36.465 + 12.306 + 2.147,
               "wgrad_gather": 16.803, "gram": 1.082}
 IN_ELEMS_PER_IMG = 13.107e6   # elements through the 17 InstanceNorm layers at 256^2
+CONV_FAMILIES = ("conv_px", "conv_ws", "conv_tc", "conv_simt")
 
 
 def read_peaks():
@@ -31,8 +38,15 @@ def read_peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
-                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "B200_PROFILING.md fallback"}
+
+
+def read_traffic():
+    """DRAM bytes per launch of each kernel family from the committed ncu --set full captures (profiles/r02_traffic.json,
+    written by profiles/summarize_ncu.py from the raw CSVs next to it); absent -> null in the JSON line."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
 
 
 class ClockSampler:
@@ -90,14 +104,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def _finish(world):
-    """Multi-rank runs leave through os._exit: tearing down an NCCL communicator whose collectives were captured in a
-    (still alive) CUDA graph blocked both ranks for minutes at interpreter exit on the B200 boxes."""
-    if world > 1:
-        sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
-
-
 def cpu_reference_step_rate(batch, size, steps, warmup, threads):
     """The reference's training step (oracle port of train_cnn.py:295-334 + Adam) on the host cores."""
     import torch
@@ -138,6 +144,141 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def kernel_family(name):
+    """Kernel name (as CUPTI reports it) -> family of ast_family_stats, or 'torch/other' for anything not ours."""
+    if "ast::" not in name and "fold_rows" not in name:
+        return "nccl" if "nccl" in name.lower() else "torch/other"
+    for key, fam in (("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"), ("conv_tc_kernel", "conv_tc"),
+                     ("conv_gather_simt", "conv_simt"), ("contract_thin", "wgrad_thin"),
+                     ("contract_tc_kernel<0>", "wgrad_tc"), ("contract_tc_kernel<1>", "gram_tc"),
+                     ("contract_tc_kernel<(int)0>", "wgrad_tc"), ("contract_tc_kernel<(int)1>", "gram_tc"),
+                     ("wgrad_gather_simt", "wgrad_simt"), ("in_apply", "in_apply"), ("in_bwd", "in_bwd"),
+                     ("in_finalize", "in_stats"), ("in_stats", "in_stats"), ("maxpool", "pool"), ("mse", "mse"),
+                     ("gram_finish", "mse"), ("adam", "optim"), ("batch_reduce", "optim"), ("pack_weights", "optim")):
+        if key in name:
+            return fam
+    return "pointwise"
+
+
+def profile_replays(step_fn, replays):
+    """{kernel name: (ms per step, launches per step)} of `replays` calls of step_fn (graph replays), via CUPTI."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(replays):
+            step_fn()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0.0, 0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            t = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            agg[ev.name][0] += t / 1e3 / replays
+            agg[ev.name][1] += 1.0 / replays
+    return {k: (v[0], v[1]) for k, v in agg.items()}
+
+
+def timed(fn, reps, warm=1):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def other_configs(ast, dist, dev, rank, world, peaks):
+    """Short legs for BASELINE configs[2..4] (not the headline): smartaverage over 512^2 paintings (sharded over the
+    ranks with the C2 all-reduce when world > 1), 1080p stylisation B=8 through the fused uint8 boundary, 1024^2 step."""
+    import torch
+    out = {}
+    torch.manual_seed(2)
+    net = ast.StyleTransfer(device=dev, precision="fast")
+    vgg = ast.VGG16(vgg_path=None, precision="fast").to(dev)
+    peak = peaks["bf16_tflops_sustained"]
+    # ---- configs[2]: 'smartaverage', 512^2, 16 paintings per rank (the real job: 4096 / 8 = 512 per rank)
+    per_rank = 16
+    g = torch.Generator(device=dev).manual_seed(2 + rank)
+    paint = [torch.randint(0, 256, (3, 512, 512), device=dev, generator=g).float() for _ in range(per_rank)]
+    grp = dist.group.WORLD if world > 1 else None
+    for mode in ("reference", "mean_gram"):
+        ms = timed(lambda: ast.style_grams_smartaverage(vgg, paint, 1, mode=mode, group=grp), 2)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        rate = per_rank * world / (ms / 1e3)
+        out[f"config3_smartaverage_{mode}"] = {
+            "value": rate, "unit": "paintings/s", "ms": ms, "paintings": per_rank * world,
+            "allreduce_bytes_per_rank": (31.46e6 * 4 if mode == "reference" else 1.39e6),
+            "tensor_frac": 145.86 * rate / world / 1e3 / peak}
+    del paint
+    # ---- configs[3]: 1080p stylisation, batch 8, uint8 BGR in -> uint8 RGB out (inference.py:107-116 fused)
+    x = torch.randint(0, 256, (8, 1080, 1920, 3), device=dev, dtype=torch.uint8)
+    y = net.stylize(x)
+    assert y.shape == x.shape and y.dtype == torch.uint8
+    ms = timed(lambda: net.stylize(x), 3)
+    out["config4_1080p_stylize_b8"] = {"value": 8 * world / (ms / 1e3), "unit": "images/s", "ms": ms,
+                                       "tensor_frac": 531.64 * 8 / ms / peak, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    del x, y
+    torch.cuda.empty_cache()
+    # ---- configs[4]: 1024^2 training step, batch 4 per GPU
+    style = ast.style_grams_single(vgg, torch.randint(0, 256, (3, 1024, 1024), device=dev).float(), 4)
+    tr = ast.PerceptualTrainer(net, vgg, style)
+    xb = torch.randint(0, 256, (4, 3, 1024, 1024), device=dev, dtype=torch.uint8)
+    ms = timed(lambda: tr.step(xb), 3, warm=2)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out["config5_1024_step_b4"] = {"value": 4 * world / (ms / 1e3), "unit": "images/s", "ms": ms,
+                                   "tensor_frac": 2205.7 * 4 / ms / peak}
+    tr.close()
+    return out
+
+
+def dp_check(ast, dist, dev, rank, world):
+    """Data-parallel exactness checked on the NCCL path before timing: the mean of the per-rank losses and
+    the all-reduced gradient arena of `world` shards of 4 images == one pass over the 4*world images on rank 0."""
+    import torch
+    torch.manual_seed(2)
+    net = ast.StyleTransfer(device=dev, precision="fast")
+    vgg = ast.VGG16(vgg_path=None, precision="fast").to(dev)
+    bs, S = 4, 128
+    full = torch.randint(0, 256, (bs * world, 3, S, S), device=dev, generator=torch.Generator(device=dev).manual_seed(5)).float()
+    style_img = torch.randint(0, 256, (3, S, S), device=dev, generator=torch.Generator(device=dev).manual_seed(6)).float()
+    arena = net._arena_for(dev)
+    gbuf = arena.new_grad_buffer()
+    arena.grad_sink = gbuf
+    # sharded: this rank's 4 images, gradients averaged over ranks through the trainer's own all-reduce path
+    style = ast.style_grams_single(vgg, style_img, bs)
+    c, s, t = ast.perceptual_step(net, vgg, full[rank * bs:(rank + 1) * bs], style)
+    from artist_style_transfer_b200 import dp
+    dp.allreduce_mean_flat(gbuf, None)
+    losses = torch.stack([c, s, t])
+    dist.all_reduce(losses, op=dist.ReduceOp.AVG)
+    sharded = gbuf.clone()
+    res = None
+    if rank == 0:
+        gbuf.zero_()
+        style_full = ast.style_grams_single(vgg, style_img, bs * world)
+        c2, s2, t2 = ast.perceptual_step(net, vgg, full, style_full)
+        ref = torch.stack([c2, s2, t2])
+        loss_rel = float(((losses - ref).abs() / ref.abs()).max())
+        grad_rel = float((sharded - gbuf).norm() / gbuf.norm())
+        res = {"loss_rel": loss_rel, "grad_rel": grad_rel, "images": bs * world, "size": S,
+               "ok": bool(loss_rel < 2e-3 and grad_rel < 3e-2)}
+    arena.grad_sink = None
+    torch.cuda.synchronize()
+    dist.barrier()
+    return res
+
+
 def run_ours(args):
     # keep stdout clean for the ONE JSON line: libraries (e.g. "NCCL version ...") write to fd 1 during init
     sys.stdout.flush()
@@ -146,7 +287,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import artist_style_transfer_b200 as ast
-    from artist_style_transfer_b200 import _lib, ops
+    from artist_style_transfer_b200 import _lib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -158,16 +299,22 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, S, K, W = args.batch, args.size, args.steps, args.warmup
+    in_dtype = torch.uint8 if args.input == "uint8" else torch.float32
 
-    torch.manual_seed(2)                                   # identical replicas on every rank (SEED, train_cnn.py:44)
+    check = dp_check(ast, dist, dev, rank, world) if world > 1 else None
+
+    torch.manual_seed(2 + rank)                            # replicas are made identical by the trainer's broadcast
     net = ast.StyleTransfer(device=dev, precision=args.precision)
     vgg = ast.VGG16(vgg_path=None, precision=args.precision).to(dev)
+    if world > 1:                                          # the frozen VGG is not a trained parameter: same on all ranks
+        for p in vgg.parameters():
+            dist.broadcast(p.data, src=0)
     gen = torch.Generator(device=dev).manual_seed(2 + 7919 * rank)
     style_img = torch.randint(0, 256, (3, S, S), device=dev, generator=torch.Generator(device=dev).manual_seed(2)).float()
     style = ast.style_grams_single(vgg, style_img, B)
     trainer = ast.PerceptualTrainer(net, vgg, style, cuda_graph=not args.no_graph)
     nbuf = 4
-    batches = [torch.randint(0, 256, (B, 3, S, S), device=dev, generator=gen).float() for _ in range(nbuf)]
+    batches = [torch.randint(0, 256, (B, 3, S, S), device=dev, generator=gen).to(in_dtype) for _ in range(nbuf)]
 
     def barrier():
         if world > 1:
@@ -181,7 +328,6 @@ def run_ours(args):
         trainer.step(batches[i % nbuf])
     barrier()
     t_begin = time.time()
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
@@ -189,18 +335,18 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
     clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = B * world * K / (ms / 1e3)
+    losses_last = [float(x) for x in losses]
 
-    # ---- e2e: host buffers -> H2D copy -> step -> D2H loss read, every step (same workload)
-    host = [torch.randint(0, 256, (B, 3, S, S)).float().pin_memory() for _ in range(2)]
+    # ---- e2e: pinned host buffers -> H2D copy -> step -> D2H loss read, every step (same workload, >= 20 steps)
+    host = [torch.randint(0, 256, (B, 3, S, S)).to(in_dtype).pin_memory() for _ in range(2)]
     loss_host = torch.zeros(3, dtype=torch.float32).pin_memory()
-    ke = max(2, min(K, 5))
+    ke = max(20, K)
     barrier()
     e0.record()
     nxt = trainer.prefetch(host[0])                         # H2D of step 0's inputs (inside the timed region)
@@ -218,24 +364,26 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = B * world * ke / (float(te.item()) / 1e3)
 
-    # ---- per-kernel-family device time (CUDA events on the launching stream), 2 instrumented steps
-    lc0 = _lib.launch_count()
-    ops.profile_begin()
-    kp = 2
-    for i in range(kp):
-        trainer._eager_step(batches[i % nbuf])          # per-op events need eager launches (not a graph replay)
-    prof = ops.profile_end()
-    if not args.no_graph:        # replays do not pass through the library's launch counter: use the eager count
-        launches = (_lib.launch_count() - lc0) // kp * K
-    fam = {k: {"ms_per_step": v[0] / kp, "launches_per_step": v[1] / kp} for k, v in prof.items()}
-    scale = (S / 256.0) ** 2
+    # ---- algorithmic work per kernel family: the library's accounting over ONE eager step of the same workload
+    lc0, fs0 = _lib.launch_count(), _lib.family_stats()
+    trainer._eager_step(batches[0], trainer.style_gram)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - lc0
+    work = _lib.family_delta(fs0)
+    # ---- device time per kernel from the graph replay (CUPTI, after the timed region)
+    R = 3
+    kern = profile_replays(lambda: trainer.step(batches[0]), R)
+    fam_ms, fam_n = collections.defaultdict(float), collections.defaultdict(float)
+    for name, (kms, cnt) in kern.items():
+        fam_ms[kernel_family(name)] += kms
+        fam_n[kernel_family(name)] += cnt
+    sum_ms = sum(fam_ms.values())
+
     peaks = read_peaks()
-    conv_ms = sum(fam[k]["ms_per_step"] for k in ("conv_gather_tc", "conv_gather_simt") if k in fam)
-    conv_launches = sum(fam[k]["launches_per_step"] for k in ("conv_gather_tc", "conv_gather_simt") if k in fam)
-    conv_tf = GF_PER_IMG["conv_gather"] * scale * B / conv_ms            # GF/ms == TF/s
-    peak_tf = peaks["bf16_tflops_sustained"]
-    # TF32 peak is not in MEASURED_PEAKS.json: measure it the same way (cuBLAS 8192^3, best of 5).
-    # 42 % of the conv FLOPs of this mode run in TF32 (VGG forward + Gram backward), the rest in bf16.
+    traffic = read_traffic()
+    scale = (S / 256.0) ** 2
+    peak_tf, peak_bw = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
+    # TF32 peak is not in MEASURED_PEAKS.json: measured here the same way (cuBLAS 8192^3, best of 6)
     tf32_peak = None
     if rank == 0 and args.precision == "fast":
         old = torch.backends.cuda.matmul.allow_tf32
@@ -249,33 +397,76 @@ def run_ours(args):
         tf32_peak = 2 * 8192 ** 3 / best / 1e9
         torch.backends.cuda.matmul.allow_tf32 = old
         del a_, b_
+
+    def entry(fam, bound, algo, unit_peak):
+        ms_f = fam_ms.get(fam, 0.0)
+        if ms_f <= 0:
+            return None
+        achieved = algo / (ms_f / 1e3) / (1e12 if bound == "tensor" else 1e9)
+        tr = traffic.get(fam)
+        return {"kernel": fam, "bound": bound, "achieved": achieved, "peak": unit_peak,
+                "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": achieved / unit_peak,
+                "ms_per_step": ms_f, "launches_per_step": fam_n.get(fam, 0.0),
+                "launch_ms_avg": ms_f / max(1.0, fam_n.get(fam, 1.0)),
+                "algorithmic_per_step": algo, "traffic": None if not tr else tr.get("dram_bytes_per_launch"),
+                "traffic_src": None if not tr else tr.get("src")}
+
+    # conv families: the library counts executed flops (3-channel ends padded to 32); scale them so that all conv launches
+    # together carry SURVEY 8(d)'s algorithmic 119.97 GF per image
+    lib_conv = sum(work[f][1] for f in CONV_FAMILIES if f in work)
+    conv_algo_total = GF_PER_IMG["conv_gather"] * 1e9 * scale * B
+    rooflines = []
+    for f in CONV_FAMILIES:
+        if f in work and work[f][1] > 0:
+            rooflines.append(entry(f, "tensor", work[f][1] / lib_conv * conv_algo_total, peak_tf))
+    wg = sum(work[f][1] for f in ("wgrad_tc", "wgrad_thin", "wgrad_simt") if f in work)
+    for f in ("wgrad_tc", "wgrad_thin", "wgrad_simt"):
+        if f in work and work[f][1] > 0:
+            rooflines.append(entry(f, "tensor", work[f][1] / wg * GF_PER_IMG["wgrad_gather"] * 1e9 * scale * B, peak_tf))
+    for f in ("gram_tc", "gram_simt"):                     # Gram at 256^2 is HBM bound: one read of F + G out
+        if f in work and work[f][2] > 0:
+            rooflines.append(entry(f, "hbm", work[f][2], peak_bw))
+    for f in ("in_apply", "in_bwd", "pool", "mse", "pointwise", "optim"):
+        if f in work and work[f][2] > 0:
+            rooflines.append(entry(f, "hbm", work[f][2], peak_bw))
+    rooflines = [r for r in rooflines if r]
+    conv_ms = sum(fam_ms.get(f, 0.0) for f in CONV_FAMILIES)
+    conv_tf = conv_algo_total / (conv_ms / 1e3) / 1e12
     # TF32: VGG forward on the generated batch (36.465) and on the content batch (12.306) + the Gram backward (2.147);
-    # bf16: TransformerNet forward / dgrad and, since the bf16 gradient chain, the VGG dgrad (36.465)
+    # bf16: TransformerNet forward / dgrad and the VGG dgrad (36.465)
     tf32_share = (36.465 + 12.306 + 2.147) / GF_PER_IMG["conv_gather"]
     mix_peak = None if not tf32_peak else 1.0 / (tf32_share / tf32_peak + (1 - tf32_share) / peaks["bf16_tflops"])
-    roofline = {"kernel": "conv_gather (all conv fwd/dgrad launches of one step: conv_px_kernel + conv_tc_kernel + conv_ws_kernel)",
-                "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
-                "traffic": 491.8e6, "traffic_note": "dram read+write bytes of one conv_px<tf32> launch (128->128 @128^2, "
-                "B=32) from profiles/r01f_conv_px_ncu_full_excerpt.csv; algorithmic bytes of that launch: 537 MB",
-                "peak_source": f"{peaks['src']} bf16 sustained", "launch_ms_avg": conv_ms / max(1.0, conv_launches),
-                "tf32_tflops_measured": tf32_peak, "tf32_flop_share": tf32_share,
-                "frac_of_precision_mix_peak": None if not mix_peak else conv_tf / mix_peak}
-    in_ms = fam.get("instnorm", {"ms_per_step": float("nan")})["ms_per_step"]
+    roofline_conv = {"kernel": "all conv fwd/dgrad launches of one step (conv_px + conv_ws + conv_tc kernels)",
+                     "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
+                     "ms_per_step": conv_ms, "peak_source": f"{peaks['src']} bf16 sustained",
+                     "tf32_tflops_measured_here_cublas_8192": tf32_peak, "tf32_flop_share": tf32_share,
+                     "frac_of_precision_mix_peak": None if not mix_peak else conv_tf / mix_peak, "traffic": None}
     esz = 2 if args.precision == "fast" else 4
+    in_ms = fam_ms.get("in_apply", 0.0) + fam_ms.get("in_bwd", 0.0) + fam_ms.get("in_stats", 0.0)
     in_gb = IN_ELEMS_PER_IMG * scale * B * esz * 5 / 1e9                 # fwd 1R+1W, bwd 2R+1W
-    # the kernels physically move 7 passes (apply 1R+1W; backward statistics 2R, backward apply 2R+1W; the forward
-    # statistics ride in the conv epilogue) where 5 are algorithmic
-    roofline_in = {"kernel": "instnorm (in_apply_staged fwd; in_bwd_stats_staged + in_bwd_apply_staged bwd)", "bound": "hbm",
-                   "achieved": in_gb / (in_ms / 1e3), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": in_gb / (in_ms / 1e3) / peaks["hbm_gbs"], "traffic": None,
-                   "achieved_physical": in_gb * 7 / 5 / (in_ms / 1e3),
-                   "frac_physical": in_gb * 7 / 5 / (in_ms / 1e3) / peaks["hbm_gbs"]}
+    tr_in = traffic.get("in_bwd")
+    roofline_in = {"kernel": "InstanceNorm (in_apply_staged fwd; in_bwd_* bwd; forward statistics ride in the conv epilogues)",
+                   "bound": "hbm", "achieved": in_gb / (in_ms / 1e3), "peak": peak_bw, "unit": "GB/s",
+                   "frac": in_gb / (in_ms / 1e3) / peak_bw, "ms_per_step": in_ms,
+                   "traffic": None if not tr_in else tr_in.get("dram_bytes_per_launch"),
+                   "note": "13.107 M elements/img x 5 algorithmic passes (SURVEY 8d)"}
+    dominant = max(rooflines, key=lambda r: r["ms_per_step"]) if rooflines else roofline_conv
+    dominant = dict(dominant, peak_source=f"{peaks['src']} ({'bf16 sustained' if dominant['bound'] == 'tensor' else 'HBM copy'})")
 
+    extra = None
+    if not args.no_other_configs:
+        trainer.close()
+        del trainer, batches, host
+        torch.cuda.empty_cache()
+        extra = other_configs(ast, dist, dev, rank, world, peaks)
+        trainer = None
+    if trainer is not None:
+        trainer.close()
     if world > 1:                      # everyone is done with the GPU work; from here on only rank 0 has something to do
         torch.cuda.synchronize()
         dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        _finish(world)
         return
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -283,44 +474,49 @@ def run_ours(args):
         rate, _ = cpu_reference_step_rate(4, S, 3, 1, threads)
         cpu_baseline = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": f"1 warm-up + 3 timed steps of B=4 at {S}x{S}, fp32 oracle port of train_cnn.py:295-334 + Adam"}
+    in_bytes = B * 3 * S * S * (1 if in_dtype == torch.uint8 else 4)
     line = {
         "metric": "train_images_per_sec_256", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "fast" else "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: perceptual-loss training step, {S}x{S}, batch {B}/GPU, "
-                               f"precision={args.precision}, random-init TransformerNet+VGG16, Adam",
+                               f"precision={args.precision}, random-init TransformerNet+VGG16, fused Adam(L2)",
                    "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                   "input": f"{args.input} BGR [B,3,{S},{S}] (dataset.py:97-108 images are uint8-derived)",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; inputs rotate over 4 buffers"},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
-                "d2h_bytes_per_step": 12, "steps": ke},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_instnorm": roofline_in,
-        "kernel_families": fam, "cpu_baseline": cpu_baseline,
-        "losses_last_step": [float(x) for x in losses],
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12, "steps": ke},
+        "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step), "clocks": clocks,
+        "roofline": dominant, "roofline_conv": roofline_conv, "roofline_instnorm": roofline_in, "rooflines": rooflines,
+        "family_ms_per_step": dict(fam_ms), "sum_kernel_ms_per_step": sum_ms,
+        "timing_source": f"CUPTI kernel durations over {R} CUDA-graph replays after the timed region",
+        "cpu_baseline": cpu_baseline, "dp_check": check, "other_configs": extra,
+        "losses_last_step": losses_last,
         "gflop_per_image": GF_PER_IMG["total"] * scale,
         "tensor_frac_whole_step": GF_PER_IMG["total"] * scale * B * K / ms / peak_tf,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
-    _finish(world)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fast", choices=["fast", "fp32"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--input", default="uint8", choices=["uint8", "float32"], help="dtype of the content batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short BASELINE configs[2..4] legs")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    run_ours(args)
 
 
 if __name__ == "__main__":

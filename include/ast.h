@@ -25,9 +25,13 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 4
+#define AST_ABI_VERSION 5
 
-typedef enum { AST_F32 = 0, AST_BF16 = 1, AST_TF32 = 2 /* fp32 storage rounded to TF32; pack_weights only */ } ast_dtype;
+typedef enum {
+  AST_F32 = 0, AST_BF16 = 1,
+  AST_TF32 = 2, /* fp32 storage rounded to TF32; weight packing only */
+  AST_U8 = 3    /* uint8 images at the host boundary (dataset.py:97-108 / inference.py:110,116): ast_row_im2col input, ast_fold_rows output */
+} ast_dtype;
 
 /* strided 4-D view; strides in ELEMENTS.  */
 typedef struct {
@@ -58,9 +62,11 @@ typedef struct {
   int16_t dy[AST_MAX_TAPS];
   int16_t dx[AST_MAX_TAPS];
   int64_t w_img_stride;    /* elements between per-image weight sets, 0 = shared weights */
-  float*  stats;           /* optional fp32 [n][cout][2] (sum x, sum x^2 of the fp32 results, BEFORE bias/activation),
+  double* stats;           /* optional fp64 [n][cout][2] (sum x, sum x^2 of the fp32 results, BEFORE bias/activation),
                               accumulated by the tensor-core epilogue: InstanceNorm statistics fused into the producing
-                              conv (cnn.py:63,68).  Zeroed by the caller; NULL = off; tensor-core launches only. */
+                              conv (cnn.py:63,68).  Per-tile partial sums are fp32 (centred where a thread owns a channel),
+                              the accumulation across the plane is fp64 so that var = E[x^2] - mean^2 survives |mean| >> std.
+                              Zeroed by the caller; NULL = off; tensor-core launches only. */
   const ast_image* pooled; /* optional [n, mi/2, mj/2, cout]: nn.MaxPool2d(2, 2) of the epilogue result, written by the same
                               kernel (torchvision VGG16 features idx 4/9/16 after the conv+ReLU before them,
                               train_cnn.py:54,72-73).  Plain stride-1 launches (so = 1, no phase offset) of the
@@ -107,10 +113,6 @@ int ast_pack_weights_ex(const float* src, const int32_t* tap_off, int32_t ntaps,
 int ast_row_im2col(const ast_image* src, const ast_image* out, const float* shift, int32_t kw, int32_t sign,
                    int32_t px, int32_t py, int32_t reflect, int32_t round_tf32, void* stream);
 
-/* out[n, y, x, d*C + j] = src[n, y + sign*d - py, x, j] (0 outside), d in [0, kh): folds the kh vertical taps of an NHWC
- * tensor into channels so that a kh-tap ast_wgrad_gather becomes one tap over kh*C channels (thin 9x9 layers). */
-int ast_unfold_rows(const ast_image* src, const ast_image* out, int32_t kh, int32_t sign, int32_t py, void* stream);
-
 /* Finishes a thin-OUTPUT k x k convolution (cnn.py:39, the 32->3 9x9 layer) whose kw horizontal taps were computed as
  * kw*C output channels of a k-tap vertical ast_conv_gather:
  *   out[n, y, x, c] = bias[c] + sum_{d < kw} part[n, y, x + d, d*C + c]      (optional ReLU)
@@ -122,7 +124,7 @@ int ast_fold_rows(const ast_image* part, const ast_image* out, const float* bias
 int64_t ast_instnorm_workspace_bytes(int32_t n, int32_t c);
 int ast_instnorm_stats(const ast_image* x, float* mean, float* rstd, float eps, void* workspace, void* stream);
 /* mean/rstd from the (sum x, sum x^2) pairs a conv epilogue accumulated (ast_gather_geom.stats): [n*c][2] -> [n*c]. */
-int ast_instnorm_finalize(const float* sums, int32_t n, int32_t c, int32_t hw, float eps, float* mean, float* rstd,
+int ast_instnorm_finalize(const double* sums, int32_t n, int32_t c, int32_t hw, float eps, float* mean, float* rstd,
                           void* stream);
 /* y = gamma*(x-mean)*rstd + beta (+ residual) (ReLU if relu), written to the interior of `out`, which is an
  * (h+2*pad) x (w+2*pad) image whose border is filled by mirroring (the next layer's nn.ReflectionPad2d). */
@@ -133,7 +135,10 @@ int ast_instnorm_apply(const ast_image* x, const float* mean, const float* rstd,
  *   g'   = (fold_reflect(gpad, pad) + gextra) * (relu ? y>0 : 1)
  *   s1[n,c] = sum g' ; s2[n,c] = sum g'*xhat                       (pass 1, ast_instnorm_bwd_stats)
  *   dx   = gamma*rstd*(g' - s1/HW - xhat*s2/HW) ; gtotal = g'      (pass 2, ast_instnorm_bwd_apply)
- * gpad may be NULL (no padded consumer), gextra may be NULL, gtotal may be NULL. */
+ * gpad may be NULL (no padded consumer), gextra may be NULL, gtotal may be NULL.
+ * relu: bit 0 = the forward applied ReLU; AST_IN_SUMS_ZEROED = s1/s2 were zeroed by the caller (one fill for all layers)
+ * instead of two memsets per call. */
+#define AST_IN_SUMS_ZEROED 2
 int ast_instnorm_bwd_stats(const ast_image* x, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, const ast_image* gpad, int32_t pad, const ast_image* gextra,
                            int32_t relu, float* s1, float* s2, void* stream);
@@ -141,6 +146,14 @@ int ast_instnorm_bwd_apply(const ast_image* x, const float* mean, const float* r
                            const float* beta, const ast_image* gpad, int32_t pad, const ast_image* gextra,
                            int32_t relu, const float* s1, const float* s2, const ast_image* dx,
                            const ast_image* gtotal, void* stream);
+
+/* Both passes in one call.  With `arrive` (n int32, ZERO on entry, together with AST_IN_SUMS_ZEROED) and x + g' small
+ * enough to stay in the 126 MB L2, ONE cooperative kernel runs the statistics pass, meets the other blocks of the same
+ * image at a counter barrier and re-reads its rows for the apply pass from L2 (5 HBM passes instead of 7); otherwise the
+ * two kernels above run back to back.  Same results either way. */
+int ast_instnorm_bwd(const ast_image* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     const ast_image* gpad, int32_t pad, const ast_image* gextra, int32_t relu, float* s1, float* s2,
+                     int32_t* arrive, const ast_image* dx, const ast_image* gtotal, void* stream);
 
 /* nn.MaxPool2d(2,2) of torchvision vgg16.features idx 4/9/16 and its backward fused with the tap-gradient add
  * and the ReLU mask of the producing layer:  gx = (route(gy) + gadd) * (x > 0). */
@@ -150,6 +163,20 @@ int ast_maxpool2_bwd(const ast_image* x, const ast_image* y, const ast_image* gy
 
 /* gram(), train_cnn.py:103-107:  G[n] = F[n] F[n]^T * scale, F = x viewed as (c, h*w).  G fp32 [n][c][c], zeroed here. */
 int ast_gram(const ast_image* x, float* g, float scale, int32_t flags, void* stream);
+
+/* The style term of one VGG tap in one call (train_cnn.py:321-325 with gram() :103-107; north_star: "fuse the 1/(CHW)
+ * scale and the style-MSE reduction into the epilogue"):
+ *   G[n]     = F[n] F[n]^T * scale                 (upper triangle on the tensor cores, mirrored by the finishing CTA)
+ *   loss[0] += loss_scale * sum_{n,i,j} (G[n][i][j] - S[n][i][j])^2             (nn.MSELoss numerator)
+ *   D[n]     = d_scale * (G[n] - S[n])             (optional; with d_scale = 4*w/(B*C^2*CHW) these are the per-image 1x1
+ *                                                   weights of the Gram backward dF = D F, see ast_conv_gather)
+ * target: S with `target_img_stride` elements between images (0 = one C x C target for the whole batch, which is what
+ * train_cnn.py:187-190 builds by expanding one style image).  g ([n][c][c]) and counters
+ * (AST_GRAM_COUNTERS_PER_IMAGE ints per image) must be ZERO on entry; loss is an fp64 accumulator shared by the taps of a
+ * step (hundreds of small addends into a ~1e4 total: an fp32 accumulator loses 1e-5 of it).  flags: AST_CONV_TENSOR. */
+#define AST_GRAM_COUNTERS_PER_IMAGE 16
+int ast_gram_mse(const ast_image* x, float* g, float scale, const float* target, int64_t target_img_stride, double* loss,
+                 float loss_scale, float* d, float d_scale, int32_t* counters, int32_t flags, void* stream);
 
 /* nn.MSELoss pieces (train_cnn.py:249,307,323): loss[0] += scale * sum((a-b)^2) ; grad = gscale*(a-b) (optional).
  * a/b/grad are images of identical logical shape. */
@@ -163,6 +190,57 @@ int ast_accumulate(const ast_image* x, const ast_image* acc, void* stream);
 
 /* out = (a + b) * (mask > 0)   (b may be NULL; nn.ReLU backward on an incoming tap gradient) */
 int ast_mask_add(const ast_image* a, const ast_image* b, const ast_image* mask, const ast_image* out, void* stream);
+
+/* ---- optimizer side (train_cnn.py:247-248,334,375: optim.Adam(lr 0.0024, weight_decay 1e-4) + StepLR), SURVEY 8f-1 ----
+ * One table-driven launch applies L2 + Adam to every TransformerNet parameter tensor (addressed relative to one base
+ * pointer, so the nn.Parameters stay where PyTorch allocated them) and refreshes the packed operand copies ([tap][cout][cin] bf16 / TF32 / fp32) the next step's convolutions read.
+ * Gradients are read in the layout the filter-gradient kernels wrote them (tap-major scratch) through a per-tensor map,
+ * so no permute / flatten pass is needed between backward, the NCCL all-reduce of the gradient arena and the update.
+ *
+ * Parameter element i of a tensor with logical shape dim = (A, B, U, V) decomposes as i = ((a*B + b)*U + u)*V + v;
+ *   gradient  = grads[g_off + a*g_stride[0] + b*g_stride[1] + tap_table[g_tap + u*V + v]]
+ *   pack k    = ((dtype*)((char*)pack_arena + pack[k].off))[a*stride[0] + b*stride[1] + tap_table[pack[k].tap + u*V + v]] */
+typedef struct {
+  int64_t off;            /* BYTES from the start of the pack arena */
+  int64_t stride[2];      /* elements */
+  int32_t tap;            /* first entry of this map in the tap table */
+  int32_t dtype;          /* ast_dtype of the packed copy */
+} ast_pack_map;
+typedef struct {
+  int64_t p_off;          /* first element relative to `params` (any fp32 tensors of one device: params = lowest address) */
+  int64_t s_off;          /* first element in the exp_avg / exp_avg_sq arenas */
+  int64_t numel;
+  int32_t dim[4];
+  int64_t g_off, g_stride[2];
+  int32_t g_tap, n_pack;
+  ast_pack_map pack[2];
+} ast_param_desc;
+typedef struct {          /* DEVICE-resident hyper-parameters and step state: graph replays read the current values */
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+  float step, bias_c1, bias_c2;     /* step count, 1 - beta1^step, 1 - beta2^step: maintained by ast_adam_step */
+} ast_adam_state;
+/* descs / work / tap_table / state are DEVICE pointers.  work: n_work pairs (descriptor index, first element); every work
+ * item covers ast_adam_work_item() consecutive elements of one tensor.  update = 0 only refreshes the packs (after
+ * load_state_dict).  update = 1: state->step += 1 first (a one-thread kernel), then p, m, v and the packs are updated. */
+int ast_adam_step(const ast_param_desc* descs, int32_t n_desc, const int32_t* work, int32_t n_work, float* params,
+                  const float* grads, float* exp_avg, float* exp_avg_sq, void* pack_arena, const int64_t* tap_table,
+                  ast_adam_state* state, int32_t update, void* stream);
+int32_t ast_adam_work_item(void);
+
+/* dst[dst_off + c] = sum_{r < rows} src[src_off + r*row_stride + c], c < cols, for n_desc descriptors (DEVICE array) in
+ * one launch: dbeta / dgamma of all InstanceNorm layers from their per-(n, c) partial sums (aten::sum). */
+typedef struct { int64_t src_off, dst_off, row_stride; int32_t rows, cols; } ast_reduce_desc;
+int ast_batch_reduce(const float* src, float* dst, const ast_reduce_desc* descs, int32_t n_desc, int32_t max_cols,
+                     void* stream);
+/* out[c] += sum_{n,h,w} x[n,h,w,c]   (bias gradient of the last, norm-free conv layer, cnn.py:39; aten::sum) */
+int ast_channel_sum(const ast_image* x, float* out, void* stream);
+
+/* per-kernel-family accounting: launches and ALGORITHMIC flops / bytes of everything launched so far (bench.py divides
+ * them by the family's device time; tests assert which kernel a case ran on).  Families: ast_family_name(0..count-1). */
+int ast_family_count(void);
+const char* ast_family_name(int family);
+int ast_family_stats(int family, int64_t* launches, double* flops, double* bytes);
+void ast_family_reset(void);
 
 /* bitmask of the tensor-core kernels compiled into this build: 1 = tcgen05 gather conv, 2 = tcgen05 Gram/wgrad */
 int ast_capabilities(void);

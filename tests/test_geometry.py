@@ -95,20 +95,92 @@ def test_sizes():
     assert [len(l.taps) for l in cg.convT_fwd(3, 2, 1, 1, 8, 8)] == [1, 2, 2, 4]      # SURVEY 8c sub-pixel phases
 
 
-def test_zero_arena_slices_are_disjoint_aligned_and_zero():
-    """cnn._ZeroArena: one zero buffer carved into 16-byte aligned, non-overlapping accumulators."""
+def _emulate_pack(w, pack, dims):
+    """What ast_adam_step writes for one packed copy: element (a,b,u,v) -> a*s0 + b*s1 + taps[u*V+v] (include/ast.h)."""
     import torch
-    from artist_style_transfer_b200.cnn import _ZeroArena
-    sizes = [5, 64, 3 * 7, 1]
-    arena = _ZeroArena(sizes, torch.device("cpu"))
-    views = [arena.take(5), arena.take(8, 8), arena.take(3, 7), arena.take(1)]
-    base = arena.buf.data_ptr()
+    A, B, U, V = dims
+    n = 1
+    for d in pack.shape:
+        n *= d
+    ia = torch.arange(A).view(A, 1, 1) * pack.stride[0]
+    ib = torch.arange(B).view(1, B, 1) * pack.stride[1]
+    it = torch.tensor(pack.taps, dtype=torch.int64).view(1, 1, U * V)
+    offs = (ia + ib + it).reshape(-1)
+    assert int(torch.bincount(offs, minlength=n).max()) == 1, "two master elements map to the same packed slot"
+    flat = torch.zeros(n, dtype=torch.float64)
+    flat[offs] = w.reshape(-1)
+    return flat.view(pack.shape)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fast"])
+def test_arena_layouts_match_the_gather_kernels_operand_layouts(mode):
+    """arena.TransferArena (host logic, CPU): the table-driven pack maps reproduce the [tap][cout][cin] operand layouts
+    that conv_geometry's launches index, for conv / stride-2 conv / ConvTranspose phases / the 3-channel ends; gradient
+    segments are disjoint and 16-byte aligned and the strided p.grad views address the same elements as the maps."""
+    import torch
+    from artist_style_transfer_b200 import arena as arena_mod, cnn
+    net = cnn.StyleTransfer(device="cpu", precision=mode)
+    stages = net._stages()
+    ar = arena_mod.TransferArena(stages, mode, torch.device("cpu"))
     spans = []
-    for v, n in zip(views, sizes):
-        assert v.numel() == n and float(v.abs().sum()) == 0.0
-        assert (v.data_ptr() - base) % 16 == 0
-        spans.append((v.data_ptr() - base, v.data_ptr() - base + 4 * n))
+    for st, pl in zip(stages, ar.plans):
+        w = st.conv.weight.detach().double()
+        k, co, ci = st.k, st.cout, st.cin
+        dims = tuple(w.shape)
+        conv = st.kind == "conv"
+        # ---- forward pack
+        got = _emulate_pack(w, pl.fwd, dims)
+        if pl.thin_in:
+            for dy in range(k):
+                for dx in range(k):
+                    assert torch.equal(got[dy, :, dx * ci:(dx + 1) * ci], w[:, :, dy, dx])
+            assert float(got[:, :, k * ci:].abs().sum()) == 0.0
+        elif pl.thin_out:
+            for dy in range(k):
+                for dx in range(k):
+                    assert torch.equal(got[dy, dx * co:(dx + 1) * co, :], w[:, :, dy, dx])
+        else:
+            launches = cnn._fwd_geometry(st, 16 + k, 16 + k)[0]
+            ar.woff(pl.fwd, launches)
+            for l in launches:
+                for t, (u, v) in enumerate(l.wtaps):
+                    ref = w[:, :, u, v] if conv else w[:, :, u, v].t()           # [co][ci]
+                    assert torch.equal(got[l.woff + t], ref), (st.kind, k, st.stride, u, v)
+        # ---- data-gradient pack
+        if pl.dgrad is not None:
+            got = _emulate_pack(w, pl.dgrad, dims)
+            if pl.thin_out:
+                for dy in range(k):
+                    for dx in range(k):
+                        assert torch.equal(got[dy, :, dx * co:(dx + 1) * co], w[:, :, dy, dx].t())
+            else:
+                dl = (cg.conv_dgrad(k, st.stride, 0, 16 + k, 16 + k) if conv else cg.convT_dgrad(k, st.stride, k // 2, 16, 16))
+                ar.woff(pl.dgrad, dl)
+                for l in dl:
+                    for t, (u, v) in enumerate(l.wtaps):
+                        ref = w[:, :, u, v].t() if conv else w[:, :, u, v]       # [ci][co]
+                        assert torch.equal(got[l.woff + t], ref)
+        n = 1
+        for d in pl.g_shape:
+            n *= d
+        spans += [(pl.g_off, pl.g_off + n), (pl.g_cb, pl.g_cb + co)]
+        if st.norm:
+            spans += [(pl.g_gam, pl.g_gam + co), (pl.g_bet, pl.g_bet + co)]
+    spans.sort()
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
-        assert a1 <= b0
-    views[1].fill_(1.0)
-    assert float(views[0].sum()) == 0.0 and float(views[2].sum()) == 0.0
+        assert a1 <= b0 and b0 % 4 == 0
+    assert spans[-1][1] <= ar.g_numel
+    # strided gradient views == the (a, b, tap) maps of the descriptors
+    gbuf = torch.arange(ar.g_numel, dtype=torch.float32)
+    views = ar.grad_views(gbuf)
+    it = iter(views)
+    for st, pl in zip(stages, ar.plans):
+        gw = next(it)
+        assert tuple(gw.shape) == tuple(st.conv.weight.shape)
+        k = st.k
+        for (a, b, u, v) in [(0, 0, 0, 0), (1, 2, k - 1, 0), (2, 1, 0, k - 1), (gw.shape[0] - 1, gw.shape[1] - 1, k - 1, k - 1)]:
+            want = pl.g_off + a * pl.g_stride[0] + b * pl.g_stride[1] + pl.g_taps[u * k + v]
+            assert int(gw[a, b, u, v]) == want
+        assert int(next(it)[0]) == pl.g_cb
+        if st.norm:
+            assert int(next(it)[0]) == pl.g_gam and int(next(it)[0]) == pl.g_bet
