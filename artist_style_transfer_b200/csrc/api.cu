@@ -30,7 +30,7 @@ void count_work(int family, double flops, double bytes) {
   atomic_add(g_fam_bytes[family], bytes);
 }
 static const char* const kFamilyNames[FAM_COUNT] = {
-  "conv_tc", "conv_px", "conv_ws", "conv_simt", "wgrad_tc", "wgrad_thin", "wgrad_simt", "gram_tc", "gram_simt",
+  "conv_tc", "conv_px", "conv_ws", "conv_hx", "conv_simt", "wgrad_tc", "wgrad_thin", "wgrad_simt", "gram_tc", "gram_simt",
   "in_apply", "in_bwd", "in_stats", "pool", "mse", "pointwise", "optim"};
 }  // namespace ast
 

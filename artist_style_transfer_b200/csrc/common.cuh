@@ -21,7 +21,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // geometry on the host.  bench.py divides these by the device time of the same family in the CUDA-graph replay; the
 // tests use the launch counts to assert which kernel a case really ran on.
 enum Family {
-  FAM_CONV_TC = 0, FAM_CONV_PX, FAM_CONV_WS, FAM_CONV_SIMT, FAM_WGRAD_TC, FAM_WGRAD_THIN, FAM_WGRAD_SIMT, FAM_GRAM_TC,
+  FAM_CONV_TC = 0, FAM_CONV_PX, FAM_CONV_WS, FAM_CONV_HX, FAM_CONV_SIMT, FAM_WGRAD_TC, FAM_WGRAD_THIN, FAM_WGRAD_SIMT, FAM_GRAM_TC,
   FAM_GRAM_SIMT, FAM_IN_APPLY, FAM_IN_BWD, FAM_IN_STATS, FAM_POOL, FAM_MSE, FAM_POINTWISE, FAM_OPTIM, FAM_COUNT
 };
 void count_work(int family, double flops, double bytes);

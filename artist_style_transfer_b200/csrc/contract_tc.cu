@@ -238,19 +238,26 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
           const int mb0 = m0 + tr * 32, nb0 = n0 + tc * 32;
           if (mb0 >= p.m_valid || nb0 >= C || nb0 + 31 < mb0) continue;     // tile outside the matrix / strictly below the diagonal
           const int n = nb0 + lane;
-#pragma unroll 4
+          // all 32 + 32 loads of the tile first (independent, in flight together), then the arithmetic and the stores:
+          // interleaving them serialises on the load latency because the stores may alias the loads
+          float gv[32], sv[32];
+#pragma unroll
           for (int r = 0; r < 32; ++r) {
             const int mm = mb0 + r;
-            float gv = 0.f, dv = 0.f;
-            if (mm < p.m_valid && n < C && n >= mm) {
-              gv = __ldcg(G + (long long)mm * C + n);
-              if (S) {
-                dv = gv - __ldg(S + (long long)mm * C + n);
-                part = fmaf(n > mm ? 2.f : 1.f, dv * dv, part);
-                if (D) D[(long long)mm * C + n] = round_tf32(fin.d_scale * dv);
-              }
+            const bool ok = mm < p.m_valid && n < C && n >= mm;
+            gv[r] = ok ? __ldcg(G + (long long)mm * C + n) : 0.f;
+            sv[r] = (ok && S) ? __ldg(S + (long long)mm * C + n) : 0.f;
+          }
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int mm = mb0 + r;
+            float dv = 0.f;
+            if (S && mm < p.m_valid && n < C && n >= mm) {
+              dv = gv[r] - sv[r];
+              part = fmaf(n > mm ? 2.f : 1.f, dv * dv, part);
+              if (D) D[(long long)mm * C + n] = round_tf32(fin.d_scale * dv);
             }
-            tg[r * 33 + lane] = gv;
+            tg[r * 33 + lane] = gv[r];
             td[r * 33 + lane] = dv;
           }
           __syncwarp();

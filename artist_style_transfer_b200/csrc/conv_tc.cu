@@ -192,6 +192,9 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
 int conv_gather_px(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                    const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
                    cudaStream_t stream);   // conv_px.cu: 1 = launched, 0 = not applicable
+int conv_gather_hx(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
+                   cudaStream_t stream);   // conv_hx.cu: 1 = launched, 0 = not applicable
 int tc_capabilities() { return 3; }   // 1 = conv_tc.cu, 2 = contract_tc.cu (both are always built together)
 
 int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, const float* in_shift,
@@ -216,10 +219,12 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
-  // dispatch: weight-stationary kernel (filter resident in smem, stride 1), then the pixels-as-N kernel (cout 64/128,
-  // long K loops), then the generic kernel below
+  // dispatch: weight-stationary kernel (filter resident in smem, stride 1), then the halo-reusing pixels-as-N kernel
+  // (stride 1, cout % 128 == 0, multi-tap), then the per-tap pixels-as-N kernel (cout 64/128, long K loops: stride-2
+  // layers), then the generic kernel below (short K loops, per-image weights, thin outputs)
   if (int wr = conv_gather_ws(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return wr == 1 ? 0 : wr;
   AST_CHECK_ARG(!g->pooled, "conv_tc: a pooled output needs the weight-stationary kernel (stride 1, filter resident in smem)");
+  if (int hr = conv_gather_hx(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return hr == 1 ? 0 : hr;
   if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
 
   TcParams p;

@@ -552,17 +552,18 @@ static Rows to_rows(const ast_image* im) {
   return r;
 }
 // rows per block / segments / stages; false when the shape does not suit the staged kernels
-static bool ns_plan(NsShape* sh, int n, int C, int H, int W, int pad, int rows_total, int width, int esz, int nslabs, int* nblk) {
+static bool ns_plan(NsShape* sh, int n, int C, int H, int W, int pad, int rows_total, int width, int esz, int nslabs, int* nblk,
+                    int slab_max = NS_SLAB_MAX, int budget = NS_SMEM_BUDGET) {
   if (C * esz > NS_SLAB_MAX / 8 || NS_CONSUMERS % (C / (16 / esz)) != 0) return false;
   sh->C = C; sh->H = H; sh->W = W; sh->pad = pad;
-  const int seg_max = NS_SLAB_MAX / (C * esz) - (width != W ? 2 * pad : 0);   // apply: the x span of a segment adds <= 2*pad
+  const int seg_max = slab_max / (C * esz) - (width != W ? 2 * pad : 0);   // apply: the x span of a segment adds <= 2*pad
   if (seg_max < 4 * pad + 1) return false;
   sh->nseg = (width + seg_max - 1) / seg_max;
   sh->seg = (width + sh->nseg - 1) / sh->nseg;
   sh->nseg = (width + sh->seg - 1) / sh->seg;
   const int slab_px = sh->seg + (width != W ? 2 * pad : 0);
   sh->slab_bytes = (slab_px * C * esz + 127) / 128 * 128;
-  sh->stages = NS_SMEM_BUDGET / (nslabs * sh->slab_bytes);
+  sh->stages = budget / (nslabs * sh->slab_bytes);
   if (sh->stages > NS_MAX_STAGES) sh->stages = NS_MAX_STAGES;
   if (sh->stages < 2) return false;
   // as many blocks per image as fit one wave of 2 blocks per SM; rows are split proportionally (7/8 rows each at
@@ -687,10 +688,12 @@ int instnorm_bwd_fused_staged(const ast_image* x, const float* mean, const float
   if (resident > 104e6) return 0;                    // would not survive in the 126 MB L2 next to the dx / skip-gradient writes
   NsShape sh;
   int nblk;
-  if (!ns_plan(&sh, x->n, x->c, x->h, x->w, pad, x->h, x->w, esz, nslabs, &nblk)) return 0;
-  if ((long long)nblk * x->n > 2ll * num_sms()) return 0;          // the counter barrier needs every block resident
   const size_t scratch = 2 * (size_t)(NS_CONSUMERS / (x->c / vec)) * x->c * sizeof(float);
-  while (sh.stages > 2 && (size_t)sh.stages * nslabs * sh.slab_bytes + scratch + 128 > (size_t)NS_SMEM_BUDGET + 8192) --sh.stages;
+  // the reduction scratch sits behind the ring (the producer refills the ring during the barrier): give the ring what is
+  // left of the per-block budget, with 8 KB slabs when three tensors are staged
+  if (!ns_plan(&sh, x->n, x->c, x->h, x->w, pad, x->h, x->w, esz, nslabs, &nblk, nslabs == 3 ? 8192 : NS_SLAB_MAX,
+               NS_SMEM_BUDGET + 8192 - (int)scratch)) return 0;
+  if ((long long)nblk * x->n > 2ll * num_sms()) return 0;          // the counter barrier needs every block resident
   const size_t smem = (size_t)sh.stages * nslabs * sh.slab_bytes + scratch + 128;
   if (smem > 110 * 1024) return 0;
   dim3 grid(nblk, x->n);

@@ -165,7 +165,7 @@ def test_cycle_gram_bank(ast):
     for t in (0, 1, 2, 4):
         single = ast.style_grams_single(vgg, paintings[t % 3], 2)
         for k, v in bank.target(t).items():
-            assert torch.equal(v, single[k][0])
+            assert rel(v, single[k][0]) < 1e-6           # split-K atomics: summation order differs run to run
     content = [weights.content_batch(2, 64, 2, step=i).cuda() for i in range(6)]
     for graph in (False, True):
         neta, _ = build(ast, "fast")

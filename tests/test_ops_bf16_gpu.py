@@ -107,11 +107,13 @@ def test_maxpool2_bwd_and_mask_add_bf16(env):
     assert_bf16_close(out, (a.double() + b.double()) * (mask > 0), "mask_add")
 
 
-@pytest.mark.parametrize("cin,cout,size,family", [(128, 128, 128, "conv_px"), (64, 64, 256, "conv_ws"),
-                                                   (256, 128, 64, "conv_px"), (512, 512, 32, "conv_tc")])
+@pytest.mark.parametrize("cin,cout,size,family", [(128, 128, 128, "conv_hx"), (64, 64, 256, "conv_ws"),
+                                                   (256, 128, 64, "conv_hx"), (512, 512, 32, "conv_hx"),
+                                                   (128, 64, 128, "conv_ws"), (512, 256, 33, "conv_hx")])
 def test_vgg_dgrad_with_add_and_mask_production_tiles(env, cin, cout, size, family):
     """Data gradient of a VGG 3x3 conv (train_cnn.py:54) with the tap-gradient add and the ReLU mask in the epilogue, bf16
-    gradients, at the image sizes of the B=32 step: conv_px (cout 128), conv_ws (conv1_2's 64->64 at 256^2), conv_tc."""
+    gradients, at the image sizes of the B=32 step: conv_hx (halo kernel, cout % 128 == 0), conv_ws (conv1_2's 64->64 at
+    256^2), conv_px (cout 64 with a filter too large for conv_ws); one ragged size (33) for the tile-edge predicates."""
     _lib, cg, ops = env
     torch.manual_seed(cin + size)
     n = 1
@@ -129,6 +131,32 @@ def test_vgg_dgrad_with_add_and_mask_production_tiles(env, cin, cout, size, fami
     ref = F.conv_transpose2d(g.double().cpu().permute(0, 3, 1, 2), bf(wt).double().cpu(), padding=1).permute(0, 2, 3, 1)
     ref = (ref + add.double().cpu()) * (mask.double().cpu() > 0)
     assert_bf16_close(out, ref, family)
+
+
+@pytest.mark.parametrize("cin,cout,size,family", [(64, 128, 130, "conv_px"), (32, 64, 258, "conv_ws"), (128, 128, 66, "conv_hx")])
+def test_transform_convs_with_fused_statistics(env, cin, cout, size, family):
+    """Forward convs of the TransformerNet on physically padded bf16 inputs (cnn.py:18-20 stride 2, :26-30 residual) with
+    the InstanceNorm sums accumulated by the epilogue: raw output to one bf16 rounding, mean / rstd against fp64."""
+    _lib, cg, ops = env
+    torch.manual_seed(cin + size)
+    n = 2
+    stride = 2 if family != "conv_hx" else 1
+    x = bf(torch.randn(n, size, size, cin, device="cuda"))
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5
+    launches = cg.conv_fwd(3, stride, 0, size, size)
+    ho = launches[0].mi
+    wp = ops.pack_weights(wt, launches, cout, cin, cin * 9, 9, 3, 1, torch.bfloat16)
+    raw = torch.full((n, ho, ho, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    sums = torch.zeros(2 * n * cout, dtype=torch.float64, device="cuda")
+    before = _lib.family_stats()
+    ops.conv_gather(x, wp, launches, raw, tensor=True, stats=sums)
+    delta = _lib.family_delta(before)
+    assert delta[family][0] == 1, {k: v[0] for k, v in delta.items() if v[0]}
+    mean, rstd = ops.instnorm_finalize(sums, n, cout, ho * ho)
+    y = F.conv2d(x.double().cpu().permute(0, 3, 1, 2), bf(wt).double().cpu(), stride=stride)
+    assert_bf16_close(raw, y.permute(0, 2, 3, 1), family)
+    assert rel(mean, y.mean(dim=(2, 3)).reshape(-1)) < 1e-4
+    assert rel(rstd, (y.var(dim=(2, 3), unbiased=False) + 1e-5).rsqrt().reshape(-1)) < 1e-5
 
 
 def test_fused_instnorm_statistics_survive_large_mean(env):
