@@ -176,6 +176,66 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
     // the split-K CTAs of one output all finish together: rotate each CTA's walk over (tap, column block) so that they
     // do not all hit the same addresses at the same moment
     const int nblk = p.bn / 32;
+    if (fin.enabled && p.ksplit == 1) {
+      // ---- single writer (no split-K): the Gram block is final in TMEM, so the whole style term is computed from the
+      // registers of the tcgen05.ld - scale, G stores, (G - S)^2, D - without atomics, tickets or a second pass.  A thread
+      // owns row m and 32 consecutive columns: the (m, n) stores are 128-byte runs per thread; for the mirrored (n, m)
+      // entries the 32 lanes of a warp hold 32 consecutive m of one n, i.e. one coalesced 128-byte store per column.
+      const int C = p.n_valid;
+      float* G = out + (long long)img_fixed * p.out_img_stride;
+      const float* S = fin.target ? fin.target + (long long)img_fixed * fin.target_img_stride : nullptr;
+      float* D = fin.dmat ? fin.dmat + (long long)img_fixed * p.out_img_stride : nullptr;
+      float part = 0.f;
+      for (int cb0 = 0; cb0 < nblk; ++cb0) {
+        const int nb0 = n0 + cb0 * 32;
+        if (nb0 + 31 < m0 + q * 32 || nb0 >= C) continue;          // warp-uniform: chunk strictly below this warp's rows
+        float v[32], sv[32];
+        tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(cb0 * 32), v);
+        const bool row_ok = m < p.m_valid;
+        if (S) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok && nb0 + e + 3 < C) t4 = __ldg(reinterpret_cast<const float4*>(S + (long long)m * C + nb0 + e));
+            sv[e] = t4.x; sv[e + 1] = t4.y; sv[e + 2] = t4.z; sv[e + 3] = t4.w;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = nb0 + e;
+          const float gv = v[e] * p.scale;
+          const bool up = row_ok && n < C && n >= m;
+          float dv = 0.f;
+          if (S && up) { dv = gv - sv[e]; part = fmaf(n > m ? 2.f : 1.f, dv * dv, part); }
+          v[e] = gv;
+          sv[e] = round_tf32(fin.d_scale * dv);
+          if (up && n > m) {                                       // mirrored entry: lanes = consecutive m
+            G[(long long)n * C + m] = gv;
+            if (D) D[(long long)n * C + m] = sv[e];
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const int n = nb0 + e;
+            if (n + 3 < C && n >= m) {                             // whole quad on / above the diagonal
+              *reinterpret_cast<float4*>(G + (long long)m * C + n) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              if (D) *reinterpret_cast<float4*>(D + (long long)m * C + n) = make_float4(sv[e], sv[e + 1], sv[e + 2], sv[e + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (n + k < C && n + k >= m) { G[(long long)m * C + n + k] = v[e + k]; if (D) D[(long long)m * C + n + k] = sv[e + k]; }
+            }
+          }
+        }
+      }
+      if (S && fin.loss) {
+        part = warp_sum(part);
+        if (lane == 0) s_red[warp - 2] = part;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) atomicAdd(fin.loss, (double)fin.loss_scale * (double)(s_red[0] + s_red[1] + s_red[2] + s_red[3]));
+      }
+    } else {
     const int rot = (int)(blockIdx.x % (unsigned)(nt * nblk));
     for (int it = 0; it < nt * nblk; ++it) {
       const int idx = (it + rot) % (nt * nblk);
@@ -280,6 +340,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
         }
       }
     }
+    }   // split-K (ticket) path
   }
 
   tc_fence_before();
@@ -525,6 +586,13 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   p.m_boxes = 128 / p.cb;
   const int n_pad = (cols->c + p.cb - 1) / p.cb * p.cb;
   p.bn = n_pad <= 256 ? n_pad : (n_pad % 256 == 0 ? 256 : (n_pad % 128 == 0 ? 128 : p.cb));
+  // Gram with the fused finish: 128-wide column blocks when that yields enough single-writer CTAs to fill the GPU without
+  // split-K (C = 256 at B = 32: 3 upper blocks x 32 images = 96 CTAs) - the finish then runs from registers
+  if (finp && upper_only && n_pad % 128 == 0 && n_pad >= 256) {
+    const int mb = (rows->c + 127) / 128, nb = n_pad / 128;
+    const long long upper_blocks = (long long)rows->n * (mb * nb - mb * (mb - 1) / 2);
+    if (upper_blocks * 10 >= num_sms() * 6) p.bn = 128;
+  }
   p.n_boxes = p.bn / p.cb;
   p.m_blocks = (rows->c + 127) / 128;
   p.n_blocks = (n_pad + p.bn - 1) / p.bn;
@@ -558,6 +626,7 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   const long long fixed = (long long)p.ngroups * p.m_blocks * p.n_blocks * (p.per_img ? p.n_img : 1);
   // one CTA per SM (200 KB of smem each): size the split-K so the whole grid is a single wave without a tail
   long long ks = num_sms() / fixed;
+  if (finp && fixed * 10 >= num_sms() * 6) ks = 1;     // enough single-writer CTAs: the register finish beats split-K + ticket
   if (ks < 1) ks = 1;
   if (ks > p.chunks_total) ks = p.chunks_total;
   p.chunks_per_cta = (int)((p.chunks_total + ks - 1) / ks);

@@ -174,17 +174,22 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     st.mask_r = p.so * mask.sh; st.mask_c = p.so * mask.sw;
     const int jlim = min(p.mj, (out.w - p.ox0 + p.so - 1) / p.so), ilim = min(p.mi, (out.h - p.oy0 + p.so - 1) / p.so);
     int as = 0; unsigned aph = 0;
+    double s1 = 0.0, s2 = 0.0;                     // running InstanceNorm sums of (image, channel): flushed when either changes
+    int s_img = -1, s_ch = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int slice, tj, ti, img;
       hx_tile(p, tile, slice, tj, ti, img);
       const int ch = slice * 128 + q * 32 + lane;
+      if (stats && (img != s_img || ch != s_ch)) {
+        if (s_img >= 0) { double* srow = stats + ((long long)s_img * p.cout + s_ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
+        s1 = s2 = 0.0; s_img = img; s_ch = ch;
+      }
       const float b = bias ? bias[ch] : 0.f;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * 256 + half * 128);
       const int j0 = tj * HX_TW;
       const int nvc = max(0, min(HX_TW, jlim - j0));
-      double s1 = 0.0, s2 = 0.0;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         const int r0 = half * 16 + (c0 >> 3);              // first tile row of this 32-column chunk
@@ -201,15 +206,11 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (nvr > 0 && nvc > 0)
           px_chunk<8>(v, off, st, nvr, nvc, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
       }
-      if (stats) {
-        double* srow = stats + ((long long)img * p.cout + ch) * 2;
-        atomicAdd(srow, s1);
-        atomicAdd(srow + 1, s2);
-      }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (stats && s_img >= 0) { double* srow = stats + ((long long)s_img * p.cout + s_ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
   }
 
   tc_fence_before();

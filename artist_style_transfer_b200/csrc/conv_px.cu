@@ -135,14 +135,19 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const bool ch_ok = ch < p.cout;
     const float b = (bias && ch_ok) ? bias[ch] : 0.f;
     int as = 0; unsigned aph = 0;
+    double s1 = 0.0, s2 = 0.0;                     // running InstanceNorm sums of this thread's channel over one image
+    int s_img = -1;
     for (long long pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
       const int img = (int)(pair / p.pairs_per_img);
+      if (stats && img != s_img) {                 // flush once per image, not once per tile (atomic contention)
+        if (s_img >= 0 && ch_ok) { double* srow = stats + ((long long)s_img * p.cout + ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
+        s1 = s2 = 0.0; s_img = img;
+      }
       const int sp = 2 * (int)(pair % p.pairs_per_img) + half;
       const int ti = sp / p.tiles_j, tj = sp - ti * p.tiles_j;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * 256 + half * 128);
-      double s1 = 0.0, s2 = 0.0;
       if (q * 32 < p.cout) {                       // warp-uniform: quarters beyond cout hold nothing
         const bool fast = (p.tw & 31) == 0;
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -179,16 +184,12 @@ conv_px_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             px_chunk<0>(v, off, st, 0, 0, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
           }
         }
-        if (stats && ch_ok) {
-          double* srow = stats + ((long long)img * p.cout + ch) * 2;
-          atomicAdd(srow, s1);
-          atomicAdd(srow + 1, s2);
-        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (stats && s_img >= 0 && ch_ok) { double* srow = stats + ((long long)s_img * p.cout + ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
   }
 
   tc_fence_before();

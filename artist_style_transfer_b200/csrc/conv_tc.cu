@@ -143,12 +143,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const int row = q * 32 + lane;
     const int ty = row / p.tw, tx = row % p.tw;
     int as = 0; unsigned aph = 0;
+    EpiStatAcc sacc;
+    sacc.reset(-1);
+    const int s_chunks = (p.bn - cpar * 32 + 63) / 64;          // 32-channel chunks this warp drains per tile
+    const bool s_run = stats && s_chunks <= 2 && p.n_tiles_n == 1;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long r = tile;
       const int nt = (int)(r % p.n_tiles_n); r /= p.n_tiles_n;
       const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
+      if (s_run && img != sacc.img) { sacc.flush(stats, p.cout_valid, cpar * 32, lane, s_chunks); sacc.reset(img); }
       const int i = ti * p.th + ty, j = tj * p.tw + tx;
       const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
       const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
@@ -164,7 +169,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (p.thin) {
           if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
         } else {
-          if (stats) tc_epi_stats(v, valid, stats + ((long long)img * p.cout_valid + co) * 2, lane);
+          if (stats) {
+            float su, sq;
+            tc_epi_stats_reduce(v, valid, lane, su, sq);
+            if (s_run) { const int k = (c0 - cpar * 32) >> 6; sacc.s[k & 1][0] += (double)su; sacc.s[k & 1][1] += (double)sq; }
+            else { double* row = stats + ((long long)img * p.cout_valid + co + lane) * 2; atomicAdd(row, (double)su); atomicAdd(row + 1, (double)sq); }
+          }
           // (a mask prefetch like conv_ws's was tried here: the extra registers slowed the unmasked layers more than
           // the masked deep VGG dgrads gained)
           tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
@@ -175,6 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (s_run) sacc.flush(stats, p.cout_valid, cpar * 32, lane, s_chunks);
   }
 
   tc_fence_before();

@@ -181,9 +181,9 @@ struct EpiRows { long long off[8]; };
 // butterfly (16+8+4+2+1 shuffles per quantity) leaves lane L with the sum over the warp's 32 rows of channel co+L,
 // which is added to stats[(img*C + co+L)*2 + {0,1}] (double) with one fire-and-forget atomic each.
 // The two partial sums cover only this warp's 32 pixels (fp32 is accurate enough there); the accumulation across the
-// plane runs in DOUBLE (atomicAdd on doubles, finalize in double), so E[x^2] - mean^2 does not cancel catastrophically
-// for planes with |mean| >> std (SURVEY section 7 "shifted sums or Welford-merge").
-__device__ __forceinline__ void tc_epi_stats(const float* v, bool valid, double* __restrict__ stats_row, int lane) {
+// plane runs in DOUBLE (per-thread running sums, atomicAdd on doubles, finalize in double), so E[x^2] - mean^2 does not
+// cancel catastrophically for planes with |mean| >> std (SURVEY section 7 "shifted sums or Welford-merge").
+__device__ __forceinline__ void tc_epi_stats_reduce(const float* v, bool valid, int lane, float& sum, float& sumsq) {
   float a[32], b[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) { a[e] = valid ? v[e] : 0.f; b[e] = a[e] * a[e]; }
@@ -198,9 +198,27 @@ __device__ __forceinline__ void tc_epi_stats(const float* v, bool valid, double*
       b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, half);
     }
   }
-  atomicAdd(stats_row + 2 * lane, (double)a[0]);
-  atomicAdd(stats_row + 2 * lane + 1, (double)b[0]);
+  sum = a[0]; sumsq = b[0];
 }
+// Per-thread running sums of the persistent epilogue: (sum x, sum x^2) of up to two 32-channel chunks, kept in DOUBLE across
+// the tiles of one image and flushed with one atomic per quantity when the image changes (a persistent CTA walks the tiles
+// of an image consecutively).  At 1080p a plane has ~16,000 tiles: flushing per tile made 33 M double atomics contend for
+// 512 addresses and doubled the time of the 32-channel layers.
+struct EpiStatAcc {
+  double s[2][2];
+  int img;
+  __device__ __forceinline__ void reset(int image) { s[0][0] = s[0][1] = s[1][0] = s[1][1] = 0.0; img = image; }
+  __device__ __forceinline__ void flush(double* __restrict__ stats, int cout, int co_first, int lane, int nchunks) {
+    if (img < 0) return;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k >= nchunks) break;
+      double* row = stats + ((long long)img * cout + co_first + k * 64 + lane) * 2;
+      atomicAdd(row, s[k][0]);
+      atomicAdd(row + 1, s[k][1]);
+    }
+  }
+};
 
 __device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

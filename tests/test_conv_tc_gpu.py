@@ -233,3 +233,33 @@ def test_conv_pooled_rejected_where_unsupported(env):
     yp = torch.empty(1, 4, 4, 512, device="cuda")
     with pytest.raises(RuntimeError, match="pooled"):
         ops.conv_gather(x, wp, cg.conv_fwd(3, 1, 1, 8, 8), y, tensor=True, pooled=yp)
+
+
+@pytest.mark.parametrize("c,h,w,n,shared", [(64, 32, 32, 2, True), (128, 16, 24, 3, False), (256, 16, 16, 2, True),
+                                            (512, 8, 8, 3, False), (256, 64, 64, 32, True), (512, 32, 32, 32, True),
+                                            (64, 13, 9, 1, False)])
+def test_gram_mse_fused(env, c, h, w, n, shared):
+    """ast_gram_mse (train_cnn.py:321-325 + :103-107 in one kernel): Gram, style-MSE numerator and the Gram-backward
+    weights D = d_scale (G - S) against torch fp64, for the split-K / ticket finish (C <= 128) and the single-writer
+    register finish (C >= 256 at enough images), shared and per-image targets."""
+    cg, ops = env
+    from oracle import port
+    torch.manual_seed(c + h + n)
+    f = tf32_round(torch.randn(n, h, w, c, device="cuda") * 2)
+    tgt = torch.randn(c, c, device="cuda") if shared else torch.randn(n, c, c, device="cuda")
+    tgt = (tgt + tgt.transpose(-1, -2)) / 2                       # style Grams are symmetric
+    g = torch.zeros(n, c, c, device="cuda")
+    counters = torch.zeros(n * 16, dtype=torch.int32, device="cuda")
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d = torch.full((n, c, c), float("nan"), device="cuda")
+    ops.gram_mse(f, tgt, g, counters, loss=loss, loss_scale=0.5, d=d, d_scale=3.0, tensor=True)
+    ref = port.gram(f.double().cpu().permute(0, 3, 1, 2))
+    diff = ref - tgt.double().cpu()
+    # fp32 TMEM accumulation over K = h*w pixels in ONE CTA (single-writer blocks): the tensor core's accumulate step
+    # truncates, so long sums of squares (the diagonal) drift by ~K/8 * 2^-25: 1e-5 up to K = 1024, 1e-4 at K = 4096
+    assert rel(g, ref) < (1e-5 if h * w <= 1024 else 1e-4), rel(g, ref)
+    assert float((g - g.transpose(1, 2)).abs().max()) == 0.0
+    assert abs(float(loss) - 0.5 * float((diff ** 2).sum())) < 1e-4 * 0.5 * float((diff ** 2).sum())
+    assert not torch.isnan(d).any()
+    assert rel(d, 3.0 * diff) < 1e-3                              # D is rounded to TF32 (it feeds a kind::tf32 conv)
+    assert float((d - d.transpose(1, 2)).abs().max()) == 0.0
