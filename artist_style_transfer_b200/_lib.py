@@ -32,7 +32,8 @@ class GatherGeom(ctypes.Structure):
                 ("oy0", ctypes.c_int32), ("ox0", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("flags", ctypes.c_int32),
                 ("dy", ctypes.c_int16 * AST_MAX_TAPS), ("dx", ctypes.c_int16 * AST_MAX_TAPS),
-                ("w_img_stride", ctypes.c_int64), ("stats", ctypes.c_void_p), ("pooled", ctypes.POINTER(Image))]
+                ("w_img_stride", ctypes.c_int64), ("stats", ctypes.c_void_p), ("pooled", ctypes.POINTER(Image)),
+                ("pool_codes", ctypes.POINTER(Image))]
 
 
 class PackMap(ctypes.Structure):
@@ -78,7 +79,7 @@ _SIGNATURES = {
                                _vp, _vp, _P(Image), _P(Image), _vp],
     "ast_instnorm_bwd": [_P(Image), _vp, _vp, _vp, _vp, _P(Image), ctypes.c_int32, _P(Image), ctypes.c_int32,
                          _vp, _vp, _vp, _P(Image), _P(Image), _vp],
-    "ast_maxpool2_fwd": [_P(Image), _P(Image), _vp],
+    "ast_maxpool2_fwd": [_P(Image), _P(Image), _P(Image), _vp],
     "ast_maxpool2_bwd": [_P(Image), _P(Image), _P(Image), _P(Image), _P(Image), _vp],
     "ast_gram": [_P(Image), _vp, ctypes.c_float, ctypes.c_int32, _vp],
     "ast_gram_mse": [_P(Image), _vp, ctypes.c_float, _vp, ctypes.c_int64, _vp, ctypes.c_float, _vp, ctypes.c_float, _vp,

@@ -41,7 +41,7 @@ template <int KIND, int MINB>
 __global__ void __launch_bounds__(WS_THREADS, MINB)
 conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const WsParams p,
                const float* __restrict__ bias, const Img add, const Img mask, const Img out,
-               double* __restrict__ stats, const Img pooled) {
+               double* __restrict__ stats, const Img pooled, const Img pcodes) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long pfull[WS_MAX_PBUF], pempty[WS_MAX_PBUF], tfull_bar[2], tempty_bar[2], wbar;
   __shared__ unsigned tmem_slot;
@@ -190,12 +190,35 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           if (pooled.ptr) {
             // nn.MaxPool2d(2, 2) of the finished values (v was updated in place): a tile row is 8 pixels and a warp owns 4
             // tile rows, so the 2x2 window of pixel (ty, tx) = lanes l, l^1 (x neighbour), l^8 (y neighbour), l^9
+            const bool lead = !(lane & 9) && i + 1 < p.mi && j + 1 < p.mj && co < p.cout;   // even (ty, tx), window inside
+            if (pcodes.ptr) {      // + the 1-byte window codes the backward needs instead of the activations
+              unsigned pk[8];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float m = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
-              v[e] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+              for (int e = 0; e < 32; ++e) {
+                const float b1 = __shfl_xor_sync(0xffffffffu, v[e], 1), c1 = __shfl_xor_sync(0xffffffffu, v[e], 8);
+                const float d1 = __shfl_xor_sync(0xffffffffu, v[e], 9);
+                int arg = 0; float m = v[e];
+                if (b1 > m) { m = b1; arg = 1; }
+                if (c1 > m) { m = c1; arg = 2; }
+                if (d1 > m) { m = d1; arg = 3; }
+                const unsigned code = (unsigned)arg | ((v[e] > 0.f) ? 4u : 0u) | ((b1 > 0.f) ? 8u : 0u) | ((c1 > 0.f) ? 16u : 0u) |
+                                      ((d1 > 0.f) ? 32u : 0u);
+                if ((e & 3) == 0) pk[e >> 2] = code; else pk[e >> 2] |= code << (8 * (e & 3));
+                v[e] = m;
+              }
+              if (lead) {
+                uint4* cp = reinterpret_cast<uint4*>(pcodes.ptr + img_off(pcodes, img, i >> 1, j >> 1, co));
+                cp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                cp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                float m = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
+                v[e] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+              }
             }
-            if (!(lane & 9) && i + 1 < p.mi && j + 1 < p.mj && co < p.cout) {   // even (ty, tx), window fully inside
+            if (lead) {
               const long long po = img_off(pooled, img, i >> 1, j >> 1, co);
 #pragma unroll
               for (int e = 0; e < 32; e += 4) st4_img(pooled, po + e, v + e);
@@ -233,6 +256,10 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
     AST_CHECK_ARG(q->n == in->n && q->h == g->mi / 2 && q->w == g->mj / 2 && q->c == out->c && q->sc == 1 &&
                   q->sw % 4 == 0 && q->sh % 4 == 0 && q->sn % 4 == 0 && ((uintptr_t)q->ptr & 15) == 0,
                   "conv_ws: pooled must be [n, mi/2, mj/2, cout] NHWC with 16-byte aligned pixels");
+    const ast_image* pc = g->pool_codes;
+    AST_CHECK_ARG(!pc || (pc->dtype == AST_U8 && same_shape(pc, q) && pc->sc == 1 && pc->sw % 16 == 0 && pc->sh % 16 == 0 &&
+                          pc->sn % 16 == 0 && ((uintptr_t)pc->ptr & 15) == 0 && pc->c % 32 == 0),
+                  "conv_ws: pool_codes must be uint8 [n, mi/2, mj/2, cout] NHWC with 16-byte aligned pixels");
   }
   const int esz = in->dtype == AST_F32 ? 4 : 2;
   int dy_min = 1 << 30, dy_max = -(1 << 30), dx_min = 1 << 30, dx_max = -(1 << 30);
@@ -306,10 +333,11 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   const int grid = (int)(p.total_tiles < max_ctas ? p.total_tiles : max_ctas);
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   Img pooli = g->pooled ? to_img(g->pooled) : null_img();
+  Img codei = (g->pooled && g->pool_codes) ? to_img(g->pool_codes) : null_img();
   cudaError_t e;
 #define WS_LAUNCH(K, B)                                                                                          \
   e = set_max_smem(conv_ws_kernel<K, B>, smem);                                                                   \
-  if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats, pooli)
+  if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats, pooli, codei)
   if (in->dtype == AST_BF16) {
     if (two) { WS_LAUNCH(0, 2); } else { WS_LAUNCH(0, 1); }
   } else {

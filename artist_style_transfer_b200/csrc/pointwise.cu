@@ -8,7 +8,15 @@ namespace ast {
 
 constexpr int NT = 256;
 
-__global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y) {
+__device__ __forceinline__ unsigned pool_code(float a, float b, float c, float d) {
+  int arg = 0; float m = a;
+  if (b > m) { m = b; arg = 1; }
+  if (c > m) { m = c; arg = 2; }
+  if (d > m) { m = d; arg = 3; }
+  return (unsigned)arg | ((a > 0.f) ? 4u : 0u) | ((b > 0.f) ? 8u : 0u) | ((c > 0.f) ? 16u : 0u) | ((d > 0.f) ? 32u : 0u);
+}
+
+__global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y, Img codes) {
   const int lanes = x.c / 4;
   const long long total = (long long)y.n * y.h * y.w * lanes;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
@@ -17,18 +25,50 @@ __global__ void __launch_bounds__(NT) maxpool2_fwd_kernel(Img x, Img y) {
     const int j = (int)(r % y.w); r /= y.w;
     const int i = (int)(r % y.h);
     const int n = (int)(r / y.h);
-    float m[4], v[4];
-    ld4_img(x, img_off(x, n, 2 * i, 2 * j, c), m);
-    ld4_img(x, img_off(x, n, 2 * i, 2 * j + 1, c), v);
+    float m[4], v0[4], v1[4], v2[4], v3[4];
+    ld4_img(x, img_off(x, n, 2 * i, 2 * j, c), v0);
+    ld4_img(x, img_off(x, n, 2 * i, 2 * j + 1, c), v1);
+    ld4_img(x, img_off(x, n, 2 * i + 1, 2 * j, c), v2);
+    ld4_img(x, img_off(x, n, 2 * i + 1, 2 * j + 1, c), v3);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = v[e] > m[e] ? v[e] : m[e];
-    ld4_img(x, img_off(x, n, 2 * i + 1, 2 * j, c), v);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = v[e] > m[e] ? v[e] : m[e];
-    ld4_img(x, img_off(x, n, 2 * i + 1, 2 * j + 1, c), v);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = v[e] > m[e] ? v[e] : m[e];
+    for (int e = 0; e < 4; ++e) m[e] = fmaxf(fmaxf(v0[e], v1[e]), fmaxf(v2[e], v3[e]));
     st4_img(y, img_off(y, n, i, j, c), m);
+    if (codes.ptr) {
+      unsigned pk = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk |= pool_code(v0[e], v1[e], v2[e], v3[e]) << (8 * e);
+      *reinterpret_cast<unsigned*>(codes.ptr + img_off(codes, n, i, j, c)) = pk;
+    }
+  }
+}
+
+// Backward of ReLU + MaxPool2d from the 1-byte window codes: 8 channels per thread (16-byte bf16 vectors).
+//   gx[2i+dy, 2j+dx] = (gadd[2i+dy, 2j+dx] + (arg == 2dy+dx ? gy[i, j] : 0)) * bit(2dy+dx)
+__global__ void __launch_bounds__(NT) maxpool2_bwd_codes_kernel(Img codes, Img gy, Img gadd, Img gx) {
+  const int lanes = gx.c / 8;
+  const long long total = (long long)gy.n * gy.h * gy.w * lanes;
+  for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+    const int c = (int)(idx % lanes) * 8;
+    long long r = idx / lanes;
+    const int j = (int)(r % gy.w); r /= gy.w;
+    const int i = (int)(r % gy.h);
+    const int n = (int)(r / gy.h);
+    const uint2 cw = *reinterpret_cast<const uint2*>(codes.ptr + img_off(codes, n, i, j, c));
+    float g[8];
+    ld4_img(gy, img_off(gy, n, i, j, c), g); ld4_img(gy, img_off(gy, n, i, j, c + 4), g + 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * i + (k >> 1), xx = 2 * j + (k & 1);
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (gadd.ptr) { ld4_img(gadd, img_off(gadd, n, yy, xx, c), o); ld4_img(gadd, img_off(gadd, n, yy, xx, c + 4), o + 4); }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const unsigned code = ((e < 4 ? cw.x : cw.y) >> (8 * (e & 3))) & 0xffu;
+        if ((int)(code & 3u) == k) o[e] += g[e];
+        o[e] = (code >> (2 + k)) & 1u ? o[e] : 0.f;
+      }
+      st4_img(gx, img_off(gx, n, yy, xx, c), o); st4_img(gx, img_off(gx, n, yy, xx, c + 4), o + 4);
+    }
   }
 }
 
@@ -242,23 +282,42 @@ __global__ void __launch_bounds__(NT) gram_finish_kernel(const float* __restrict
 
 using namespace ast;
 
-extern "C" int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, void* stream) {
+static bool codes_ok(const ast_image* codes, const ast_image* pooled_like) {
+  return codes->dtype == AST_U8 && same_shape(codes, pooled_like) && codes->sc == 1 && codes->c % 8 == 0 && codes->sw % 8 == 0 &&
+         codes->sh % 8 == 0 && codes->sn % 8 == 0 && ((uintptr_t)codes->ptr & 7) == 0;
+}
+
+extern "C" int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, const ast_image* codes, void* stream) {
   AST_CHECK_ARG(x && y, "ast_maxpool2_fwd: null argument");
   AST_CHECK_ARG(vec_ok(x) && vec_ok(y), "ast_maxpool2_fwd: needs NHWC, C %% 4 == 0");
   AST_CHECK_ARG(y->n == x->n && y->c == x->c && y->h == x->h / 2 && y->w == x->w / 2, "ast_maxpool2_fwd: y must be (h/2, w/2)");
+  AST_CHECK_ARG(!codes || codes_ok(codes, y), "ast_maxpool2_fwd: codes must be uint8 NHWC [n, h/2, w/2, c], C %% 8 == 0");
   const long long total = (long long)y->n * y->h * y->w * (y->c / 4);
   if (total == 0) return 0;
-  launch_k(maxpool2_fwd_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(y));
+  launch_k(maxpool2_fwd_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(y), codes ? to_img(codes) : null_img());
   count_launch();
   count_work(FAM_POOL, 0.0, img_bytes(x) + img_bytes(y));
   AST_CUDA_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ast_maxpool2_bwd(const ast_image* x, const ast_image* y, const ast_image* gy, const ast_image* gadd,
+extern "C" int ast_maxpool2_bwd(const ast_image* x, const ast_image* codes, const ast_image* gy, const ast_image* gadd,
                                 const ast_image* gx, void* stream) {
-  (void)y;
-  AST_CHECK_ARG(x && gy && gx, "ast_maxpool2_bwd: null argument");
+  AST_CHECK_ARG((x || codes) && gy && gx, "ast_maxpool2_bwd: null argument");
+  if (codes) {
+    AST_CHECK_ARG(codes_ok(codes, gy), "ast_maxpool2_bwd: codes must be uint8 NHWC shaped like gy, C %% 8 == 0");
+    AST_CHECK_ARG(gx->n == gy->n && gx->c == gy->c && gx->h == 2 * gy->h && gx->w == 2 * gy->w,
+                  "ast_maxpool2_bwd: the code path needs even h, w (gx = 2 x gy)");
+    AST_CHECK_ARG(vec_ok(gy) && vec_ok(gx) && (!gadd || (vec_ok(gadd) && same_shape(gadd, gx))), "ast_maxpool2_bwd: needs NHWC, C %% 4 == 0");
+    const long long tot = (long long)gy->n * gy->h * gy->w * (gy->c / 8);
+    if (tot == 0) return 0;
+    launch_k(maxpool2_bwd_codes_kernel, blocks_for(tot), NT, 0, (cudaStream_t)stream, to_img(codes), to_img(gy),
+             gadd ? to_img(gadd) : null_img(), to_img(gx));
+    count_launch();
+    count_work(FAM_POOL, 0.0, img_bytes(codes) + img_bytes(gy) + img_bytes(gadd) + img_bytes(gx));
+    AST_CUDA_LAUNCH_CHECK();
+    return 0;
+  }
   AST_CHECK_ARG(vec_ok(x) && vec_ok(gy) && vec_ok(gx) && (!gadd || vec_ok(gadd)), "ast_maxpool2_bwd: needs NHWC, C %% 4 == 0");
   AST_CHECK_ARG(gy->n == x->n && gy->c == x->c && gy->h == x->h / 2 && gy->w == x->w / 2, "ast_maxpool2_bwd: gy must be (h/2, w/2)");
   AST_CHECK_ARG(same_shape(gx, x) && (!gadd || same_shape(gadd, x)), "ast_maxpool2_bwd: gx/gadd shape");

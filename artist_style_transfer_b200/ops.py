@@ -55,7 +55,7 @@ def profile_end():
     return out
 
 
-def _geom(launch, flags=0, w_img_stride=0, stats=None, pooled=None):
+def _geom(launch, flags=0, w_img_stride=0, stats=None, pooled=None, pool_codes=None):
     g = GatherGeom()
     g.mi, g.mj, g.si, g.so, g.oy0, g.ox0 = launch.mi, launch.mj, launch.si, launch.so, launch.oy0, launch.ox0
     g.ntaps = len(launch.taps)
@@ -68,6 +68,9 @@ def _geom(launch, flags=0, w_img_stride=0, stats=None, pooled=None):
     if pooled is not None:
         g._pooled_img = pooled                      # keep the ctypes struct alive as long as the geometry
         g.pooled = _lib.ctypes.pointer(pooled)
+    if pool_codes is not None:
+        g._codes_img = pool_codes
+        g.pool_codes = _lib.ctypes.pointer(pool_codes)
     return g
 
 
@@ -153,18 +156,20 @@ def tc_eligible(x, cout):
 
 def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False,
                 reflect=False, tensor=False, w_img_stride=0, round_tf32=False, stats=None, pooled=None,
-                pool_only=False):
+                pool_only=False, pool_codes=None):
     """Run every launch of an op. x/out/add/mask: (N,H,W,C)-ordered tensors; wpacked: [taps][cout][cin].
-    pooled: optional (N,H/2,W/2,C) tensor receiving MaxPool2d(2,2) of the result (weight-stationary kernel only)."""
+    pooled: optional (N,H/2,W/2,C) tensor receiving MaxPool2d(2,2) of the result (weight-stationary kernel only);
+    pool_codes: optional uint8 (N,H/2,W/2,C) window codes for the pooling backward (include/ast.h)."""
     lib = _lib.load()
     flags = ((CONV_RELU if relu else 0) | (CONV_REFLECT if reflect else 0) | (CONV_TENSOR if tensor else 0)
              | (CONV_ROUND_TF32 if round_tf32 else 0) | (_lib.CONV_POOL_ONLY if pool_only else 0))
     xi, oi, ai, mi = image(x), image(out), image(add), image(mask)
     pooled = image(pooled)
+    pool_codes = image(pool_codes)
     cout, cin = wpacked.shape[-2], wpacked.shape[-1]
     esz = wpacked.element_size()
     for l in launches:
-        g = _geom(l, flags, w_img_stride, stats, pooled)
+        g = _geom(l, flags, w_img_stride, stats, pooled, pool_codes)
         wp = _lib.ctypes.c_void_p(wpacked.data_ptr() + l.woff * cout * cin * esz)
         check(lib.ast_conv_gather(ref(xi), wp, ptr(bias), ptr(in_shift), ref(ai), ref(mi), ref(oi), ref(g),
                                   stream_ptr()), "ast_conv_gather")
@@ -238,18 +243,20 @@ def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, 
     return s12
 
 
-def _maxpool2_fwd_impl(x):
+def _maxpool2_fwd_impl(x, codes=None):
     n, h, w, c = x.shape
     y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
-    xi, yi = image(x), image(y)
-    check(_lib.load().ast_maxpool2_fwd(ref(xi), ref(yi), stream_ptr()), "ast_maxpool2_fwd")
+    xi, yi, ci = image(x), image(y), image(codes)
+    check(_lib.load().ast_maxpool2_fwd(ref(xi), ref(yi), ref(ci), stream_ptr()), "ast_maxpool2_fwd")
     return y
 
 
-def _maxpool2_bwd_impl(x, gy, gadd=None):
-    gx = torch.empty(x.shape, dtype=gy.dtype, device=x.device)
-    xi, gyi, gai, gxi = image(x), image(gy), image(gadd), image(gx)
-    check(_lib.load().ast_maxpool2_bwd(ref(xi), None, ref(gyi), ref(gai), ref(gxi), stream_ptr()), "ast_maxpool2_bwd")
+def _maxpool2_bwd_impl(x, gy, gadd=None, codes=None):
+    n, hp, wp, c = gy.shape
+    shape = x.shape if x is not None else (n, 2 * hp, 2 * wp, c)
+    gx = torch.empty(shape, dtype=gy.dtype, device=gy.device)
+    xi, gyi, gai, gxi, ci = image(x if codes is None else None), image(gy), image(gadd), image(gx), image(codes)
+    check(_lib.load().ast_maxpool2_bwd(ref(xi), ref(ci), ref(gyi), ref(gai), ref(gxi), stream_ptr()), "ast_maxpool2_bwd")
     return gx
 
 
@@ -295,14 +302,14 @@ def pack_weights(w, launches, a, b, s_a, s_b, s_u, s_v, dtype):
 
 
 def conv_gather(x, wpacked, launches, out, bias=None, in_shift=None, add=None, mask=None, relu=False, reflect=False,
-                tensor=False, w_img_stride=0, round_tf32=False, stats=None, pooled=None, pool_only=False):
+                tensor=False, w_img_stride=0, round_tf32=False, stats=None, pooled=None, pool_only=False, pool_codes=None):
     label = "conv_gather_tc" if tensor else "conv_gather_simt"
     if PROFILE_DETAIL and _prof is not None:
         label += f"|{tuple(x.shape)}->{tuple(out.shape)} taps={sum(len(l.taps) for l in launches)} {str(x.dtype)[6:]}"
     with _timed(label):
         return _conv_gather_impl(x, wpacked, launches, out, bias=bias, in_shift=in_shift, add=add, mask=mask, relu=relu,
                                  reflect=reflect, tensor=tensor, w_img_stride=w_img_stride, round_tf32=round_tf32,
-                                 stats=stats, pooled=pooled, pool_only=pool_only)
+                                 stats=stats, pooled=pooled, pool_only=pool_only, pool_codes=pool_codes)
 
 
 def wgrad_gather(x, gout, launches, dw, s_co, s_ci, s_u, s_v, reflect=False, tensor=False):
@@ -332,14 +339,16 @@ def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal
                                   zeroed=zeroed, arrive=arrive)
 
 
-def maxpool2_fwd(x):
+def maxpool2_fwd(x, codes=None):
+    """MaxPool2d(2,2); codes: optional uint8 (N,H/2,W/2,C) output with the window codes the backward can use instead of x."""
     with _timed(_pw("maxpool_fwd", x)):
-        return _maxpool2_fwd_impl(x)
+        return _maxpool2_fwd_impl(x, codes=codes)
 
 
-def maxpool2_bwd(x, gy, gadd=None):
-    with _timed(_pw("maxpool_bwd", x)):
-        return _maxpool2_bwd_impl(x, gy, gadd=gadd)
+def maxpool2_bwd(x, gy, gadd=None, codes=None):
+    """gx = (route(gy) + gadd) * (x > 0); with `codes` (from the forward) x is not read (and may be None)."""
+    with _timed(_pw("maxpool_bwd", gy)):
+        return _maxpool2_bwd_impl(x, gy, gadd=gadd, codes=codes)
 
 
 def gram(x, scale, tensor=False):

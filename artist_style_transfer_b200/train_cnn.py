@@ -45,83 +45,152 @@ def _vgg_layout():
     return layers
 
 
+def _vgg_forward(x, module, upto, shift, only_last, need_grad):
+    """conv3x3(pad 1)+ReLU / maxpool chain up to `upto` on NHWC buffers.  Returns (taps [(idx, NHWC tensor)], plan, tensor)
+    where plan = [(idx, kind, input, output, pool codes)] is what `_vgg_backward` walks."""
+    if not x.is_cuda:
+        raise RuntimeError("VGG16 kernels run on CUDA only (no CPU fallback)")
+    tensor = module._mode() == "fast" and _lib.has_tc_conv()
+    x32 = x.detach()
+    if x32.dtype not in (torch.float32, torch.uint8):      # uint8 images are widened inside conv1_1's loader
+        x32 = x32.to(torch.float32)
+    n, _, h, w = x32.shape
+    dev = x32.device
+    cur = x32.permute(0, 2, 3, 1)            # NCHW tensor described as an (N,H,W,C) view; conv1_1 reads it directly
+    taps, plan = [], []
+    pooled_next, codes_next = None, None
+    packed = module._packed(tensor)
+    for idx, kind, cin, cout in module._layout:
+        if idx > upto:
+            break
+        if kind == "conv" and idx == 0 and tensor:
+            # conv1_1 on the tensor cores: fold the 3 horizontal taps (and the mean shift, applied before the
+            # zero padding like train_cnn.py:300-301) into a 16-channel TF32 tensor, then a 3-tap vertical conv
+            xr = torch.empty((n, h, w, 16), dtype=torch.float32, device=dev)
+            ops.row_im2col(cur, xr, 3, 1, 1, 0, False, shift=shift, round_tf32=True)
+            launches = [cg.Launch(h, w, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]
+            out = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev)
+            wp, bias = packed[idx]
+            ops.conv_gather(xr, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True)
+            plan.append((idx, "conv", cur, out, None))
+            cur = out
+        elif kind == "conv":
+            if cur.dtype == torch.uint8:        # strict mode: the FFMA conv reads fp32
+                f32 = torch.empty(cur.shape, dtype=torch.float32, device=dev)
+                ops.copy_image(cur, f32)
+                cur = f32
+            launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
+            out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
+            wp, bias = packed[idx]
+            use_tc = tensor and ops.tc_eligible(cur, cout)
+            # conv1_2 -> ReLU -> MaxPool2d: the weight-stationary kernel also writes the pooled tensor (saves the pool
+            # kernel's 537 MB read at B=32) and, when a backward will follow, the 1-byte window codes it needs instead
+            # of the activations; when nothing needs the full-resolution relu1_2 (no-grad content branch asking only
+            # for its last tap) it is not even stored
+            fuse_pool = (use_tc and cin == 64 and cout == 64 and idx + 2 <= upto
+                         and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0)
+            if fuse_pool:
+                hp, wp_ = cur.shape[1] // 2, cur.shape[2] // 2
+                pooled_next = torch.empty((n, hp, wp_, cout), dtype=torch.float32, device=dev)
+                codes_next = torch.empty((n, hp, wp_, cout), dtype=torch.uint8, device=dev) if need_grad else None
+                skip_full = only_last and not need_grad
+                ops.conv_gather(cur, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True,
+                                pooled=pooled_next, pool_only=skip_full, pool_codes=codes_next)
+                if skip_full:
+                    out = None
+            else:
+                ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None, relu=True,
+                                tensor=use_tc, round_tf32=tensor)
+            plan.append((idx, "conv", cur, out, None))
+            cur = out
+        elif kind == "pool":
+            codes = None
+            if pooled_next is not None:
+                out, codes, pooled_next, codes_next = pooled_next, codes_next, None, None
+            else:
+                if need_grad and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0 and cur.shape[3] % 8 == 0:
+                    codes = torch.empty((n, cur.shape[1] // 2, cur.shape[2] // 2, cur.shape[3]), dtype=torch.uint8, device=dev)
+                out = ops.maxpool2_fwd(cur, codes=codes)
+            plan.append((idx, "pool", cur, out, codes))
+            cur = out
+        if idx in _TAPS and cur is not None:
+            taps.append((idx, cur))
+    if only_last:
+        taps = taps[-1:]
+    return taps, plan, tensor
+
+
+def _vgg_backward(module, plan, tensor, tapg):
+    """Data gradient of the chain w.r.t. its input image.  tapg: {tap index: NHWC gradient (fp32 or bf16, contiguous)}."""
+    # fast mode: the gradient chain through the frozen VGG runs in bf16 (fp32 accumulation), like the transform
+    # net's backward; the forward taps, Grams and losses keep TF32 (parity is stated on those).
+    bf16_bwd = tensor
+    gdt = torch.bfloat16 if bf16_bwd else torch.float32
+    packed = module._packed_dgrad(tensor, bf16_bwd)
+    g = None            # gradient w.r.t. the OUTPUT of the current plan entry (already ReLU-masked for convs)
+    gx = None
+    for pos in reversed(range(len(plan))):
+        idx, kind, xin, out, codes = plan[pos]
+        if kind == "pool":
+            if g is None:
+                continue
+            # out = pool(xin); xin is the ReLU output of the conv before: route + add its tap grad + mask.  With the
+            # forward's window codes the activations are not re-read (1 byte per window instead of 4 x fp32)
+            prev_relu_idx = idx - 1
+            g = ops.maxpool2_bwd(xin, g, tapg.pop(prev_relu_idx, None), codes=codes)
+            continue
+        relu_idx = idx + 1
+        if relu_idx in tapg:   # tap gradient not yet folded in (only when no pool/conv consumer did it)
+            t = tapg.pop(relu_idx)
+            m = torch.empty(t.shape, dtype=gdt, device=t.device)
+            ops.mask_add(t, g, out, m)       # (tap grad + downstream grad) * (relu out > 0)
+            g = m
+        if g is None:
+            continue
+        # g is d/d(relu out) masked == d/d(conv out).  dgrad to the conv input:
+        if idx == 0:
+            gx = torch.empty((out.shape[0], 3, out.shape[1], out.shape[2]), dtype=torch.float32, device=g.device)
+            if tensor and g.dtype == torch.bfloat16:
+                # d(image) of conv1_1 as 3 VERTICAL taps whose 9 (of 32) output channels are the partial sums of the
+                # 3 horizontal taps x 3 image channels, finished by ast_fold_rows - 12 instead of 36 N=32 MMAs per
+                # 128 pixels and no strided 3-channel epilogue:
+                #   P[a][u][kx][ci] = sum_{ky,co} g[a-ky+1][u][co] W[co][ci][ky][kx],  gx[a][b][ci] = sum_kx P[a][b-kx+1][kx][ci]
+                hh, ww = out.shape[1], out.shape[2]
+                part = torch.empty((out.shape[0], hh, ww + 2, 32), dtype=torch.float32, device=g.device)
+                taps = [(1 - ky, -1) for ky in range(3)]
+                lv = [cg.Launch(hh, ww + 2, 1, 1, 0, 0, taps, [(ky, 0) for ky in range(3)], 0)]
+                ops.conv_gather(g, module._packed_conv11_vdgrad(g.dtype), lv, part, tensor=True)
+                ops.fold_rows(part, gx.permute(0, 2, 3, 1), 3)
+            else:
+                launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
+                ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1), tensor=tensor)
+            break
+        launches = cg.conv_dgrad(3, 1, 1, xin.shape[1], xin.shape[2])
+        gin = torch.empty(xin.shape, dtype=gdt, device=g.device)
+        # the conv input is either a ReLU output (mask here, add its tap grad) or a pool output (no mask)
+        prev_kind = plan[pos - 1][1]
+        use_tc = tensor and ops.tc_eligible(g, xin.shape[3])
+        if prev_kind == "conv":
+            ops.conv_gather(g, packed[idx], launches, gin, add=tapg.pop(idx - 1, None), mask=xin, tensor=use_tc,
+                            round_tf32=tensor and not bf16_bwd)
+        else:
+            ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc, round_tf32=tensor and not bf16_bwd)
+        g = gin
+    return gx
+
+
 class _VGGFunction(torch.autograd.Function):
-    """conv3x3(pad 1)+ReLU / maxpool chain up to `upto`, returning the tapped activations (NCHW views)."""
+    """VGG16.forward as an autograd node returning the tapped activations (NCHW views)."""
 
     @staticmethod
     def forward(ctx, x, module, upto, shift, only_last, *weights):
-        if not x.is_cuda:
-            raise RuntimeError("VGG16 kernels run on CUDA only (no CPU fallback)")
-        tensor = module._mode() == "fast" and _lib.has_tc_conv()
-        x32 = x.detach()
-        if x32.dtype not in (torch.float32, torch.uint8):      # uint8 images are widened inside conv1_1's loader
-            x32 = x32.to(torch.float32)
-        n, _, h, w = x32.shape
-        dev = x32.device
-        cur = x32.permute(0, 2, 3, 1)            # NCHW tensor described as an (N,H,W,C) view; conv1_1 reads it directly
-        acts, taps, plan = {}, [], []
-        pooled_next = None
-        packed = module._packed(tensor)
-        for idx, kind, cin, cout in module._layout:
-            if idx > upto:
-                break
-            if kind == "conv" and idx == 0 and tensor:
-                # conv1_1 on the tensor cores: fold the 3 horizontal taps (and the mean shift, applied before the
-                # zero padding like train_cnn.py:300-301) into a 16-channel TF32 tensor, then a 3-tap vertical conv
-                xr = torch.empty((n, h, w, 16), dtype=torch.float32, device=dev)
-                ops.row_im2col(cur, xr, 3, 1, 1, 0, False, shift=shift, round_tf32=True)
-                launches = [cg.Launch(h, w, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]
-                out = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev)
-                wp, bias = packed[idx]
-                ops.conv_gather(xr, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True)
-                plan.append((idx, "conv", cur, out))
-                cur = out
-            elif kind == "conv":
-                if cur.dtype == torch.uint8:        # strict mode: the FFMA conv reads fp32
-                    f32 = torch.empty(cur.shape, dtype=torch.float32, device=dev)
-                    ops.copy_image(cur, f32)
-                    cur = f32
-                launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
-                out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
-                wp, bias = packed[idx]
-                use_tc = tensor and ops.tc_eligible(cur, cout)
-                # conv1_2 -> ReLU -> MaxPool2d: the weight-stationary kernel also writes the pooled tensor (saves the pool
-                # kernel's 537 MB read at B=32); when nothing needs the full-resolution relu1_2 (no-grad content branch
-                # asking only for its last tap) it is not even stored
-                fuse_pool = (use_tc and cin == 64 and cout == 64 and idx + 2 <= upto
-                             and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0)
-                if fuse_pool:
-                    pooled_next = torch.empty((n, cur.shape[1] // 2, cur.shape[2] // 2, cout), dtype=torch.float32, device=dev)
-                    skip_full = only_last and not ctx.needs_input_grad[0]
-                    ops.conv_gather(cur, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True,
-                                    pooled=pooled_next, pool_only=skip_full)
-                    if skip_full:
-                        out = None
-                else:
-                    ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None, relu=True,
-                                    tensor=use_tc, round_tf32=tensor)
-                plan.append((idx, "conv", cur, out))
-                cur = out
-            elif kind == "pool":
-                if pooled_next is not None:
-                    out, pooled_next = pooled_next, None
-                else:
-                    out = ops.maxpool2_fwd(cur)
-                plan.append((idx, "pool", cur, out))
-                cur = out
-            if idx in _TAPS and cur is not None:
-                taps.append((idx, cur))
+        taps, plan, tensor = _vgg_forward(x, module, upto, shift, only_last, ctx.needs_input_grad[0])
         ctx.module, ctx.plan, ctx.tensor = module, plan, tensor
         ctx.tap_idx = [i for i, _ in taps]
-        if only_last:
-            taps = taps[-1:]
-            ctx.tap_idx = ctx.tap_idx[-1:]
-        outs = tuple(t.permute(0, 3, 1, 2) for _, t in taps)
-        return outs
+        return tuple(t.permute(0, 3, 1, 2) for _, t in taps)
 
     @staticmethod
     def backward(ctx, *gtaps):
-        module, plan, tensor = ctx.module, ctx.plan, ctx.tensor
         tapg = {}
         for idx, g in zip(ctx.tap_idx, gtaps):
             if g is not None:
@@ -131,61 +200,9 @@ class _VGGFunction(torch.autograd.Function):
                     ops.copy_image(g, gc)
                     g = gc
                 tapg[idx] = g
-        # fast mode: the gradient chain through the frozen VGG runs in bf16 (fp32 accumulation), like the transform
-        # net's backward; the forward taps, Grams and losses keep TF32 (parity is stated on those).
-        bf16_bwd = tensor
-        gdt = torch.bfloat16 if bf16_bwd else torch.float32
-        packed = module._packed_dgrad(tensor, bf16_bwd)
-        g = None            # gradient w.r.t. the OUTPUT of the current plan entry (already ReLU-masked for convs)
-        gx = None
-        for pos in reversed(range(len(plan))):
-            idx, kind, xin, out = plan[pos]
-            if kind == "pool":
-                if g is None:
-                    continue
-                # out = pool(xin); xin is the ReLU output of the conv before: route + add its tap grad + mask
-                prev_relu_idx = idx - 1
-                g = ops.maxpool2_bwd(xin, g, tapg.pop(prev_relu_idx, None))
-                continue
-            relu_idx = idx + 1
-            if relu_idx in tapg:   # tap gradient not yet folded in (only when no pool/conv consumer did it)
-                t = tapg.pop(relu_idx)
-                m = torch.empty(t.shape, dtype=gdt, device=t.device)
-                ops.mask_add(t, g, out, m)       # (tap grad + downstream grad) * (relu out > 0)
-                g = m
-            if g is None:
-                continue
-            # g is d/d(relu out) masked == d/d(conv out).  dgrad to the conv input:
-            if idx == 0:
-                gx = torch.empty((out.shape[0], 3, out.shape[1], out.shape[2]), dtype=torch.float32, device=g.device)
-                if tensor and g.dtype == torch.bfloat16:
-                    # d(image) of conv1_1 as 3 VERTICAL taps whose 9 (of 32) output channels are the partial sums of the
-                    # 3 horizontal taps x 3 image channels, finished by ast_fold_rows - 12 instead of 36 N=32 MMAs per
-                    # 128 pixels and no strided 3-channel epilogue:
-                    #   P[a][u][kx][ci] = sum_{ky,co} g[a-ky+1][u][co] W[co][ci][ky][kx],  gx[a][b][ci] = sum_kx P[a][b-kx+1][kx][ci]
-                    hh, ww = out.shape[1], out.shape[2]
-                    part = torch.empty((out.shape[0], hh, ww + 2, 32), dtype=torch.float32, device=g.device)
-                    taps = [(1 - ky, -1) for ky in range(3)]
-                    lv = [cg.Launch(hh, ww + 2, 1, 1, 0, 0, taps, [(ky, 0) for ky in range(3)], 0)]
-                    ops.conv_gather(g, module._packed_conv11_vdgrad(g.dtype), lv, part, tensor=True)
-                    ops.fold_rows(part, gx.permute(0, 2, 3, 1), 3)
-                else:
-                    launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
-                    ops.conv_gather(g, packed[idx], launches, gx.permute(0, 2, 3, 1), tensor=tensor)
-                break
-            launches = cg.conv_dgrad(3, 1, 1, xin.shape[1], xin.shape[2])
-            gin = torch.empty(xin.shape, dtype=gdt, device=g.device)
-            # the conv input is either a ReLU output (mask here, add its tap grad) or a pool output (no mask)
-            prev_kind = plan[pos - 1][1]
-            use_tc = tensor and ops.tc_eligible(g, xin.shape[3])
-            if prev_kind == "conv":
-                ops.conv_gather(g, packed[idx], launches, gin, add=tapg.pop(idx - 1, None), mask=xin, tensor=use_tc,
-                                round_tf32=tensor and not bf16_bwd)
-            else:
-                ops.conv_gather(g, packed[idx], launches, gin, tensor=use_tc, round_tf32=tensor and not bf16_bwd)
-            g = gin
+        gx = _vgg_backward(ctx.module, ctx.plan, ctx.tensor, tapg)
         ctx.plan = None
-        return (gx, None, None, None, None) + tuple(None for _ in module._weights())
+        return (gx, None, None, None, None) + tuple(None for _ in ctx.module._weights())
 
 
 class VGG16(nn.Module, _cnn._Precision):
@@ -419,82 +436,126 @@ def mse_loss(a, b, weight=1.0):
     return _MSEFunction.apply(a, b, weight)
 
 
-class _PerceptualLossFunction(torch.autograd.Function):
-    """The whole loss side of train_cnn.py:307-329 as ONE autograd node over the four VGG taps of the generated batch.
+def _loss_forward(names, feats, targets, content_feat, content_weight, style_weight, fast, need_grad):
+    """Loss side of train_cnn.py:307-329 over the VGG taps of the generated batch.  feats: NCHW-shaped tensors (any strides).
 
-    Per tap, ONE kernel (ast_gram_mse) computes the upper triangle of the Gram on the tensor cores and - in the finishing
-    CTA of every block - the style-MSE contribution and D = 4 w_s (G - S) / (B C^2 CHW), the symmetric per-image 1x1
-    weights of the Gram backward dF = D F.  The content term on relu2_2 (train_cnn.py:307-308) is one
-    MSE pass producing loss and gradient; the backward adds that gradient inside the epilogue of relu2_2's Gram-backward
-    convolution.  unit_grad=True promises that the upstream gradients of both losses are exactly 1 (perceptual_step calls
-    total.backward() itself with total = content + style): nothing is rescaled.
-    Returns (content_loss, style_loss, grams...) - the Grams are exposed for inspection / tests (no gradient).
+    Per tap, ONE kernel (ast_gram_mse) computes the upper triangle of the Gram on the tensor cores and - in its finishing
+    step - the style-MSE contribution and D = 4 w_s (G - S) / (B C^2 CHW), the symmetric per-image 1x1 weights of the Gram
+    backward dF = D F.  The content term on relu2_2 (train_cnn.py:307-308) is one MSE pass producing
+    loss and gradient.  Returns (content loss 1-elem fp32, style loss 1-elem fp64, [Gram], state for `_loss_backward`).
     """
+    dev = feats[0].device
+    b = feats[0].shape[0]
+    n_taps = len(feats)
+    sizes = [b * f.shape[1] * f.shape[1] for f in feats]
+    cnt = b * _lib.GRAM_COUNTERS_PER_IMAGE
+    # one zero fill: [style loss (one fp64), content loss, pad | Gram 0..n | ticket counters 0..n (int32 views)]
+    zeros = torch.zeros(4 + sum(sizes) + n_taps * cnt, dtype=torch.float32, device=dev)
+    style_acc, content_acc = zeros[:2].view(torch.float64), zeros[2:3]
+    off = 4
+    grams, dmats, saved = [], [], []
+    content_grad = None
+    for i, f in enumerate(feats):
+        _, c, h, w = f.shape
+        fv = f.detach()
+        if fv.dtype not in (torch.float32, torch.bfloat16):
+            fv = fv.float()
+        xv = fv.permute(0, 2, 3, 1)
+        g = zeros[off:off + sizes[i]].view(b, c, c)
+        off += sizes[i]
+        counters = zeros[4 + sum(sizes) + i * cnt:4 + sum(sizes) + (i + 1) * cnt].view(torch.int32)
+        d = torch.empty((b, c, c), dtype=torch.float32, device=dev) if need_grad else None
+        tgt = targets[i].detach()
+        if tgt.dtype != torch.float32:
+            tgt = tgt.float()
+        ops.gram_mse(xv, tgt, g, counters, loss=style_acc, loss_scale=float(style_weight) / (b * c * c), d=d,
+                     d_scale=4.0 * float(style_weight) / (float(b) * c * c * c * h * w),
+                     tensor=fast and b > 0 and ops.tc_contract_eligible(xv, xv))
+        if names[i] == "relu2_2" and content_feat is not None:                       # train_cnn.py:307-308
+            numel = f.numel()
+            content_grad = torch.empty(xv.shape, dtype=torch.float32, device=dev) if need_grad else None
+            ops.mse(xv, content_feat.detach().permute(0, 2, 3, 1), content_acc, float(content_weight) / numel,
+                    content_grad, 2.0 * float(content_weight) / numel)
+        grams.append(g)
+        dmats.append(d)
+        saved.append(fv)
+    return content_acc, style_acc, grams, (names, saved, dmats, content_grad, fast)
+
+
+def _loss_backward(state, g_content, g_style, unit_grad, out_dtype):
+    """dF per tap as NHWC tensors of `out_dtype`: a 1x1 gather-conv with per-image C x C weights D (+ the content gradient
+    in the epilogue of relu2_2's).  unit_grad: the upstream gradients of both losses are exactly 1 - nothing is rescaled."""
+    names, feats, dmats, content_grad, fast = state
+    outs = []
+    for i, fv in enumerate(feats):
+        b, c, h, w = fv.shape
+        x = fv.permute(0, 2, 3, 1)
+        d = dmats[i]
+        cgrad = content_grad if names[i] == "relu2_2" else None
+        if not unit_grad:
+            d = d * g_style
+            cgrad = None if cgrad is None else cgrad * g_content
+        if d.dtype != fv.dtype:
+            d = d.to(fv.dtype)
+        out = torch.empty((b, h, w, c), dtype=out_dtype, device=fv.device)
+        ops.conv_gather(x, d.view(b, 1, c, c), cg.conv_fwd(1, 1, 0, h, w), out, add=cgrad, w_img_stride=c * c,
+                        tensor=fast and x.is_contiguous() and ops.tc_eligible(x, c), round_tf32=fast and out_dtype == torch.float32)
+        outs.append(out)
+    return outs
+
+
+class _PerceptualLossFunction(torch.autograd.Function):
+    """`_loss_forward` / `_loss_backward` as ONE autograd node over externally computed VGG taps (the drop-in call sites:
+    `vgg(generated)` then the losses).  Returns (content_loss, style_loss, grams...) - the Grams are for inspection (no grad)."""
 
     @staticmethod
     def forward(ctx, content_feat, content_weight, style_weight, fast, unit_grad, n_taps, *rest):
-        feats, targets = rest[:n_taps], rest[n_taps:2 * n_taps]
-        names = rest[2 * n_taps]
-        dev = feats[0].device
-        b = feats[0].shape[0]
-        sizes = [b * f.shape[1] * f.shape[1] for f in feats]
-        cnt = b * _lib.GRAM_COUNTERS_PER_IMAGE
-        # one zero fill: [style loss (one fp64), content loss, pad | Gram 0..n | ticket counters 0..n (int32 views)]
-        zeros = torch.zeros(4 + sum(sizes) + n_taps * cnt, dtype=torch.float32, device=dev)
-        style_acc, content_acc = zeros[:2].view(torch.float64), zeros[2:3]
-        off = 4
-        grams, dmats, saved = [], [], []
+        feats, targets, names = rest[:n_taps], rest[n_taps:2 * n_taps], rest[2 * n_taps]
         need_grad = any(ctx.needs_input_grad[6:6 + n_taps])
-        content_grad = None
-        for i, f in enumerate(feats):
-            _, c, h, w = f.shape
-            fv = f.detach()
-            if fv.dtype not in (torch.float32, torch.bfloat16):
-                fv = fv.float()
-            xv = fv.permute(0, 2, 3, 1)
-            g = zeros[off:off + sizes[i]].view(b, c, c)
-            off += sizes[i]
-            counters = zeros[4 + sum(sizes) + i * cnt:4 + sum(sizes) + (i + 1) * cnt].view(torch.int32)
-            d = torch.empty((b, c, c), dtype=torch.float32, device=dev) if need_grad else None
-            tgt = targets[i].detach()
-            if tgt.dtype != torch.float32:
-                tgt = tgt.float()
-            ops.gram_mse(xv, tgt, g, counters, loss=style_acc, loss_scale=float(style_weight) / (b * c * c), d=d,
-                         d_scale=4.0 * float(style_weight) / (float(b) * c * c * c * h * w),
-                         tensor=fast and b > 0 and ops.tc_contract_eligible(xv, xv))
-            if names[i] == "relu2_2" and content_feat is not None:                       # train_cnn.py:307-308
-                numel = f.numel()
-                content_grad = torch.empty(xv.shape, dtype=torch.float32, device=dev) if need_grad else None
-                ops.mse(xv, content_feat.detach().permute(0, 2, 3, 1), content_acc, float(content_weight) / numel,
-                        content_grad, 2.0 * float(content_weight) / numel)
-            grams.append(g)
-            dmats.append(d)
-            saved.append(fv)
-        ctx.feats, ctx.dmats, ctx.content_grad, ctx.names = saved, dmats, content_grad, names
-        ctx.fast, ctx.unit_grad, ctx.n_taps = fast, unit_grad, n_taps
+        content_acc, style_acc, grams, ctx.state = _loss_forward(names, feats, targets, content_feat, content_weight,
+                                                                 style_weight, fast, need_grad)
+        ctx.unit_grad, ctx.n_taps = unit_grad, n_taps
         ctx.mark_non_differentiable(*grams)
         return (content_acc[0], style_acc[0].to(torch.float32), *grams)
 
     @staticmethod
     def backward(ctx, g_content, g_style, *_):
-        outs = []
-        for i, fv in enumerate(ctx.feats):
-            b, c, h, w = fv.shape
-            x = fv.permute(0, 2, 3, 1)
-            d = ctx.dmats[i]
-            cgrad = ctx.content_grad if ctx.names[i] == "relu2_2" else None
-            if not ctx.unit_grad:
-                d = d * g_style
-                cgrad = None if cgrad is None else cgrad * g_content
-            if d.dtype != fv.dtype:
-                d = d.to(fv.dtype)
-            out = torch.empty((b, h, w, c), dtype=torch.float32, device=fv.device)
-            # dF = D F: a 1x1 gather-conv with per-image C x C weights (+ the content gradient in its epilogue)
-            ops.conv_gather(x, d.view(b, 1, c, c), cg.conv_fwd(1, 1, 0, h, w), out, add=cgrad, w_img_stride=c * c,
-                            tensor=ctx.fast and x.is_contiguous() and ops.tc_eligible(x, c), round_tf32=ctx.fast)
-            outs.append(out.permute(0, 3, 1, 2))
-        ctx.feats = ctx.dmats = ctx.content_grad = None
-        return (None, None, None, None, None, None, *outs, *([None] * (ctx.n_taps + 1)))
+        outs = _loss_backward(ctx.state, g_content, g_style, ctx.unit_grad, torch.float32)
+        ctx.state = None
+        return (None, None, None, None, None, None, *[o.permute(0, 3, 1, 2) for o in outs], *([None] * (ctx.n_taps + 1)))
+
+
+class _VGGPerceptualFunction(torch.autograd.Function):
+    """VGG16(generated) + the whole loss side as ONE autograd node: the training path of `perceptual_step`.
+
+    Nothing between the taps and the losses has to be an autograd tensor, so the tap gradients stay in the kernels' own
+    format: bf16 NHWC (half the bytes of the fp32 NCHW gradients autograd would demand), consumed directly by the epilogues
+    of the VGG data-gradient convolutions and the pooling backward (which reads the forward's 1-byte window codes, not the
+    activations).  Same arithmetic as `vgg(x)` followed by `perceptual_losses(...)`."""
+
+    @staticmethod
+    def forward(ctx, generated, module, shift, content_feat, content_weight, style_weight, unit_grad, names, *targets):
+        need_grad = ctx.needs_input_grad[0]
+        last = max(k for k, v in _TAPS.items() if v in names)
+        taps, plan, tensor = _vgg_forward(generated, module, last, shift, False, need_grad)
+        feats = [t.permute(0, 3, 1, 2) for idx, t in taps if _TAPS[idx] in names]
+        tap_names = tuple(_TAPS[idx] for idx, _ in taps if _TAPS[idx] in names)
+        tgt = dict(zip(names, targets))
+        content_acc, style_acc, grams, state = _loss_forward(tap_names, feats, [tgt[k] for k in tap_names], content_feat,
+                                                             content_weight, style_weight, module._mode() == "fast", need_grad)
+        ctx.module, ctx.plan, ctx.tensor, ctx.state = module, plan, tensor, state
+        ctx.tap_idx = [idx for idx, _ in taps if _TAPS[idx] in names]
+        ctx.unit_grad = unit_grad
+        ctx.mark_non_differentiable(*grams)
+        return (content_acc[0], style_acc[0].to(torch.float32), *grams)
+
+    @staticmethod
+    def backward(ctx, g_content, g_style, *_):
+        gdt = torch.bfloat16 if ctx.tensor else torch.float32
+        outs = _loss_backward(ctx.state, g_content, g_style, ctx.unit_grad, gdt)
+        gx = _vgg_backward(ctx.module, ctx.plan, ctx.tensor, dict(zip(ctx.tap_idx, outs)))
+        ctx.plan = ctx.state = None
+        return (gx, None, None, None, None, None, None, None, *([None] * len(ctx.tap_idx)))
 
 
 def perceptual_losses(gen_feats, content_feat, style_gram, content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT,
@@ -522,9 +583,10 @@ def perceptual_step(transfer, vgg, content_batch, style_gram, content_weight=CON
     generated = transfer(content_batch)                                        # :299
     with torch.no_grad():
         content_feat = vgg(content_batch, shift=shift, upto="relu2_2", only_last=True)["relu2_2"]   # :300
-    gen_feats = vgg(generated, shift=shift)                                    # :301
-    content_loss, style_loss, _ = perceptual_losses(gen_feats, content_feat, style_gram, content_weight, style_weight,
-                                                    fast=vgg._mode() == "fast", unit_grad=bool(backward))   # :307-325
+    names = tuple(k for k in _TAPS.values() if k in style_gram)
+    out = _VGGPerceptualFunction.apply(generated, vgg, shift, content_feat, content_weight, style_weight, bool(backward),
+                                       names, *[style_gram[k] for k in names])                   # :301, :307-325
+    content_loss, style_loss = out[0], out[1]
     total = content_loss + style_loss                                          # :329
     if backward:
         total.backward()                                                       # :333

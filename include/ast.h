@@ -72,6 +72,10 @@ typedef struct {
                               train_cnn.py:54,72-73).  Plain stride-1 launches (so = 1, no phase offset) of the
                               weight-stationary tensor-core kernel only: any other request is an error.  With
                               AST_CONV_POOL_ONLY the full-resolution `out` is not written (no-grad content branch). */
+  const ast_image* pool_codes; /* optional, with `pooled`: uint8 [n, mi/2, mj/2, cout], one byte per pooling window and channel
+                              = everything the backward of ReLU + MaxPool2d needs from the forward activations:
+                              bits 0-1 = arg max position k = 2*dy + dx (first maximum wins, like ATen), bits 2-5 = (x_k > 0)
+                              for k = 0..3.  ast_maxpool2_bwd then reads 1 byte instead of four fp32 activations. */
 } ast_gather_geom;
 
 #define AST_CONV_RELU     1   /* epilogue max(v,0)                       (nn.ReLU, train_cnn.py VGG idx 1,3,...)   */
@@ -157,8 +161,10 @@ int ast_instnorm_bwd(const ast_image* x, const float* mean, const float* rstd, c
 
 /* nn.MaxPool2d(2,2) of torchvision vgg16.features idx 4/9/16 and its backward fused with the tap-gradient add
  * and the ReLU mask of the producing layer:  gx = (route(gy) + gadd) * (x > 0). */
-int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, void* stream);
-int ast_maxpool2_bwd(const ast_image* x, const ast_image* y, const ast_image* gy, const ast_image* gadd,
+/* codes (optional, uint8 [n, h/2, w/2, c]): see ast_gather_geom.pool_codes - written by the forward, and accepted by the
+ * backward INSTEAD of x (x may then be NULL; h and w must be even). */
+int ast_maxpool2_fwd(const ast_image* x, const ast_image* y, const ast_image* codes, void* stream);
+int ast_maxpool2_bwd(const ast_image* x, const ast_image* codes, const ast_image* gy, const ast_image* gadd,
                      const ast_image* gx, void* stream);
 
 /* gram(), train_cnn.py:103-107:  G[n] = F[n] F[n]^T * scale, F = x viewed as (c, h*w).  G fp32 [n][c][c], zeroed here. */

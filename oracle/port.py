@@ -81,14 +81,14 @@ def gram(f):
     return torch.bmm(m, m.transpose(1, 2)) / (c * h * w)
 
 
-def neg_mean(dtype=torch.float32):
-    return torch.tensor(IMAGENET_NEG_MEAN, dtype=torch.float32).reshape(1, 3, 1, 1).to(dtype)
+def neg_mean(dtype=torch.float32, device=None):
+    return torch.tensor(IMAGENET_NEG_MEAN, dtype=torch.float32, device=device).reshape(1, 3, 1, 1).to(dtype)
 
 
 # ----------------------------------------------------------------------------- style-gram setup
 def style_grams_single(style_img, vgg_sd, batch):
     """'random'/'average' setup, train_cnn.py:184-190,199-204: one image expanded to the batch."""
-    st = style_img + neg_mean(style_img.dtype)                            # (3,H,W)+(1,3,1,1) -> (1,3,H,W)
+    st = style_img + neg_mean(style_img.dtype, style_img.device)                            # (3,H,W)+(1,3,1,1) -> (1,3,H,W)
     feats = vgg_features(st.expand(batch, -1, -1, -1), vgg_sd)
     return {k: gram(v) for k, v in feats.items()}
 
@@ -102,7 +102,7 @@ def style_grams_smartaverage(paintings, vgg_sd, batch, mode="reference"):
     """
     acc = None
     for p in paintings:
-        st = p + neg_mean(p.dtype)
+        st = p + neg_mean(p.dtype, p.device)
         feats = vgg_features(st.expand(batch, -1, -1, -1), vgg_sd)
         cur = feats if mode == "reference" else {k: gram(v) for k, v in feats.items()}
         if acc is None:
@@ -120,7 +120,7 @@ def style_grams_smartaverage(paintings, vgg_sd, batch, mode="reference"):
 def perceptual_losses(generated, content, vgg_sd, style_gram,
                       content_weight=CONTENT_WEIGHT, style_weight=STYLE_WEIGHT):
     """train_cnn.py:300-329 (method != 3): returns content, style, total and the generated Grams."""
-    nm = neg_mean(generated.dtype)
+    nm = neg_mean(generated.dtype, generated.device)
     cf = vgg_features(content + nm, vgg_sd)                               # :300
     gf = vgg_features(generated + nm, vgg_sd)                             # :301
     content_loss = F.mse_loss(gf["relu2_2"], cf["relu2_2"]) * content_weight  # :307-308

@@ -1,0 +1,76 @@
+"""Turn `ncu -i <report> --page raw --csv` output into the committed per-kernel summary (CSV with the metrics the judge
+reads) and profiles/r02_traffic.json (DRAM bytes per launch per kernel family, read by bench.py's roofline entries).
+
+usage: python profiles/summarize_ncu.py raw.csv order.txt out_prefix
+order.txt = the "N launch(es): description" lines printed by scratch/prof_families.py (same order as the report)."""
+import csv
+import json
+import re
+import sys
+
+KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__cycles_elapsed.avg.per_second",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem"]
+FAMILY = (("conv_hx_kernel", "conv_hx"), ("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"),
+          ("conv_tc_kernel", "conv_tc"), ("contract_thin", "wgrad_thin"), ("contract_tc_kernel<(int)0>", "wgrad_tc"),
+          ("contract_tc_kernel<(int)1>", "gram_tc"), ("contract_tc_kernel<0>", "wgrad_tc"), ("contract_tc_kernel<1>", "gram_tc"),
+          ("in_apply", "in_apply"), ("in_bwd", "in_bwd"), ("maxpool2_bwd", "pool"), ("mse", "mse"), ("adam_pack", "optim"),
+          ("row_im2col", "pointwise"), ("fold_rows", "pointwise"))
+
+
+def main():
+    raw, order, prefix = sys.argv[1:4]
+    rows = list(csv.reader(open(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    labels = []
+    for line in open(order):
+        m = re.match(r"(\d+) launch\(es\): (.*)", line.strip())
+        if m:
+            labels += [m.group(2)] * int(m.group(1))
+    skip = ("adam_tick", "FillFunctor", "memset", "Memset")
+    kernels = [d for d in data if len(d) == len(hdr) and not any(s in d[idx["Kernel Name"]] for s in skip)]
+    out_rows, traffic = [], {}
+    li = 0
+    for d in kernels:
+        name = d[idx["Kernel Name"]]
+        label = labels[li] if li < len(labels) else ""
+        li += 1
+        row = {"kernel": name.split("(")[0], "case": label}
+        for k in KEEP:
+            if k in idx:
+                row[f"{k} [{units[idx[k]]}]"] = d[idx[k]]
+        out_rows.append(row)
+        fam = next((f for key, f in FAMILY if key in name), None)
+        try:
+            rd, wr = float(d[idx["dram__bytes_read.sum"]]), float(d[idx["dram__bytes_write.sum"]])
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd *= scale[units[idx["dram__bytes_read.sum"]]]
+            wr *= scale[units[idx["dram__bytes_write.sum"]]]
+        except (KeyError, ValueError):
+            continue
+        if fam and fam not in traffic:          # first (= most representative, listed first) launch of a family
+            traffic[fam] = {"dram_bytes_per_launch": rd + wr, "case": label,
+                            "src": f"{prefix}_ncu.csv ({name.split('(')[0]}; ncu --set full --clock-control none, cold caches)"}
+    cols = list(out_rows[0].keys())
+    with open(prefix + "_ncu.csv", "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=cols)
+        w.writeheader()
+        for r in out_rows:
+            w.writerow(r)
+    json.dump(traffic, open("profiles/r02_traffic.json", "w"), indent=1)
+    for r in out_rows:
+        t = [v for k, v in r.items() if k.startswith("gpu__time_duration")][0]
+        tp = [v for k, v in r.items() if k.startswith("sm__pipe_tensor_cycles_active")]
+        dr = [v for k, v in r.items() if k.startswith("gpu__dram_throughput")]
+        print(f"{t:>10s} us  tensor {tp[0] if tp else '-':>6s} %  dram {dr[0] if dr else '-':>6s} %  {r['kernel'][:34]:34s} {r['case'][:70]}")
+
+
+if __name__ == "__main__":
+    main()

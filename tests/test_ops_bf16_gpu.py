@@ -107,6 +107,37 @@ def test_maxpool2_bwd_and_mask_add_bf16(env):
     assert_bf16_close(out, (a.double() + b.double()) * (mask > 0), "mask_add")
 
 
+def test_pool_window_codes(env):
+    """The 1-byte window codes (arg max + four ReLU bits) written by ast_maxpool2_fwd and by the fused conv1_2 + pool
+    epilogue let ast_maxpool2_bwd run without the activations: identical results to the path that re-reads x."""
+    _lib, cg, ops = env
+    torch.manual_seed(5)
+    n, h, w, c = 2, 64, 48, 128
+    x = torch.relu(torch.randn(n, h, w, c, device="cuda"))
+    x[0, :2, :2, :] = 0.0                                       # ties (all-zero windows): first maximum wins, mask off
+    gy = bf(torch.randn(n, h // 2, w // 2, c, device="cuda"))
+    gadd = bf(torch.randn(n, h, w, c, device="cuda"))
+    codes = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda")
+    y = ops.maxpool2_fwd(x, codes=codes)
+    assert torch.equal(y, F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))
+    ref = ops.maxpool2_bwd(x, gy, gadd)
+    got = ops.maxpool2_bwd(None, gy, gadd, codes=codes)
+    assert torch.equal(ref, got)
+    assert torch.equal(ops.maxpool2_bwd(x, gy, None), ops.maxpool2_bwd(None, gy, None, codes=codes))
+    # the fused conv + ReLU + pool epilogue writes the same codes as the stand-alone pooling kernel on its own output
+    xin = torch.randn(n, 32, 40, 64, device="cuda")
+    wt = torch.randn(64, 64, 3, 3, device="cuda") / 24
+    launches = cg.conv_fwd(3, 1, 1, 32, 40)
+    wp = ops.pack_weights(wt, launches, 64, 64, 64 * 9, 9, 3, 1, ops.TF32)
+    full = torch.empty(n, 32, 40, 64, device="cuda")
+    pooled = torch.empty(n, 16, 20, 64, device="cuda")
+    fcodes = torch.empty(n, 16, 20, 64, dtype=torch.uint8, device="cuda")
+    ops.conv_gather(xin, wp, launches, full, relu=True, tensor=True, round_tf32=True, pooled=pooled, pool_codes=fcodes)
+    codes2 = torch.empty_like(fcodes)
+    pooled2 = ops.maxpool2_fwd(full, codes=codes2)
+    assert torch.equal(pooled, pooled2) and torch.equal(fcodes, codes2)
+
+
 @pytest.mark.parametrize("cin,cout,size,family", [(128, 128, 128, "conv_hx"), (64, 64, 256, "conv_ws"),
                                                    (256, 128, 64, "conv_hx"), (512, 512, 32, "conv_hx"),
                                                    (128, 64, 128, "conv_ws"), (512, 256, 33, "conv_hx")])
