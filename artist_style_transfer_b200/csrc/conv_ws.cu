@@ -23,6 +23,7 @@ struct WsParams {
   int so, oy0, ox0;
   int dy_min, dx_min, ph, pw;
   int patch_bytes, patch_tx, n_pbuf, w_tile_bytes, w_total_bytes;
+  int T;                   // sub-tiles (16 rows x 8 px each, stacked vertically) per pipeline step / TMEM stage
   unsigned idesc, layout_type, sbo;
   long long total_tiles;
   short tdy[AST_MAX_TAPS];
@@ -50,7 +51,8 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   unsigned char* smem_w = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_p = smem_w + ((p.w_total_bytes + 1023) & ~1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned tmem_cols = (2 * p.bn <= 32) ? 32 : (2 * p.bn <= 64) ? 64 : (2 * p.bn <= 128) ? 128 : (2 * p.bn <= 256) ? 256 : 512;
+  const int acc_cols = p.T * p.bn;               // one TMEM stage: T accumulators of bn columns
+  const unsigned tmem_cols = (2 * acc_cols <= 32) ? 32 : (2 * acc_cols <= 64) ? 64 : (2 * acc_cols <= 128) ? 128 : (2 * acc_cols <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
@@ -89,7 +91,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const int tj = (int)(r % p.tiles_j); r /= p.tiles_j;
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
-      const int x0 = tj * WS_TW + p.dx_min, y0 = ti * WS_TH + p.dy_min;
+      const int x0 = tj * WS_TW + p.dx_min, y0 = ti * WS_TH * p.T + p.dy_min;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&pempty[s], ph ^ 1);
         if (lane == 0) {
@@ -112,7 +114,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
-      const unsigned d_tmem = tmem_base + (unsigned)(as * p.bn);
+      const unsigned d_tmem0 = tmem_base + (unsigned)(as * acc_cols);
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&pfull[s], ph);
         tc_fence_after();
@@ -121,18 +123,23 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           const unsigned p_lo = ((smem_u32(smem_p + (size_t)s * p.patch_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
           const unsigned w_lo = ((w_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
           const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
-          unsigned acc = kc > 0 ? 1u : 0u;
+          const unsigned sub16 = (unsigned)(WS_TH * p.pw * p.rowb) >> 4;      // patch offset of the next sub-tile (16 rows down)
 #pragma unroll 1
-          for (int t = 0; t < p.ntaps; ++t) {
-            const unsigned a_lo = p_lo + s_tapoff[t];
-            const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
-            tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
-            tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
-            if (kmma == 4) {
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
-              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
+          for (int st = 0; st < p.T; ++st) {
+            const unsigned d_tmem = d_tmem0 + (unsigned)(st * p.bn);
+            unsigned acc = kc > 0 ? 1u : 0u;
+#pragma unroll 1
+            for (int t = 0; t < p.ntaps; ++t) {
+              const unsigned a_lo = p_lo + s_tapoff[t] + (unsigned)st * sub16;
+              const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
+              tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
+              if (kmma == 4) {
+                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 4, hi_a), pack_desc(b_lo + 4, hi_b), p.idesc, 1u);
+                tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
+              }
+              acc = 1u;
             }
-            acc = 1u;
           }
           tc_commit(&pempty[s]);
           if (kc == p.kchunks - 1) tc_commit(&tfull_bar[as]);
@@ -160,68 +167,69 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const int ti = (int)(r % p.tiles_i);
       const int img = (int)(r / p.tiles_i);
       if (s_run && img != sacc.img) { sacc.flush(stats, p.cout_valid, cpar * 32, lane, s_chunks); sacc.reset(img); }
-      const int i = ti * WS_TH + ty, j = tj * WS_TW + tx;
-      const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
-      const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
-      float pm[32];                                   // mask of this warp's first chunk, loaded while the MMAs still run
-      const bool use_pm = MINB == 1 && mask.ptr && !p.thin && cpar * 32 < p.bn;   // (the 2-CTA build has no registers to spare)
-      if (use_pm) tc_epi_prefetch_mask(mask, img, oy, ox, cpar * 32, valid, pm);
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * p.bn);
-      EpiRows rows;
-      const bool store_out = !(p.flags & AST_CONV_POOL_ONLY);
-      if (!p.thin) tc_epi_row_offsets((valid && store_out) ? img_off(out, img, oy, ox, 0) : -1, lane, out.dtype == AST_F32, rows);
-      for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
-        float v[32];
-        tc_ld32(taddr0 + c0, v);
-        const int co = c0;
-        if (p.thin) {
-          if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
-        } else {
-          if (stats) {
-            float su, sq;
-            tc_epi_stats_reduce(v, valid, lane, su, sq);
-            if (s_run) { const int k = (c0 - cpar * 32) >> 6; sacc.s[k & 1][0] += (double)su; sacc.s[k & 1][1] += (double)sq; }
-            else { double* row = stats + ((long long)img * p.cout_valid + co + lane) * 2; atomicAdd(row, (double)su); atomicAdd(row + 1, (double)sq); }
-          }
-          tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
-                                  pm, use_pm && c0 == cpar * 32);
-          if (pooled.ptr) {
-            // nn.MaxPool2d(2, 2) of the finished values (v was updated in place): a tile row is 8 pixels and a warp owns 4
-            // tile rows, so the 2x2 window of pixel (ty, tx) = lanes l, l^1 (x neighbour), l^8 (y neighbour), l^9
-            const bool lead = !(lane & 9) && i + 1 < p.mi && j + 1 < p.mj && co < p.cout;   // even (ty, tx), window inside
-            if (pcodes.ptr) {      // + the 1-byte window codes the backward needs instead of the activations
-              unsigned pk[8];
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                const float b1 = __shfl_xor_sync(0xffffffffu, v[e], 1), c1 = __shfl_xor_sync(0xffffffffu, v[e], 8);
-                const float d1 = __shfl_xor_sync(0xffffffffu, v[e], 9);
-                int arg = 0; float m = v[e];
-                if (b1 > m) { m = b1; arg = 1; }
-                if (c1 > m) { m = c1; arg = 2; }
-                if (d1 > m) { m = d1; arg = 3; }
-                const unsigned code = (unsigned)arg | ((v[e] > 0.f) ? 4u : 0u) | ((b1 > 0.f) ? 8u : 0u) | ((c1 > 0.f) ? 16u : 0u) |
-                                      ((d1 > 0.f) ? 32u : 0u);
-                if ((e & 3) == 0) pk[e >> 2] = code; else pk[e >> 2] |= code << (8 * (e & 3));
-                v[e] = m;
+      for (int st = 0; st < p.T; ++st) {
+        const int i = (ti * p.T + st) * WS_TH + ty, j = tj * WS_TW + tx;
+        const int oy = p.oy0 + p.so * i, ox = p.ox0 + p.so * j;
+        const bool valid = i < p.mi && j < p.mj && oy < out.h && ox < out.w;
+        float pm[32];                                   // mask of this warp's first chunk, loaded while the MMAs still run
+        const bool use_pm = MINB == 1 && mask.ptr && !p.thin && cpar * 32 < p.bn;   // (the 2-CTA build has no registers to spare)
+        if (use_pm) tc_epi_prefetch_mask(mask, img, oy, ox, cpar * 32, valid, pm);
+        if (st == 0) { mbar_wait(&tfull_bar[as], aph); tc_fence_after(); }
+        const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * acc_cols + st * p.bn);
+        EpiRows rows;
+        const bool store_out = !(p.flags & AST_CONV_POOL_ONLY);
+        if (!p.thin) tc_epi_row_offsets((valid && store_out) ? img_off(out, img, oy, ox, 0) : -1, lane, out.dtype == AST_F32, rows);
+        for (int c0 = cpar * 32; c0 < p.bn; c0 += 64) {
+          float v[32];
+          tc_ld32(taddr0 + c0, v);
+          const int co = c0;
+          if (p.thin) {
+            if (valid) tc_epilogue32(v, co, img, oy, ox, true, p.cout, p.cout_valid, p.flags, bias, add, mask, out);
+          } else {
+            if (stats) {
+              float su, sq;
+              tc_epi_stats_reduce(v, valid, lane, su, sq);
+              if (s_run) { const int k = (c0 - cpar * 32) >> 6; sacc.s[k & 1][0] += (double)su; sacc.s[k & 1][1] += (double)sq; }
+              else { double* row = stats + ((long long)img * p.cout_valid + co + lane) * 2; atomicAdd(row, (double)su); atomicAdd(row + 1, (double)sq); }
+            }
+            tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
+                                    pm, use_pm && c0 == cpar * 32);
+            if (pooled.ptr) {
+              // nn.MaxPool2d(2, 2) of the finished values (v was updated in place): a tile row is 8 pixels and a warp owns 4
+              // tile rows, so the 2x2 window of pixel (ty, tx) = lanes l, l^1 (x neighbour), l^8 (y neighbour), l^9
+              const bool lead = !(lane & 9) && i + 1 < p.mi && j + 1 < p.mj && co < p.cout;   // even (ty, tx), window inside
+              if (pcodes.ptr) {      // + the 1-byte window codes the backward needs instead of the activations
+                unsigned pk[8];
+  #pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  const float b1 = __shfl_xor_sync(0xffffffffu, v[e], 1), c1 = __shfl_xor_sync(0xffffffffu, v[e], 8);
+                  const float d1 = __shfl_xor_sync(0xffffffffu, v[e], 9);
+                  int arg = 0; float m = v[e];
+                  if (b1 > m) { m = b1; arg = 1; }
+                  if (c1 > m) { m = c1; arg = 2; }
+                  if (d1 > m) { m = d1; arg = 3; }
+                  const unsigned code = (unsigned)arg | ((v[e] > 0.f) ? 4u : 0u) | ((b1 > 0.f) ? 8u : 0u) | ((c1 > 0.f) ? 16u : 0u) |
+                                        ((d1 > 0.f) ? 32u : 0u);
+                  if ((e & 3) == 0) pk[e >> 2] = code; else pk[e >> 2] |= code << (8 * (e & 3));
+                  v[e] = m;
+                }
+                if (lead) {
+                  uint4* cp = reinterpret_cast<uint4*>(pcodes.ptr + img_off(pcodes, img, i >> 1, j >> 1, co));
+                  cp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  cp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+              } else {
+  #pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  float m = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
+                  v[e] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                }
               }
               if (lead) {
-                uint4* cp = reinterpret_cast<uint4*>(pcodes.ptr + img_off(pcodes, img, i >> 1, j >> 1, co));
-                cp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                cp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                const long long po = img_off(pooled, img, i >> 1, j >> 1, co);
+  #pragma unroll
+                for (int e = 0; e < 32; e += 4) st4_img(pooled, po + e, v + e);
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                float m = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
-                v[e] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-              }
-            }
-            if (lead) {
-              const long long po = img_off(pooled, img, i >> 1, j >> 1, co);
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) st4_img(pooled, po + e, v + e);
             }
           }
         }
@@ -280,7 +288,19 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   p.pw = (dx_max == dx_min) ? WS_TW : 16;
   const int avail = 232448 - 1024 - 1024 - 8192;        // align slack, static smem, store-transpose stage
   const int budget = avail - ((p.w_total_bytes + 1023) & ~1023);
-  p.ph = WS_TH + (dy_max - dy_min);
+  // Sub-tiles per pipeline step: T vertically stacked 16 x 8 sub-tiles share one patch load (less halo), one TMEM stage
+  // (T x bn columns) and one round of the producer -> MMA -> epilogue barrier chain.  Measured (B=32, 256^2 step): the
+  // 4-phase ConvTranspose 64->32 337 -> 252 us with T = 4, 128->64 133 -> 107 us with T = 2; no gain for cout >= 128.
+  // (What bounds the 32-channel layers is the 64-byte pixel row: both the TMA patch load and the tensor core's operand
+  // fetch move 64-byte rows at the cost of 128-byte ones - measured 160 clk per M128 x N32 MMA.)
+  p.T = 1;
+  const int t_max = p.bn <= 32 ? 4 : (p.bn <= 64 ? 2 : 1);
+  for (int T = t_max; T >= 1; --T) {
+    if (2 * T * p.bn > 512 || (T > 1 && (T - 1) * WS_TH >= g->mi)) continue;
+    const int pb = ((p.pw * (WS_TH * T + (dy_max - dy_min)) * p.rowb) + 1023) & ~1023;
+    if (budget >= (T > 1 ? 3 : 2) * pb) { p.T = T; break; }
+  }
+  p.ph = WS_TH * p.T + (dy_max - dy_min);
   p.patch_tx = p.pw * p.ph * p.rowb;
   p.patch_bytes = (p.patch_tx + 1023) & ~1023;
   if (budget < 2 * p.patch_bytes) return 0;              // the filter does not fit next to two patches
@@ -293,7 +313,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.cout_valid = out->c; p.thin = thin; p.n_img = in->n;
   p.dy_min = dy_min; p.dx_min = dx_min;
   for (int t = 0; t < g->ntaps; ++t) { p.tdy[t] = g->dy[t] - dy_min; p.tdx[t] = g->dx[t] - dx_min; }
-  p.tiles_i = (p.mi + WS_TH - 1) / WS_TH;
+  p.tiles_i = (p.mi + WS_TH * p.T - 1) / (WS_TH * p.T);
   p.tiles_j = (p.mj + WS_TW - 1) / WS_TW;
   p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j;
   p.layout_type = p.rowb == 128 ? 2u : 4u;
@@ -326,7 +346,9 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   {
     const int nb = p.n_pbuf > 3 ? 3 : p.n_pbuf;
     const size_t need = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)nb * p.patch_bytes + 8192;
-    if (2 * (need + 1024) <= 227 * 1024) { two = true; p.n_pbuf = nb; }
+    const int acc2 = 2 * p.T * p.bn;                    // TMEM columns one CTA allocates (rounded up to a power of two)
+    const int cols = acc2 <= 32 ? 32 : acc2 <= 64 ? 64 : acc2 <= 128 ? 128 : acc2 <= 256 ? 256 : 512;
+    if (2 * (need + 1024) <= 227 * 1024 && 2 * cols <= 512) { two = true; p.n_pbuf = nb; }
   }
   const size_t smem = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)p.n_pbuf * p.patch_bytes + 8192;
   const int max_ctas = (two ? 2 : 1) * num_sms();
