@@ -19,10 +19,12 @@
 //  * a producer pays ~470-620 cycles per TMA *instruction* (wait + expect_tx + issue) however many lanes of the warp take
 //    turns, so 16 KB instructions cap the feed at ~32 B/clk; the weights therefore come through a 3-D map
 //    [tap][cout][cin] with a box of `tg` = 3 taps x 128 rows: ONE 48 KB instruction per slot;
-//  * with every TMA wait removed and operands resident, this kernel's MMAs (M128 x N256 x 32 B of K, both operands in
-//    shared memory, a different address every instruction) retire one per ~170-210 cycles, not the 128 of a loop that
-//    re-reads ONE operand pair: the tensor core fetches operands at ~64 B/clk/SM, i.e. (M + N) / 2 cycles per
-//    instruction.  That (not L2) is what bounds conv_px / conv_hx (N = 256: 192 clk) and conv_ws (N <= 64: ~100 clk).
+//  * an isolated issue loop retires one M128 x N256 x 32 B MMA per 128 clk (65 clk for N <= 128) from shared memory with
+//    a different operand tile every instruction (scratch/mma_bench2.cu) - i.e. the tensor core alone pulls 96-126 B/clk
+//    of the 128 B/clk shared-memory bandwidth.  In this kernel, with every TMA wait removed, the same MMAs retire one per
+//    ~170-210 clk: the TMA fills and the epilogue compete for the remaining shared-memory bandwidth.  That (not L2) is what
+//    bounds conv_px (94 B/clk of TMA fill per stage), this kernel (41 B/clk) and conv_ws; going further needs operands
+//    that do not come from this CTA's shared memory (cta_group::2 halves B per SM, or A from TMEM).
 #include "px_common.cuh"
 
 namespace ast {
@@ -248,7 +250,9 @@ int conv_gather_hx(const ast_image* in, const void* weights, const float* bias, 
   p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.n_img = in->n; p.n_slices = cpad / 128;
   p.dy_min = dy_min; p.dx_min = dx_min;
   for (int t = 0; t < g->ntaps; ++t) { p.tdy[t] = g->dy[t] - dy_min; p.tdx[t] = g->dx[t] - dx_min; }
-  // tile rows: as few row tiles as possible, split evenly (66 rows -> 3 x 22 instead of 32 + 32 + 2)
+  // tile rows: as few row tiles as possible, split evenly (66 rows -> 3 x 22 instead of 32 + 32 + 2).  (N = 128 tiles,
+  // 5 x 16 rows, were measured SLOWER for the 66-row gradients, 68 vs 50 us: an N = 128 MMA needs 126 B/clk of operand
+  // fetch for its 65 clk and loses more to the concurrent TMA / epilogue shared-memory traffic than an N = 176 one.)
   p.tiles_i = (p.mi + 31) / 32;
   p.R = (p.mi + p.tiles_i - 1) / p.tiles_i;
   p.R = (p.R + 1) & ~1;                             // N = 8 R must be a multiple of 16

@@ -128,10 +128,14 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           for (int st = 0; st < p.T; ++st) {
             const unsigned d_tmem = d_tmem0 + (unsigned)(st * p.bn);
             unsigned acc = kc > 0 ? 1u : 0u;
-#pragma unroll 1
+            const unsigned pa = p_lo + (unsigned)st * sub16;
+            unsigned b_lo = w_lo + (unsigned)kc * w16;
+            const unsigned b_step = (unsigned)p.kchunks * w16;
+            // the issuing thread must stay ahead of the tensor pipe (65-128 clk per instruction): straight-line code,
+            // tap offsets prefetched three at a time, no multiplies in the loop
+#pragma unroll 3
             for (int t = 0; t < p.ntaps; ++t) {
-              const unsigned a_lo = p_lo + s_tapoff[t] + (unsigned)st * sub16;
-              const unsigned b_lo = w_lo + (unsigned)(t * p.kchunks + kc) * w16;
+              const unsigned a_lo = pa + s_tapoff[t];
               tc_mma<KIND>(d_tmem, pack_desc(a_lo, hi_a), pack_desc(b_lo, hi_b), p.idesc, acc);
               tc_mma<KIND>(d_tmem, pack_desc(a_lo + 2, hi_a), pack_desc(b_lo + 2, hi_b), p.idesc, 1u);
               if (kmma == 4) {
@@ -139,6 +143,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                 tc_mma<KIND>(d_tmem, pack_desc(a_lo + 6, hi_a), pack_desc(b_lo + 6, hi_b), p.idesc, 1u);
               }
               acc = 1u;
+              b_lo += b_step;
             }
           }
           tc_commit(&pempty[s]);

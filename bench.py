@@ -347,6 +347,8 @@ def run_ours(args):
     host = [torch.randint(0, 256, (B, 3, S, S)).to(in_dtype).pin_memory() for _ in range(2)]
     loss_host = torch.zeros(3, dtype=torch.float32).pin_memory()
     ke = max(20, K)
+    for i in range(2):                                      # untimed: staging buffers / pinned pages are touched once
+        trainer.step(trainer.prefetch(host[i]))
     barrier()
     e0.record()
     nxt = trainer.prefetch(host[0])                         # H2D of step 0's inputs (inside the timed region)
