@@ -38,3 +38,17 @@ run("T 1x1 128->128 64^2 +stats", bf, 128, 128, 64, 64, cg.conv_fwd(1, 1, 0, 64,
 run("VGG conv1_2 64->64 256^2 tf32", f32, 64, 64, 256, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, 256)
 run("VGG conv1_1 vt3 16->64 256^2 tf32", f32, 16, 64, 256, 256, [cg.Launch(256, 256, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)], 256, 256)
 run("VGG dgrad conv1_2 64->64 256^2 bf16 +mask", bf, 64, 64, 256, 256, cg.conv_dgrad(3, 1, 1, 256, 256), 256, 256, mask=True)
+# thin filter gradients (first / last 9x9 layers after the row fold)
+def wg(name, xs, gs, launches, dshape, s_co, s_ci, s_u, s_v, reps=10):
+    x = torch.randn(*xs, device='cuda').to(bf); g = torch.randn(*gs, device='cuda').to(bf)
+    dw = torch.zeros(*dshape, device='cuda')
+    for _ in range(3): ops.wgrad_gather(x, g, launches, dw, s_co, s_ci, s_u, s_v, tensor=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): ops.wgrad_gather(x, g, launches, dw, s_co, s_ci, s_u, s_v, tensor=True)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:44s} {e0.elapsed_time(e1)/reps*1e3:8.1f} us")
+wg("wgrad first layer x(264,256,32) g(256,256,32)", (n, 264, 256, 32), (n, 256, 256, 32), vt9, (9, 32, 32), 32, 1, 32 * 32, 0)
+lw = [cg.Launch(256, 264, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]
+wg("wgrad last layer x(264,264,32) g(256,264,32)", (n, 264, 264, 32), (n, 256, 264, 32), lw, (9, 32, 32), 32, 1, 32 * 32, 0)
