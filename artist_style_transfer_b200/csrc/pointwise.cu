@@ -187,8 +187,10 @@ __global__ void __launch_bounds__(NT) copy_image_kernel(Img src, Img dst, const 
   }
 }
 
+// acc += sum over the batch of x when acc holds ONE image (acc.n == 1), else acc[n] += x[n]
 __global__ void __launch_bounds__(NT) accumulate_kernel(Img x, Img acc) {
-  const long long total = (long long)x.n * x.h * x.w * x.c;
+  const int nsum = acc.n == 1 ? x.n : 1;
+  const long long total = (long long)(acc.n == 1 ? 1 : x.n) * x.h * x.w * x.c;
   for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
     const int c = (int)(idx % x.c);
     long long r = idx / x.c;
@@ -196,7 +198,32 @@ __global__ void __launch_bounds__(NT) accumulate_kernel(Img x, Img acc) {
     const int y = (int)(r % x.h);
     const int n = (int)(r / x.h);
     float* p = (float*)acc.ptr + img_off(acc, n, y, xx, c);
-    *p += ld_elem(x, img_off(x, n, y, xx, c));
+    float s = *p;
+    for (int k = 0; k < nsum; ++k) s += ld_elem(x, img_off(x, n + k, y, xx, c));
+    *p = s;
+  }
+}
+
+// vectorised NHWC variant (4 channels per thread)
+__global__ void __launch_bounds__(NT) accumulate_vec_kernel(Img x, Img acc) {
+  const int nsum = acc.n == 1 ? x.n : 1;
+  const int lanes = x.c / 4;
+  const long long total = (long long)(acc.n == 1 ? 1 : x.n) * x.h * x.w * lanes;
+  for (long long idx = blockIdx.x * (long long)NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+    const int c = (int)(idx % lanes) * 4;
+    long long r = idx / lanes;
+    const int xx = (int)(r % x.w); r /= x.w;
+    const int y = (int)(r % x.h);
+    const int n = (int)(r / x.h);
+    float s[4], v[4];
+    const long long ao = img_off(acc, n, y, xx, c);
+    ld4((const float*)acc.ptr + ao, s);
+    for (int k = 0; k < nsum; ++k) {
+      ld4_img(x, img_off(x, n + k, y, xx, c), v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] += v[e];
+    }
+    st4((float*)acc.ptr + ao, s);
   }
 }
 
@@ -363,10 +390,14 @@ extern "C" int ast_copy_image(const ast_image* src, const ast_image* dst, const 
 
 extern "C" int ast_accumulate(const ast_image* x, const ast_image* acc, void* stream) {
   AST_CHECK_ARG(x && acc, "ast_accumulate: null argument");
-  AST_CHECK_ARG(same_shape(x, acc) && acc->dtype == AST_F32, "ast_accumulate: acc must be fp32 of the same shape");
-  const long long total = (long long)x->n * x->h * x->w * x->c;
-  if (total == 0) return 0;
-  launch_k(accumulate_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(acc));
+  AST_CHECK_ARG(acc->dtype == AST_F32 && acc->h == x->h && acc->w == x->w && acc->c == x->c && (acc->n == x->n || acc->n == 1),
+                "ast_accumulate: acc must be fp32 of the same shape (or hold one image: batch sum)");
+  const long long total = (long long)(acc->n == 1 ? 1 : x->n) * x->h * x->w * x->c;
+  if (total == 0 || x->n == 0) return 0;
+  if (vec_ok(x) && vec_ok(acc))
+    launch_k(accumulate_vec_kernel, blocks_for(total / 4), NT, 0, (cudaStream_t)stream, to_img(x), to_img(acc));
+  else
+    launch_k(accumulate_kernel, blocks_for(total), NT, 0, (cudaStream_t)stream, to_img(x), to_img(acc));
   count_launch();
   count_work(FAM_POINTWISE, 0.0, img_bytes(x) + 2.0 * img_bytes(acc));
   AST_CUDA_LAUNCH_CHECK();

@@ -371,31 +371,38 @@ def style_grams_single(vgg, style_tensor, batch_size):
         return {k: gram(v).expand(batch_size, -1, -1) for k, v in feats.items()}
 
 
-def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group=None):
+def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group=None, chunk=16):
     """'smartaverage' artist style (train_cnn.py:224-244).
 
     mode='reference': sum the VGG features over the artist's paintings, divide by the count, ONE Gram of the
     mean feature (exactly the reference).  mode='mean_gram': mean of per-painting Grams (north-star
     wording).  With `group` (torch.distributed), each rank passes ITS shard of the paintings and the sums are
     all-reduced (NCCL) before the division; `paintings` is a list of (3,H,W) tensors or a [P,3,H,W] tensor.
+    The reference pushes one painting (expanded to B identical copies) through the VGG at a time; here `chunk` DIFFERENT
+    paintings share one VGG pass and the feature (or Gram) sum over the chunk is taken by the accumulate kernel - same
+    sums, far fewer and fuller launches.
     """
     acc, count = None, 0
-    shift = None
     with torch.no_grad():
-        for p in paintings:
-            shift = neg_mean(p.device) if shift is None else shift
-            feats = vgg(p.float().unsqueeze(0), shift=shift)
-            cur = {}
-            for k, v in feats.items():
-                cur[k] = v.permute(0, 2, 3, 1) if mode == "reference" else gram(v)
-            if acc is None:
-                acc = {k: torch.zeros(v.shape, dtype=torch.float32, device=v.device) for k, v in cur.items()}
-            for k, v in cur.items():
+        plist = list(paintings) if not torch.is_tensor(paintings) else list(paintings.unbind(0))
+        for i0 in range(0, len(plist), max(1, chunk)):
+            part = plist[i0:i0 + max(1, chunk)]
+            if any(p.shape != part[0].shape for p in part):          # ragged sizes: one painting per pass
+                groups = [[p] for p in part]
+            else:
+                groups = [part]
+            for grp in groups:
+                x = torch.stack([p.float() if p.dtype != torch.uint8 else p for p in grp])
+                feats = vgg(x, shift=neg_mean(x.device))
                 if mode == "reference":
-                    ops.accumulate(v, acc[k])                      # train_cnn.py:239 in-place feature sum
+                    cur = {k: v.permute(0, 2, 3, 1) for k, v in feats.items()}       # NHWC views of the taps
                 else:
-                    ops.accumulate(v.unsqueeze(0), acc[k].unsqueeze(0))
-            count += 1
+                    cur = {k: gram(v).unsqueeze(1) for k, v in feats.items()}        # [k, C, C] as images [k, 1, C, C]
+                if acc is None:
+                    acc = {k: torch.zeros((1,) + tuple(v.shape[1:]), dtype=torch.float32, device=v.device) for k, v in cur.items()}
+                for k, v in cur.items():
+                    ops.accumulate(v, acc[k])                       # train_cnn.py:239 in-place sum (over the chunk's batch)
+                count += len(grp)
         total = torch.tensor([float(count)], device=next(iter(acc.values())).device)
         dp.allreduce_sums(list(acc.values()) + [total], group)      # C2: one exchange per artist (SURVEY 8e)
         length = float(total.item())
@@ -405,7 +412,7 @@ def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group
                 # gram(sum/len) == gram(sum)/len^2: folds train_cnn.py:242-243's divide into a C x C scale
                 g = gram(v.permute(0, 3, 1, 2)) / (length * length)
             else:
-                g = v / length
+                g = v[0] / length                                   # [1, C, C]
             out[k] = g.expand(batch_size, -1, -1)
         return out
 

@@ -191,7 +191,8 @@ int ast_mse(const ast_image* a, const ast_image* b, float* loss, float scale, co
 
 /* dst = src converted/re-strided (NCHW fp32 <-> NHWC bf16/fp32), optional per-channel shift, reflect pad. */
 int ast_copy_image(const ast_image* src, const ast_image* dst, const float* shift, int32_t pad, void* stream);
-/* acc(fp32 image) += x   ('smartaverage' in-place feature sum, train_cnn.py:239) */
+/* acc(fp32 image) += x   ('smartaverage' in-place feature sum, train_cnn.py:239).  With acc->n == 1 and x->n > 1 the batch
+ * of x is summed into the one accumulator image (several paintings per VGG pass). */
 int ast_accumulate(const ast_image* x, const ast_image* acc, void* stream);
 
 /* out = (a + b) * (mask > 0)   (b may be NULL; nn.ReLU backward on an incoming tap gradient) */
