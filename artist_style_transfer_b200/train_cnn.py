@@ -404,7 +404,8 @@ def style_grams_smartaverage(vgg, paintings, batch_size, mode="reference", group
                     ops.accumulate(v, acc[k])                       # train_cnn.py:239 in-place sum (over the chunk's batch)
                 count += len(grp)
         total = torch.tensor([float(count)], device=next(iter(acc.values())).device)
-        dp.allreduce_sums(list(acc.values()) + [total], group)      # C2: one exchange per artist
+        if group is not None:                                        # no group = every painting is local, no exchange
+            dp.allreduce_sums(list(acc.values()) + [total], group)  # C2: one exchange per artist
         length = float(total.item())
         out = {}
         for k, v in acc.items():

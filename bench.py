@@ -274,6 +274,17 @@ def dp_check(ast, dist, dev, rank, world):
         res = {"loss_rel": loss_rel, "grad_rel": grad_rel, "images": bs * world, "size": S,
                "ok": bool(loss_rel < 2e-3 and grad_rel < 3e-2)}
     arena.grad_sink = None
+    # C2: 'smartaverage' sharded over the ranks (each rank its paintings, one all-reduce of the sums) == all paintings on one rank
+    paint = [torch.randint(0, 256, (3, S, S), device=dev, generator=torch.Generator(device=dev).manual_seed(40 + i)).float()
+             for i in range(2 * world)]
+    lo, hi = dp.shard_range(len(paint), rank, world)
+    for mode in ("reference", "mean_gram"):
+        sharded_g = ast.style_grams_smartaverage(vgg, paint[lo:hi], 1, mode=mode, group=dist.group.WORLD)
+        if rank == 0:
+            seq = ast.style_grams_smartaverage(vgg, paint, 1, mode=mode)
+            err = max(float((sharded_g[k] - seq[k]).norm() / seq[k].norm()) for k in seq)
+            res[f"smartaverage_{mode}_rel"] = err
+            res["ok"] = bool(res["ok"] and err < 1e-4)
     torch.cuda.synchronize()
     dist.barrier()
     return res
@@ -302,6 +313,8 @@ def run_ours(args):
     in_dtype = torch.uint8 if args.input == "uint8" else torch.float32
 
     check = dp_check(ast, dist, dev, rank, world) if world > 1 else None
+    if check is not None and not check["ok"]:
+        raise SystemExit(f"data-parallel equivalence check failed, not timing a wrong step: {check}")
 
     torch.manual_seed(2 + rank)                            # replicas are made identical by the trainer's broadcast
     net = ast.StyleTransfer(device=dev, precision=args.precision)

@@ -67,6 +67,40 @@ def test_grad_bucket_allreduce_mean():
         torch.testing.assert_close(got, want[i], rtol=1e-6, atol=1e-7)
 
 
+def _arena_job(rank, world):
+    """The fused-optimizer path's exchange: replicas that start DIFFERENT are made identical by the trainer's broadcast,
+    and the flat gradient arena (tap-major segments, read back through the strided p.grad views) is averaged in place."""
+    from artist_style_transfer_b200 import StyleTransfer, arena as arena_mod, dp
+    torch.manual_seed(rank)                                   # deliberately different replicas
+    net = StyleTransfer(device="cpu", precision="fast")
+    params = list(net.parameters())
+    before = params[4].detach().clone()
+    dp.broadcast_parameters(params, None)
+    ar = arena_mod.TransferArena(net._stages(), "fast", torch.device("cpu"))
+    gbuf = ar.new_grad_buffer()
+    g = torch.Generator().manual_seed(200 + rank)
+    vals = []
+    for view, p in zip(ar.grad_views(gbuf), ar.params()):
+        r = torch.randn(p.shape, generator=g)
+        view.copy_(r)                                         # strided write into the arena
+        vals.append(r)
+    dp.allreduce_mean_flat(gbuf, None)
+    views = ar.grad_views(gbuf)
+    return {"p3_before": before, "p3_after": params[4].detach().clone(), "vals": [vals[0], vals[5], vals[-2]],
+            "avg": [views[0].clone(), views[5].clone(), views[-2].clone()], "numel": ar.g_numel}
+
+
+def test_arena_allreduce_and_parameter_broadcast():
+    res = _run(_arena_job)
+    assert not torch.equal(res[0]["p3_before"], res[1]["p3_before"])           # the replicas really differed
+    assert torch.equal(res[0]["p3_after"], res[1]["p3_after"]) and torch.equal(res[0]["p3_after"], res[0]["p3_before"])
+    for i in range(3):
+        want = (res[0]["vals"][i] + res[1]["vals"][i]) / 2
+        torch.testing.assert_close(res[0]["avg"][i], want, rtol=1e-6, atol=1e-7)
+        assert torch.equal(res[0]["avg"][i], res[1]["avg"][i])
+    assert res[0]["numel"] >= 1712771                                           # every parameter has a segment
+
+
 def _sum_job(rank, world):
     from artist_style_transfer_b200 import dp
     n = 11
