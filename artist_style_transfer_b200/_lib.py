@@ -15,6 +15,7 @@ AST_F32, AST_BF16, AST_TF32, AST_U8 = 0, 1, 2, 3
 AST_MAX_TAPS = 81
 CONV_RELU, CONV_REFLECT, CONV_TENSOR = 1, 2, 4
 CONV_POOL_ONLY = 16
+CONV_ROUND_TF32 = 8
 IN_SUMS_ZEROED = 2
 GRAM_COUNTERS_PER_IMAGE = 16
 
@@ -36,8 +37,20 @@ class GatherGeom(ctypes.Structure):
                 ("pool_codes", ctypes.POINTER(Image))]
 
 
+AST_MAX_VTAPS = 32
+
+
+class StackedGeom(ctypes.Structure):
+    _fields_ = [("nblk", ctypes.c_int32), ("mi", ctypes.c_int32), ("mj", ctypes.c_int32), ("sy", ctypes.c_int32),
+                ("soy", ctypes.c_int32), ("sox", ctypes.c_int32), ("oy", ctypes.c_int32 * 4), ("ox", ctypes.c_int32 * 4),
+                ("nvt", ctypes.c_int32), ("ntaps", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("dy", ctypes.c_int16 * AST_MAX_VTAPS), ("dx", ctypes.c_int16 * AST_MAX_VTAPS),
+                ("stats", ctypes.c_void_p)]
+
+
 class PackMap(ctypes.Structure):
-    _fields_ = [("off", ctypes.c_int64), ("stride", ctypes.c_int64 * 2), ("tap", ctypes.c_int32), ("dtype", ctypes.c_int32)]
+    _fields_ = [("off", ctypes.c_int64), ("stride", ctypes.c_int64 * 2), ("tap", ctypes.c_int32), ("dtype", ctypes.c_int32),
+                ("rep_stride", ctypes.c_int64), ("rep", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class ParamDesc(ctypes.Structure):
@@ -62,6 +75,7 @@ _vp = ctypes.c_void_p
 
 _SIGNATURES = {
     "ast_conv_gather": [_P(Image), _vp, _vp, _vp, _P(Image), _P(Image), _P(Image), _P(GatherGeom), _vp],
+    "ast_conv_stacked": [_P(Image), _vp, _vp, _P(Image), _P(Image), _P(Image), _P(StackedGeom), _vp],
     "ast_wgrad_gather": [_P(Image), _P(Image), _vp, _vp, ctypes.c_int64, ctypes.c_int64, _P(GatherGeom), _vp],
     "ast_pack_weights": [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
                          _vp, ctypes.c_int32, _vp],

@@ -40,10 +40,12 @@ def _canonical_dgrad(st):
 
 class _Pack:
     """One packed copy: byte offset in the arena, shape, dtype and the element map of the master weight."""
-    __slots__ = ("off", "shape", "dtype", "taps", "stride", "tapidx", "tensor")
+    __slots__ = ("off", "shape", "dtype", "taps", "stride", "tapidx", "tensor", "rep", "rep_stride", "stacked")
 
-    def __init__(self, shape, dtype, taps, stride, tapidx=None):
+    def __init__(self, shape, dtype, taps, stride, tapidx=None, rep=1, rep_stride=0, stacked=None):
         self.shape, self.dtype, self.taps, self.stride, self.tapidx = shape, dtype, taps, stride, tapidx
+        self.rep, self.rep_stride = rep, rep_stride      # copies of every element (row-interleaved stacked filters)
+        self.stacked = stacked                           # conv_geometry.Stacked of the canonical launch, or None
         self.off, self.tensor = 0, None
 
     def nbytes(self):
@@ -167,6 +169,7 @@ class TransferArena:
             for n_, pk in enumerate(packs):
                 d.pack[n_].off, d.pack[n_].tap, d.pack[n_].dtype = pk.off, add_taps(pk.taps), _DT_CODE[pk.dtype]
                 d.pack[n_].stride[0], d.pack[n_].stride[1] = pk.stride
+                d.pack[n_].rep, d.pack[n_].rep_stride = pk.rep, pk.rep_stride
             idx = len(descs)
             descs.append(d)
             for start in range(0, p.numel(), item):

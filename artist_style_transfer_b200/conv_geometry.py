@@ -81,3 +81,56 @@ def all_wtaps(launches):
     for l in launches:
         out.extend(l.wtaps)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Block-stacked launches (ast_conv_stacked, include/ast.h): nblk = 128 / cout blocks of outputs share every MMA.
+
+@dataclass
+class Stacked:
+    nblk: int
+    mi: int
+    mj: int
+    sy: int                        # input rows per grid row
+    soy: int                       # output steps per grid row / column
+    sox: int
+    oy: List[int] = field(default_factory=list)                   # output origin per block
+    ox: List[int] = field(default_factory=list)
+    vt: List[Tuple[int, int]] = field(default_factory=list)       # (dy, dx) input shift of each virtual tap
+    src: List[List[object]] = field(default_factory=list)         # src[v][g] = kernel position (u, v) or None (zero rows)
+
+    @property
+    def ntaps(self):
+        return sum(1 for row in self.src for s in row if s is not None)
+
+    def places(self):
+        """{kernel position: [(virtual tap, block), ...]}: where each filter tap sits in the stacked filter."""
+        out = {}
+        for v, row in enumerate(self.src):
+            for g, s in enumerate(row):
+                if s is not None:
+                    out.setdefault(s, []).append((v, g))
+        return out
+
+
+def stack_phases(launches):
+    """The sub-pixel phases of a stride-2 ConvTranspose2d forward / stride-2 conv data gradient (all with si = 1 and the
+    same so) as ONE stacked launch: block g = phase g, virtual taps = the union of the phases' input shifts."""
+    assert len(launches) in (2, 4) and all(l.si == 1 and l.so == launches[0].so for l in launches)
+    vt = sorted({t for l in launches for t in l.taps})
+    src = [[dict(zip(l.taps, l.wtaps)).get(t) for l in launches] for t in vt]
+    return Stacked(len(launches), max(l.mi for l in launches), max(l.mj for l in launches), 1, launches[0].so,
+                   launches[0].so, [l.oy0 for l in launches], [l.ox0 for l in launches], vt, src)
+
+
+def stack_rows(launch, nblk):
+    """A stride-1 launch with its output rows interleaved over nblk blocks: block g owns rows g, g + nblk, ...; output row
+    nblk*r + g reads input rows nblk*r + (g + dy), so virtual tap (g + dy, dx) carries tap (dy, dx) in block g."""
+    assert launch.si == 1 and launch.so == 1
+    tapmap = dict(zip(launch.taps, launch.wtaps))
+    dys = [dy for dy, _ in launch.taps]
+    dxs = sorted({dx for _, dx in launch.taps})
+    vt = [(j, dx) for j in range(min(dys), max(dys) + nblk) for dx in dxs]
+    src = [[tapmap.get((j - g, dx)) for g in range(nblk)] for j, dx in vt]
+    return Stacked(nblk, (launch.mi + nblk - 1) // nblk, launch.mj, nblk, nblk, 1,
+                   [launch.oy0 + g for g in range(nblk)], [launch.ox0] * nblk, vt, src)

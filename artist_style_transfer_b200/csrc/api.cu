@@ -31,7 +31,7 @@ void count_work(int family, double flops, double bytes) {
 }
 static const char* const kFamilyNames[FAM_COUNT] = {
   "conv_tc", "conv_px", "conv_ws", "conv_hx", "conv_simt", "wgrad_tc", "wgrad_thin", "wgrad_simt", "gram_tc", "gram_simt",
-  "in_apply", "in_bwd", "in_stats", "pool", "mse", "pointwise", "optim"};
+  "in_apply", "in_bwd", "in_stats", "pool", "mse", "pointwise", "optim", "conv_st"};
 }  // namespace ast
 
 extern "C" int ast_family_count(void) { return ast::FAM_COUNT; }

@@ -22,7 +22,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // tests use the launch counts to assert which kernel a case really ran on.
 enum Family {
   FAM_CONV_TC = 0, FAM_CONV_PX, FAM_CONV_WS, FAM_CONV_HX, FAM_CONV_SIMT, FAM_WGRAD_TC, FAM_WGRAD_THIN, FAM_WGRAD_SIMT, FAM_GRAM_TC,
-  FAM_GRAM_SIMT, FAM_IN_APPLY, FAM_IN_BWD, FAM_IN_STATS, FAM_POOL, FAM_MSE, FAM_POINTWISE, FAM_OPTIM, FAM_COUNT
+  FAM_GRAM_SIMT, FAM_IN_APPLY, FAM_IN_BWD, FAM_IN_STATS, FAM_POOL, FAM_MSE, FAM_POINTWISE, FAM_OPTIM, FAM_CONV_ST, FAM_COUNT
 };
 void count_work(int family, double flops, double bytes);
 inline double esize(const ast_image* im) { return im->dtype == AST_F32 ? 4.0 : (im->dtype == AST_U8 ? 1.0 : 2.0); }

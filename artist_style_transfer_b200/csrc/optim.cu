@@ -76,9 +76,11 @@ adam_pack_kernel(const ast_param_desc* __restrict__ descs, const int32_t* __rest
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-      if (k < d.n_pack)
-        store_pack(pack_arena, d.pack[k].off, a * d.pack[k].stride[0] + b * d.pack[k].stride[1] + taps[d.pack[k].tap + uv],
-                   d.pack[k].dtype, p);
+      if (k < d.n_pack) {
+        const long long at = a * d.pack[k].stride[0] + b * d.pack[k].stride[1] + taps[d.pack[k].tap + uv];
+        for (int r = 0; r < d.pack[k].rep; ++r)
+          store_pack(pack_arena, d.pack[k].off, at + r * d.pack[k].rep_stride, d.pack[k].dtype, p);
+      }
   }
 }
 

@@ -176,6 +176,49 @@ def _conv_gather_impl(x, wpacked, launches, out, bias=None, in_shift=None, add=N
     return out
 
 
+def _conv_stacked_impl(x, wstacked, stk, out, bias=None, add=None, mask=None, relu=False, round_tf32=False, stats=None):
+    lib = _lib.load()
+    g = _lib.StackedGeom()
+    g.nblk, g.mi, g.mj, g.sy, g.soy, g.sox = stk.nblk, stk.mi, stk.mj, stk.sy, stk.soy, stk.sox
+    for b in range(stk.nblk):
+        g.oy[b], g.ox[b] = stk.oy[b], stk.ox[b]
+    g.nvt, g.ntaps = len(stk.vt), stk.ntaps
+    g.flags = (CONV_RELU if relu else 0) | (CONV_ROUND_TF32 if round_tf32 else 0)
+    for v, (dy, dx) in enumerate(stk.vt):
+        g.dy[v], g.dx[v] = dy, dx
+    g.stats = stats.data_ptr() if stats is not None else None
+    if wstacked.shape[0] != len(stk.vt) or wstacked.shape[1] != 128 or wstacked.shape[2] != x.shape[3] or wstacked.dtype != x.dtype:
+        raise RuntimeError(f"conv_stacked: stacked filter {tuple(wstacked.shape)} {wstacked.dtype} does not match "
+                           f"{len(stk.vt)} virtual taps x 128 x {x.shape[3]} {x.dtype}")
+    xi, oi, ai, mi = image(x), image(out), image(add), image(mask)
+    check(lib.ast_conv_stacked(ref(xi), ptr(wstacked), ptr(bias), ref(ai), ref(mi), ref(oi), ref(g), stream_ptr()),
+          "ast_conv_stacked")
+    return out
+
+
+def conv_stacked(x, wstacked, stk, out, bias=None, add=None, mask=None, relu=False, round_tf32=False, stats=None):
+    """Block-stacked tensor-core convolution for 32/64-channel outputs (include/ast.h ast_conv_stacked).
+    stk: conv_geometry.Stacked; wstacked: [virtual taps][128][cin] (stack_filter / the arena's stacked packs)."""
+    label = "conv_stacked"
+    if PROFILE_DETAIL and _prof is not None:
+        label += f"|{tuple(x.shape)}->{tuple(out.shape)} vt={len(stk.vt)} {str(x.dtype)[6:]}"
+    with _timed(label):
+        return _conv_stacked_impl(x, wstacked, stk, out, bias=bias, add=add, mask=mask, relu=relu, round_tf32=round_tf32,
+                                  stats=stats)
+
+
+def stack_filter(tile_of, stk, cb, cin, dtype, device):
+    """[virtual taps][128][cin] stacked filter of a conv_geometry.Stacked launch; tile_of(kernel position) -> [cb][cin]
+    operand tile ([cout][cin] orientation) of that filter tap.  One-time host-driven build (frozen VGG filters, tests); the
+    TransformerNet's stacked filters are written by the fused optimizer kernel (arena.py)."""
+    w = torch.zeros(len(stk.vt), 128, cin, dtype=dtype, device=device)
+    for v, row in enumerate(stk.src):
+        for g, pos in enumerate(row):
+            if pos is not None:
+                w[v, g * cb:(g + 1) * cb] = tile_of(pos).to(dtype)
+    return w
+
+
 def tc_contract_eligible(a, b):
     """Operands the tcgen05 contraction kernel accepts (contract_tc.cu): NHWC, same dtype, 16-byte pixel stride."""
     ok = _lib.has_tc_gram() and a.dtype == b.dtype

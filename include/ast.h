@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AST_ABI_VERSION 5
+#define AST_ABI_VERSION 6
 
 typedef enum {
   AST_F32 = 0, AST_BF16 = 1,
@@ -97,6 +97,42 @@ int ast_conv_gather(const ast_image* in, const void* weights, const float* bias,
  * dw is fp32 and must be zeroed (or hold a running sum) by the caller; accumulation uses fp32 atomics. */
 int ast_wgrad_gather(const ast_image* x, const ast_image* gout, float* dw, const int32_t* tap_off,
                      int64_t s_co, int64_t s_ci, const ast_gather_geom* geom, void* stream);
+
+/* BLOCK-STACKED gather convolution for thin outputs (32 or 64 output channels), tensor-core kernel only (conv_st.cu).
+ *
+ * A tcgen05 MMA has M = 128 rows.  With pixels as N and output channels as M, a 32-channel layer would leave 3/4 of the
+ * tensor core idle; with pixels as M (conv_ws.cu) its N = 32 MMAs are bound by the A-operand fetch.  Here nblk = 128/cout
+ * independent BLOCKS of outputs share every MMA: lane block g (cout consecutive TMEM lanes) accumulates
+ *
+ *   out[n, oy[g] + soy*i, ox[g] + sox*j, co] = epi( sum_v sum_ci in[n, sy*i + dy[v], j + dx[v], ci] * Ws[v][g*cout + co][ci] )
+ *
+ * over an mi x mj grid, all blocks reading the SAME input pixels through the `nvt` virtual taps (dy[v], dx[v]); rows of
+ * Ws that belong to a (virtual tap, block) pair without a filter tap are zero.  Two uses (conv_geometry.py builds both):
+ *   - the 4 (or 2) sub-pixel PHASES of a stride-2 ConvTranspose2d / of a stride-2 convolution's data gradient
+ *     (cnn.py:107-109, train_cnn.py:333) as one launch: sy = 1, soy = sox = 2, (oy, ox)[g] = the phase, virtual taps = the
+ *     union of the phases' input shifts (4 instead of 1+2+2+4 tap launches);
+ *   - ROW-INTERLEAVED stride-1 convolutions (the vertical-tap forms of the 9x9 / 3x3 three-channel ends, cnn.py:32,39,
+ *     train_cnn.py:54 conv1_1): block g owns output rows g, g+nblk, ..: sy = soy = nblk, sox = 1, oy[g] = g, virtual tap
+ *     v = dy + g, so a k-tap layer costs k + nblk - 1 MMAs per nblk output rows instead of nblk * k.
+ * Out-of-range inputs read 0; outputs outside `out` are skipped.  weights: [nvt][128][cin] in the dtype of `in`;
+ * in->c * sizeof(elem) must be 64 or a multiple of 128 bytes; out->c == 128/nblk, channel-contiguous.
+ * bias: fp32[cout] or NULL.  add / mask / flags (RELU, ROUND_TF32) as in ast_conv_gather.  stats: as ast_gather_geom.stats. */
+#define AST_MAX_VTAPS 32
+typedef struct {
+  int32_t nblk;            /* 2 or 4 */
+  int32_t mi, mj;          /* iteration grid per image */
+  int32_t sy;              /* input rows per grid row */
+  int32_t soy, sox;        /* output steps per grid row / column */
+  int32_t oy[4], ox[4];    /* output origin of each block */
+  int32_t nvt;
+  int32_t ntaps;           /* filter taps summed over the blocks (non-zero [virtual tap][block] tiles): work accounting only */
+  int32_t flags;           /* AST_CONV_RELU | AST_CONV_ROUND_TF32 */
+  int16_t dy[AST_MAX_VTAPS];
+  int16_t dx[AST_MAX_VTAPS];
+  double* stats;
+} ast_stacked_geom;
+int ast_conv_stacked(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                     const ast_image* mask, const ast_image* out, const ast_stacked_geom* geom, void* stream);
 
 /* Re-pack fp32 master weights into the [ntaps][a][b] operand layout of ast_conv_gather:
  *   dst[t][ia][ib] = src[tap_off[t] + ia*s_a + ib*s_b]      (dst dtype = ast_dtype) */
@@ -206,12 +242,17 @@ int ast_mask_add(const ast_image* a, const ast_image* b, const ast_image* mask, 
  *
  * Parameter element i of a tensor with logical shape dim = (A, B, U, V) decomposes as i = ((a*B + b)*U + u)*V + v;
  *   gradient  = grads[g_off + a*g_stride[0] + b*g_stride[1] + tap_table[g_tap + u*V + v]]
- *   pack k    = ((dtype*)((char*)pack_arena + pack[k].off))[a*stride[0] + b*stride[1] + tap_table[pack[k].tap + u*V + v]] */
+ *   pack k    = ((dtype*)((char*)pack_arena + pack[k].off))[a*stride[0] + b*stride[1] + tap_table[pack[k].tap + u*V + v]
+ *                                                             + r*rep_stride],  r = 0 .. rep-1
+ * (rep > 1: the row-interleaved stacked filters of ast_conv_stacked hold every tap once per lane block) */
 typedef struct {
   int64_t off;            /* BYTES from the start of the pack arena */
   int64_t stride[2];      /* elements */
   int32_t tap;            /* first entry of this map in the tap table */
   int32_t dtype;          /* ast_dtype of the packed copy */
+  int64_t rep_stride;     /* elements between the copies */
+  int32_t rep;            /* copies of every element (>= 1) */
+  int32_t reserved;
 } ast_pack_map;
 typedef struct {
   int64_t p_off;          /* first element relative to `params` (any fp32 tensors of one device: params = lowest address) */

@@ -20,7 +20,7 @@ KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__cycles_elapsed.
 FAMILY = (("conv_hx_kernel", "conv_hx"), ("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"),
           ("conv_tc_kernel", "conv_tc"), ("contract_thin", "wgrad_thin"), ("contract_tc_kernel<(int)0>", "wgrad_tc"),
           ("contract_tc_kernel<(int)1>", "gram_tc"), ("contract_tc_kernel<0>", "wgrad_tc"), ("contract_tc_kernel<1>", "gram_tc"),
-          ("in_apply", "in_apply"), ("in_bwd", "in_bwd"), ("maxpool2_bwd", "pool"), ("mse", "mse"), ("adam_pack", "optim"),
+          ("in_apply", "in_apply"), ("in_bwd", "in_bwd"), ("maxpool2_bwd", "pool"), ("maxpool2_fwd", "pool_fwd"), ("mse", "mse"), ("adam_pack", "optim"),
           ("row_im2col", "pointwise"), ("fold_rows", "pointwise"))
 
 
@@ -34,7 +34,7 @@ def main():
         m = re.match(r"(\d+) launch\(es\): (.*)", line.strip())
         if m:
             labels += [m.group(2)] * int(m.group(1))
-    skip = ("adam_tick", "FillFunctor", "memset", "Memset")
+    skip = ("adam_tick", "FillFunctor", "memset", "Memset", "maxpool2_fwd")
     kernels = [d for d in data if len(d) == len(hdr) and not any(s in d[idx["Kernel Name"]] for s in skip)]
     out_rows, traffic = [], {}
     li = 0

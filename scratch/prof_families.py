@@ -22,11 +22,12 @@ def conv(name, dtype, cin, cout, hin, launches, hout, stats=False, mask=False, p
     sums = torch.zeros(2 * n * cout, dtype=torch.float64, device=dev) if stats else None
     m = torch.randn(n, hout, hout, cout, device=dev) if mask else None
     pool = torch.empty(n, hout // 2, hout // 2, cout, device=dev, dtype=dtype) if pooled else None
-    todo.append((name, lambda: ops.conv_gather(x, wp, launches, y, tensor=True, stats=sums, mask=m, pooled=pool, relu=relu,
+    pcodes = torch.empty(n, hout // 2, hout // 2, cout, device=dev, dtype=torch.uint8) if pooled else None
+    todo.append((name, lambda: ops.conv_gather(x, wp, launches, y, tensor=True, stats=sums, mask=m, pooled=pool, pool_codes=pcodes, relu=relu,
                                                w_img_stride=cout * cin * nt if w_img else 0, round_tf32=dtype == f32)))
 
 vt9 = [cg.Launch(256, 256, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]
-conv("conv_ws tf32 VGG conv1_2 64->64 256^2 +ReLU +fused MaxPool", f32, 64, 64, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, pooled=True, relu=True)
+conv("conv_ws tf32 VGG conv1_2 64->64 256^2 +ReLU +fused MaxPool +window codes", f32, 64, 64, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, pooled=True, relu=True)
 conv("conv_ws bf16 T first layer (9 vertical taps over row-im2col) 32->32 256^2 +stats", bf, 32, 32, 264, vt9, 256, stats=True)
 conv("conv_hx bf16 T residual 3x3 128->128 64^2 +stats", bf, 128, 128, 66, cg.conv_fwd(3, 1, 0, 66, 66), 64, stats=True)
 conv("conv_hx tf32 VGG conv2_2 128->128 128^2", f32, 128, 128, 128, cg.conv_fwd(3, 1, 1, 128, 128), 128, relu=True)
@@ -69,8 +70,10 @@ dxb = torch.empty_like(xb)
 todo.append(("in_bwd_stats_staged + in_bwd_apply_staged bf16 256^2x32 pad 4", lambda: ops.instnorm_bwd(xb, mb, rb, gam[:32].contiguous(), bet[:32].contiguous(), gpb, 4, None, True, dxb, None)))
 # pointwise
 xp = torch.relu(torch.randn(n, 256, 256, 64, device=dev)); gy = torch.randn(n, 128, 128, 64, device=dev).to(bf)
-ga = torch.randn(n, 256, 256, 64, device=dev)
-todo.append(("maxpool2_bwd 256^2x64 (fp32 x, bf16 gy, fp32 tap gradient)", lambda: ops.maxpool2_bwd(xp, gy, ga)))
+ga = torch.randn(n, 256, 256, 64, device=dev).to(bf)
+codes = torch.empty(n, 128, 128, 64, dtype=torch.uint8, device=dev)
+ops.maxpool2_fwd(xp, codes=codes)
+todo.append(("maxpool2_bwd_codes 256^2x64 (1-byte window codes, bf16 gy, bf16 tap gradient)", lambda: ops.maxpool2_bwd(None, gy, ga, codes=codes)))
 a2 = torch.randn(n, 128, 128, 128, device=dev); b2 = torch.randn(n, 128, 128, 128, device=dev)
 l2 = torch.zeros(1, device=dev); gr = torch.empty_like(a2)
 todo.append(("mse_vec 128^2x128 (content loss + gradient)", lambda: ops.mse(a2, b2, l2, 1.0, gr, 1.0)))

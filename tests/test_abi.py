@@ -21,7 +21,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ast.h but not exported by libast_b200.so"
     assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
-    assert lib.ast_abi_version() == 5
+    assert lib.ast_abi_version() == 6
     assert lib.ast_instnorm_workspace_bytes(4, 128) > 0
     assert lib.ast_launch_count() >= 0
 
@@ -72,15 +72,19 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ast_param_desc), offsetof(ast_param_desc, dim), offsetof(ast_param_desc, g_off),\n'
         '         offsetof(ast_param_desc, g_tap), offsetof(ast_param_desc, pack), sizeof(ast_pack_map));\n'
         '  printf("%zu %zu %zu %zu\\n", sizeof(ast_adam_state), offsetof(ast_adam_state, step), sizeof(ast_reduce_desc), offsetof(ast_reduce_desc, rows));\n'
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ast_stacked_geom), offsetof(ast_stacked_geom, oy), offsetof(ast_stacked_geom, nvt),\n'
+        '         offsetof(ast_stacked_geom, dy), offsetof(ast_stacked_geom, stats), offsetof(ast_pack_map, rep));\n'
         '  return 0;\n}\n')
     exe = tmp_path / "layout"
     subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     got = [int(v) for v in out]
     img, geom, pd, ad, rd = _lib.Image, _lib.GatherGeom, _lib.ParamDesc, _lib.AdamState, _lib.ReduceDesc
+    sg = _lib.StackedGeom
     want = [ctypes.sizeof(img), img.sn.offset, img.c.offset, img.sc.offset,
             ctypes.sizeof(geom), geom.dy.offset, geom.dx.offset, geom.w_img_stride.offset, geom.stats.offset,
             geom.pooled.offset,
             ctypes.sizeof(pd), pd.dim.offset, pd.g_off.offset, pd.g_tap.offset, pd.pack.offset, ctypes.sizeof(_lib.PackMap),
-            ctypes.sizeof(ad), ad.step.offset, ctypes.sizeof(rd), rd.rows.offset]
+            ctypes.sizeof(ad), ad.step.offset, ctypes.sizeof(rd), rd.rows.offset,
+            ctypes.sizeof(sg), sg.oy.offset, sg.nvt.offset, sg.dy.offset, sg.stats.offset, _lib.PackMap.rep.offset]
     assert got == want, (got, want)

@@ -88,6 +88,78 @@ def test_convT_fwd_and_dgrad(k, s, op, h, w):
     torch.testing.assert_close(gotd.permute(0, 3, 1, 2), gx)
 
 
+def emulate_stacked(x, ws, stk, out, cb):
+    """The formula of ast_conv_stacked (include/ast.h): x [N,H,W,Ci], ws [nvt][128][Ci]; fills the blocks' pixels of out."""
+    n, h, w, ci = x.shape
+    ii, jj = torch.arange(stk.mi), torch.arange(stk.mj)
+    acc = torch.zeros((n, stk.mi, stk.mj, 128), dtype=x.dtype)
+    for v, (dy, dx) in enumerate(stk.vt):
+        y, xx = stk.sy * ii + dy, jj + dx
+        ok = ((y >= 0) & (y < h))[:, None] & ((xx >= 0) & (xx < w))[None, :]
+        g = x[:, y.clamp(0, h - 1)][:, :, xx.clamp(0, w - 1)] * ok[None, :, :, None]
+        acc += g @ ws[v].T
+    for b in range(stk.nblk):
+        oy, ox = stk.oy[b] + stk.soy * ii, stk.ox[b] + stk.sox * jj
+        ky, kx = oy < out.shape[1], ox < out.shape[2]
+        out[:, oy[ky][:, None], ox[kx][None, :]] = acc[:, ky][:, :, kx][..., b * cb:(b + 1) * cb]
+
+
+def _stack_filter(wt, launches, stk, cb):
+    tidx = {}
+    for l in launches:
+        for t, pos in enumerate(l.wtaps):
+            tidx[pos] = l.woff + t
+    ws = torch.zeros(len(stk.vt), 128, wt.shape[2], dtype=wt.dtype)
+    for v, row in enumerate(stk.src):
+        for g, pos in enumerate(row):
+            if pos is not None:
+                ws[v, g * cb:(g + 1) * cb] = wt[tidx[pos]]
+    return ws
+
+
+@pytest.mark.parametrize("case", ["convT32", "dgrad32", "convT64", "rows9", "rows3_64", "rows9_neg", "rows3x3"])
+def test_stacked_launches_equal_the_plain_gather(case):
+    """stack_phases / stack_rows (the block-stacked tensor-core kernel's geometry) reproduce the plain launches."""
+    torch.manual_seed(1)
+    cb = 64 if "64" in case else 32
+    if case in ("convT32", "convT64"):
+        hin, win, ls = 7, 9, cg.convT_fwd(3, 2, 1, 1, 7, 9)
+        ho, wo = 14, 18
+    elif case == "dgrad32":
+        hin, win, ho, wo = 6, 7, 14, 16          # data gradient of a stride-2 3x3 conv on a padded 14 x 16 input
+        ls = cg.conv_dgrad(3, 2, 0, ho, wo)
+    elif case == "rows9":
+        hin, win, ho, wo = 19, 10, 11, 10
+        ls = [cg.Launch(ho, wo, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]
+    elif case == "rows9_neg":
+        hin, win, ho, wo = 10, 9, 18, 9           # thin-output data gradient: rows y - d, zero outside
+        ls = [cg.Launch(ho, wo, 1, 1, 0, 0, [(-d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]
+    elif case == "rows3_64":
+        hin, win, ho, wo = 9, 8, 9, 8
+        ls = [cg.Launch(ho, wo, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]
+    else:
+        hin, win, ho, wo = 10, 11, 10, 11
+        ls = cg.conv_fwd(3, 1, 1, hin, win)
+    nt = sum(len(l.taps) for l in ls)
+    x = torch.randn(2, hin, win, 6, dtype=torch.float64)
+    wt = torch.randn(nt, cb, 6, dtype=torch.float64)
+    ref = emulate_gather(x, wt, ls, (ho, wo))
+    nb = 128 // cb
+    got = torch.full_like(ref, float("nan"))
+    if len(ls) > 1:           # sub-pixel phases: one launch of 4 blocks (32 channels) or two launches of 2 (64 channels)
+        groups = [cg.stack_phases(ls[i:i + nb]) for i in range(0, len(ls), nb)]
+        assert [len(s.vt) for s in groups] == ([4] if nb == 4 else [2, 4])
+        assert sum(s.ntaps for s in groups) == nt
+    else:                     # interleaved rows: k + nblk - 1 virtual rows, every tap once per block
+        groups = [cg.stack_rows(ls[0], nb)]
+        assert len(groups[0].vt) == (len({dy for dy, _ in ls[0].taps}) + nb - 1) * len({dx for _, dx in ls[0].taps})
+        assert groups[0].ntaps == nt * nb
+    for stk in groups:
+        emulate_stacked(x, _stack_filter(wt, ls, stk, cb), stk, got, cb)
+    assert not torch.isnan(got).any(), "blocks do not cover the output"
+    torch.testing.assert_close(got, ref)
+
+
 def test_sizes():
     assert cg.conv_out_size(258, 3, 2, 0) == 128
     assert cg.convT_out_size(64, 3, 2, 1, 1) == 128
