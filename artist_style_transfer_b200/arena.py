@@ -38,14 +38,50 @@ def _canonical_dgrad(st):
     return cg.convT_dgrad(st.k, st.stride, st.k // 2, 16, 16)
 
 
+def stack_groups(launches, cb):
+    """The block-stacked launches (conv_geometry.Stacked) that replace `launches` for a cb-channel output: the
+    interleaved-row form of a single stride-1 launch, or the sub-pixel phases 128/cb at a time."""
+    nb = 128 // cb
+    if len(launches) == 1:
+        return [cg.stack_rows(launches[0], nb)]
+    assert len(launches) % nb == 0
+    return [cg.stack_phases(launches[i:i + nb]) for i in range(0, len(launches), nb)]
+
+
+def _stacked_pack(groups, cb, kdim, dtype, uv, pos_of, within, stride):
+    """_Pack of the stacked filters [sum of virtual taps][128][kdim] of `groups`.  pos_of(u, v): the kernel position under
+    which conv_geometry lists master tap (u, v); within(u, v): extra element offset inside its [cb][kdim] tile."""
+    vbase, nv = [], 0
+    for g in groups:
+        vbase.append(nv)
+        nv += len(g.vt)
+    where = {}
+    for gi, g in enumerate(groups):
+        for pos, lst in g.places().items():
+            where.setdefault(pos, []).extend(((vbase[gi] + v) * 128 + b * cb) * kdim for v, b in lst)
+    taps, rep, rep_stride = [], None, 0
+    for u, v in uv:
+        offs = sorted(where[pos_of(u, v)])
+        r = len(offs)
+        d = offs[1] - offs[0] if r > 1 else 0
+        assert all(offs[i + 1] - offs[i] == d for i in range(r - 1)), "copies of a tap must be equally spaced"
+        assert rep in (None, r) and (r == 1 or rep is None or rep_stride == d)
+        rep, rep_stride = r, d
+        taps.append(offs[0] + within(u, v))
+    pk = _Pack((nv, 128, kdim), dtype, taps, stride, None, rep, rep_stride, groups)
+    pk.vbase = vbase
+    return pk
+
+
 class _Pack:
     """One packed copy: byte offset in the arena, shape, dtype and the element map of the master weight."""
-    __slots__ = ("off", "shape", "dtype", "taps", "stride", "tapidx", "tensor", "rep", "rep_stride", "stacked")
+    __slots__ = ("off", "shape", "dtype", "taps", "stride", "tapidx", "tensor", "rep", "rep_stride", "stacked", "vbase")
 
     def __init__(self, shape, dtype, taps, stride, tapidx=None, rep=1, rep_stride=0, stacked=None):
         self.shape, self.dtype, self.taps, self.stride, self.tapidx = shape, dtype, taps, stride, tapidx
         self.rep, self.rep_stride = rep, rep_stride      # copies of every element (row-interleaved stacked filters)
-        self.stacked = stacked                           # conv_geometry.Stacked of the canonical launch, or None
+        self.stacked = stacked                           # [conv_geometry.Stacked] of the canonical launches, or None
+        self.vbase = None                                # first virtual tap of each stacked group in the filter
         self.off, self.tensor = 0, None
 
     def nbytes(self):
@@ -83,27 +119,53 @@ class TransferArena:
                                and ci % 32 == 0 and not st.norm)
             uv = [(u, v) for u in range(k) for v in range(k)]
             sa_sb = (ci, 1) if conv else (1, ci)          # element (a, b) of the master weight -> [co][ci] position
+            vt_fwd = [cg.Launch(16, 16, 1, 1, 0, 0, [(u, 0) for u in range(k)], [(u, 0) for u in range(k)], 0)]
             if pl.thin_in:        # [dy][co][dx*cin + c] (k, cout, 32): the row-im2col'd first layer, k vertical taps
-                pl.fwd = _Pack((k, co, 32), self.adt, [u * co * 32 + v * ci for u, v in uv], (32, 1))
+                if co == 32:      # block-stacked (ast_conv_stacked): 4 interleaved output rows share every MMA
+                    pl.fwd = _stacked_pack(stack_groups(vt_fwd, co), co, 32, self.adt, uv, lambda u, v: (u, 0),
+                                           lambda u, v: v * ci, (32, 1))
+                else:
+                    pl.fwd = _Pack((k, co, 32), self.adt, [u * co * 32 + v * ci for u, v in uv], (32, 1))
                 pl.g_shape, pl.g_taps, pl.g_stride = (k, co, 32), [u * co * 32 + v * ci for u, v in uv], (32, 1)
             elif pl.thin_out:     # [dy][dx*cout + co][c] (k, 32, cin): k vertical taps producing k*cout partial channels
-                pl.fwd = _Pack((k, 32, ci), self.adt, [u * 32 * ci + v * co * ci for u, v in uv], (ci, 1))
+                if (ci * 2) % 128 == 0 or ci * 2 == 64:
+                    pl.fwd = _stacked_pack(stack_groups(vt_fwd, 32), 32, ci, self.adt, uv, lambda u, v: (u, 0),
+                                           lambda u, v: v * co * ci, (ci, 1))
+                else:
+                    pl.fwd = _Pack((k, 32, ci), self.adt, [u * 32 * ci + v * co * ci for u, v in uv], (ci, 1))
                 pl.g_shape, pl.g_taps, pl.g_stride = (k, 32, ci), [u * 32 * ci + v * co * ci for u, v in uv], (ci, 1)
             else:                 # [t][co][ci], t in the order of the forward launches' taps
-                order = cg.all_wtaps(_canonical_fwd(st))
-                tapidx = {t: n for n, t in enumerate(order)}
-                pl.fwd = _Pack((k2, co, ci), self.adt, [tapidx[t] * co * ci for t in uv], sa_sb, tapidx)
+                canon = _canonical_fwd(st)
+                if tc and not conv and st.stride == 2 and co in (32, 64) and (ci * 2) % 128 == 0:
+                    # ConvTranspose2d stride 2: the 4 sub-pixel phases as lane blocks of one (cout 32) / two (cout 64) launches
+                    pl.fwd = _stacked_pack(stack_groups(canon, co), co, ci, self.adt, uv, lambda u, v: (u, v),
+                                           lambda u, v: 0, sa_sb)
+                else:
+                    order = cg.all_wtaps(canon)
+                    tapidx = {t: n for n, t in enumerate(order)}
+                    pl.fwd = _Pack((k2, co, ci), self.adt, [tapidx[t] * co * ci for t in uv], sa_sb, tapidx)
                 # tap-major gradient scratch [u][v][co][ci]: ci contiguous -> 16-byte vector reductions in the epilogue
                 pl.g_shape, pl.g_taps, pl.g_stride = (k, k, co, ci), [(u * k + v) * co * ci for u, v in uv], sa_sb
             pl.dgrad = None
             if i > 0:
                 if pl.thin_out:   # [dy][c][dx*cout + co] (k, cin, 32)
-                    pl.dgrad = _Pack((k, ci, 32), self.adt, [u * ci * 32 + v * co for u, v in uv], (1, 32))
+                    if ci == 32:  # block-stacked: rows y - dy of the row-im2col'd output gradient
+                        vt_dg = [cg.Launch(16, 16, 1, 1, 0, 0, [(-u, 0) for u in range(k)], [(u, 0) for u in range(k)], 0)]
+                        pl.dgrad = _stacked_pack(stack_groups(vt_dg, ci), ci, 32, self.adt, uv, lambda u, v: (u, 0),
+                                                 lambda u, v: v * co, (1, 32))
+                    else:
+                        pl.dgrad = _Pack((k, ci, 32), self.adt, [u * ci * 32 + v * co for u, v in uv], (1, 32))
                 else:             # [t][ci][co], t in the order of the data-gradient launches' taps (phases for stride 2)
-                    order = cg.all_wtaps(_canonical_dgrad(st))
-                    tapidx = {t: n for n, t in enumerate(order)}
-                    pl.dgrad = _Pack((k2, ci, co), self.adt, [tapidx[t] * ci * co for t in uv],
-                                     (1, co) if conv else (co, 1), tapidx)
+                    canon = _canonical_dgrad(st)
+                    dg_stride = (1, co) if conv else (co, 1)
+                    if tc and conv and st.stride == 2 and ci in (32, 64) and (co * 2) % 128 == 0:
+                        # data gradient of a stride-2 conv: the 4 output phases as lane blocks
+                        pl.dgrad = _stacked_pack(stack_groups(canon, ci), ci, co, self.adt, uv, lambda u, v: (u, v),
+                                                 lambda u, v: 0, dg_stride)
+                    else:
+                        order = cg.all_wtaps(canon)
+                        tapidx = {t: n for n, t in enumerate(order)}
+                        pl.dgrad = _Pack((k2, ci, co), self.adt, [tapidx[t] * ci * co for t in uv], dg_stride, tapidx)
             n = 1
             for d in pl.g_shape:
                 n *= d

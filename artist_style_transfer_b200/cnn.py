@@ -88,6 +88,22 @@ def _vtaps(k, sign=1):
     return taps, [(dy, 0) for dy in range(k)]
 
 
+def _conv_packed(x, pk, launches, out, **kw):
+    """One conv through an arena pack: the block-stacked tensor-core kernel when the arena laid the filter out for it
+    (32/64-channel outputs: ConvTranspose phases, stride-2 data gradients, the vertical-tap forms of the 9x9 ends)."""
+    if pk.stacked is None:
+        return ops.conv_gather(x, pk.tensor, launches, out, **kw)
+    kw.pop("tensor", None)
+    groups = arena_mod.stack_groups(launches, out.shape[3])
+    if len(groups) != len(pk.stacked):
+        raise RuntimeError("block-stacked conv: the launches of this image size do not match the packed filter")
+    for g, ref, vb in zip(groups, pk.stacked, pk.vbase):
+        if g.vt != ref.vt or g.src != ref.src:
+            raise RuntimeError("block-stacked conv: the taps of this image size do not match the packed filter")
+        ops.conv_stacked(x, pk.tensor[vb:vb + len(g.vt)], g, out, **kw)
+    return out
+
+
 class _StageFunction(torch.autograd.Function):
     """Forward/backward of a list of stages as ONE autograd node.
 
@@ -156,7 +172,7 @@ class _StageFunction(torch.autograd.Function):
                     # as k*cout (27 of 32) channels; ast_fold_rows adds the k shifted partials and the bias
                     taps, wt = _vtaps(st.k)
                     part = torch.empty((n, ho, xin.shape[2], 32), dtype=torch.float32, device=dev)
-                    ops.conv_gather(xin, wp, [cg.Launch(ho, xin.shape[2], 1, 1, 0, 0, taps, wt, 0)], part, tensor=True)
+                    _conv_packed(xin, pl.fwd, [cg.Launch(ho, xin.shape[2], 1, 1, 0, 0, taps, wt, 0)], part, tensor=True)
                     ops.fold_rows(part, outv, st.k, bias=cb.detach(), relu=st.relu, flip_channels=u8_out)
                     del part
                 else:
@@ -170,11 +186,11 @@ class _StageFunction(torch.autograd.Function):
             else:
                 raw = torch.empty((n, ho, wo, st.cout), dtype=adt, device=dev)
                 # conv bias is dead under InstanceNorm and is not added
-                use_tc = mode == "fast" and ops.tc_eligible(xin, st.cout)
+                use_tc = mode == "fast" and (ops.tc_eligible(xin, st.cout) or pl.fwd.stacked is not None)
                 if use_tc:                         # sum x / sum x^2 accumulated by the conv epilogue: no stats pass
                     sums = zeros[zoff:zoff + 2 * n * st.cout]
                     zoff += 2 * n * st.cout
-                    ops.conv_gather(xin, wp, launches, raw, tensor=True, stats=sums)
+                    _conv_packed(xin, pl.fwd, launches, raw, tensor=True, stats=sums)
                     mean, rstd = ops.instnorm_finalize(sums, n, st.cout, ho * wo)
                 else:
                     ops.conv_gather(xin, wp, launches, raw)
@@ -286,7 +302,7 @@ class _StageFunction(torch.autograd.Function):
                 taps, wt = _vtaps(st.k, -1)
                 dl = [cg.Launch(xin.shape[1], xin.shape[2], 1, 1, 0, 0, taps, wt, 0)]
                 g_in = torch.empty(xin.shape, dtype=gdt, device=dev)
-                ops.conv_gather(d_raw, pl.dgrad.tensor, dl, g_in, tensor=True)
+                _conv_packed(d_raw, pl.dgrad, dl, g_in, tensor=True)
                 gpad[i] = g_in
             elif i > 0:
                 if st.kind == "conv":
@@ -299,7 +315,7 @@ class _StageFunction(torch.autograd.Function):
                 if src.dtype != adt or not src.is_contiguous():   # fp32 NCHW grad of the last conv feeding the dgrad
                     src = torch.empty(d_raw.shape, dtype=adt, device=dev)
                     ops.copy_image(d_raw, src)
-                ops.conv_gather(src, pl.dgrad.tensor, dl, g_in, tensor=mode == "fast" and ops.tc_eligible(src, st.cin))
+                _conv_packed(src, pl.dgrad, dl, g_in, tensor=mode == "fast" and ops.tc_eligible(src, st.cin))
                 gpad[i] = g_in
         if bank_off:
             ops.batch_reduce(banks, gbuf, *arena.reduce_table(nb, bank_off))

@@ -29,7 +29,9 @@
 
 namespace ast {
 
-constexpr int HX_THREADS = 352;   // warp 0 patch TMA, warp 1 MMA, warps 2-9 epilogue, warp 10 weight TMA
+constexpr int HX_EPI_WARPS = 8;                          // 2 per TMEM lane quarter (16, at 96 registers, were measured slower: residual 3x3 44 -> 47 us, masked VGG dgrads up to 2x)
+constexpr int HX_WPROD_WARP = 2 + HX_EPI_WARPS;          // weight TMA producer
+constexpr int HX_THREADS = 32 * (HX_WPROD_WARP + 1);     // warp 0 patch TMA, warp 1 MMA, then the epilogue warps, then the weight TMA warp
 constexpr int HX_MAX_PBUF = 4;
 constexpr int HX_MAX_WBUF = 4;
 constexpr int HX_TW = 8;
@@ -76,7 +78,7 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     for (int s = 0; s < p.n_pbuf; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
     for (int s = 0; s < p.n_wbuf; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 32 * HX_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -109,7 +111,7 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == HX_WPROD_WARP) {
     if (lane == 0) {
       // ============================ weight producer: one instruction per (cin-chunk, tap group) ============================
       int s = 0; unsigned ph = 0;
@@ -166,10 +168,10 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp < 10) {
+  } else if (warp < HX_WPROD_WARP) {
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;                        // TMEM lane quarter -> output channels slice*128 + q*32 ..
-    const int half = (warp - 2) >> 2;              // accumulator columns half*128 .. : tile rows half*16 ..
+    const int par = (warp - 2) >> 2;               // 32-column chunks (4 tile rows each) k = par, par + HX_EPI_WARPS/4, ..
     PxStep st;
     st.out_r = p.so * out.sh; st.out_c = p.so * out.sw;
     st.add_r = p.so * add.sh; st.add_c = p.so * add.sw;
@@ -189,12 +191,12 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const float b = bias ? bias[ch] : 0.f;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * 256 + half * 128);
+      const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * 256);
       const int j0 = tj * HX_TW;
       const int nvc = max(0, min(HX_TW, jlim - j0));
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int r0 = half * 16 + (c0 >> 3);              // first tile row of this 32-column chunk
+      for (int c0 = par * 32; c0 < 256; c0 += 8 * HX_EPI_WARPS) {
+        const int r0 = c0 >> 3;                            // first tile row of this 32-column chunk
         if (r0 >= p.R) break;                              // warp-uniform: short tiles (R < 32) leave columns unused
         float v[32];
         tc_ld32(taddr0 + c0, v);
@@ -205,7 +207,9 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         off.out = img * out.sn + oy * out.sh + ox * out.sw;
         off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
         off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
-        if (nvr > 0 && nvc > 0)
+        if (nvr == 4 && nvc == 8)
+          px_chunk<8, true>(v, off, st, 4, 8, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
+        else if (nvr > 0 && nvc > 0)
           px_chunk<8>(v, off, st, nvr, nvc, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
       }
       tc_fence_before();

@@ -15,11 +15,18 @@
 // patch per tile (and cin-chunk) serves every virtual tap through shifted descriptors whose 8-pixel groups are
 // SBO = sy patch rows apart.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue (one thread =
 // one (block, channel) lane x 32 pixels of a tcgen05.ld, px_common.cuh).
+// Measured at B=32, 256^2 (scratch/prof_st.py, profiles/r02_summary.md; the same layers on conv_ws.cu before):
+//   first 9x9 layer (9 vertical taps, +stats) 209 -> 86 us, ConvTranspose 64->32 236 -> 77 us, stride-2 data gradient
+//   64->32 256 -> 76 us, last layer forward 175 -> 83 us / data gradient 201 -> 92 us, VGG conv1_1 196 -> 137 us and
+//   its data gradient 161 -> 95 us, ConvTranspose 128->64 104 -> 65 us, stride-2 data gradient 128->64 112 -> 55 us.
+//   With the epilogue removed the first layer takes 56 us (MMA), with the MMAs removed 62 us (epilogue), with both 30 us
+//   (TMA): the kernel runs at the overlap of an MMA-bound and an epilogue-bound pipeline, ~2x its HBM floor.
 #include "px_common.cuh"
 
 namespace ast {
 
-constexpr int ST_THREADS = 320;
+constexpr int ST_EPI_WARPS = 8;    // 2 per TMEM lane quarter (16 were measured slower: 96 registers with spills, first layer 129 -> 226 us)
+constexpr int ST_THREADS = 64 + 32 * ST_EPI_WARPS;
 constexpr int ST_MAX_PBUF = 4;
 constexpr int ST_TW = 8;
 
@@ -61,7 +68,7 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     for (int s = 0; s < p.n_pbuf; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 32 * ST_EPI_WARPS); }
     mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -87,7 +94,7 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d(smem_w + (size_t)(v * p.kchunks + kc) * p.w_tile_bytes, &tm_w, &wbar, kc * p.kc, v * 128);
       int s = 0; unsigned ph = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (long long tile = tile_begin(p.total_tiles), tile_e = tile_end(p.total_tiles); tile < tile_e; ++tile) {
         int tj, ti, img;
         st_tile(p, tile, tj, ti, img);
         const int x0 = tj * ST_TW + p.dx_min, y0 = ti * p.R * p.sy + p.dy_min;
@@ -109,7 +116,7 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const unsigned hi_p = (((unsigned)(p.sy * p.pw * p.rowb)) >> 4) | (1u << 14) | (p.layout_type << 29);          // patch: 8-pixel groups sy rows apart
     const unsigned w_lo0 = ((smem_u32(smem_w) & 0x3FFFFu) >> 4) | (1u << 16);
     const unsigned w16 = (unsigned)p.w_tile_bytes >> 4;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long tile = tile_begin(p.total_tiles), tile_e = tile_end(p.total_tiles); tile < tile_e; ++tile) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
       const unsigned d_tmem = tmem_base + (unsigned)(as * 256);
@@ -144,7 +151,7 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   } else {
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;                        // TMEM lane quarter
-    const int par = (warp - 2) >> 2;               // 32-column chunks (4 grid rows each) of this parity
+    const int par = (warp - 2) >> 2;               // 32-column chunks (4 grid rows each) k = par, par + ST_EPI_WARPS/4, ..
     const int L = q * 32 + lane;
     const int g = L / p.cb, ch = L % p.cb;         // lane block (warp-uniform: cb >= 32) and output channel
     const int oy_g = p.oy[g], ox_g = p.ox[g];
@@ -160,7 +167,7 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     double s1 = 0.0, s2 = 0.0;                     // running InstanceNorm sums of (image, channel): flushed when the image changes
     int s_img = -1;
     const int nchunks = (p.R + 3) >> 2;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long tile = tile_begin(p.total_tiles), tile_e = tile_end(p.total_tiles); tile < tile_e; ++tile) {
       int tj, ti, img;
       st_tile(p, tile, tj, ti, img);
       if (stats && img != s_img) {
@@ -173,7 +180,7 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const int j0 = tj * ST_TW;
       const int nvc = max(0, min(ST_TW, jlim - j0));
 #pragma unroll 1
-      for (int k = par; k < nchunks; k += 2) {
+      for (int k = par; k < nchunks; k += ST_EPI_WARPS / 4) {
         float v[32];
         tc_ld32(taddr0 + (unsigned)(k * 32), v);
         const int r0 = k * 4;
@@ -184,7 +191,9 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         off.out = img * out.sn + oy * out.sh + ox * out.sw;
         off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
         off.mask = mask.ptr ? img * mask.sn + oy * mask.sh + ox * mask.sw : 0;
-        if (nvr > 0 && nvc > 0)
+        if (nvr == 4 && nvc == 8)
+          px_chunk<8, true>(v, off, st, 4, 8, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
+        else if (nvr > 0 && nvc > 0)
           px_chunk<8>(v, off, st, nvr, nvc, ch, lane, b, p.flags, add, mask, out, stats != nullptr, s1, s2);
       }
       tc_fence_before();

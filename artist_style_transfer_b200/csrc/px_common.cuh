@@ -26,28 +26,32 @@ __device__ __forceinline__ void px_st(const Img32& im, int off, float v) {
 //   CW = 0 : lane e holds pixel e's offsets (out < 0 = invalid) and they are broadcast with shuffles.
 struct PxOff { int out, add, mask; };
 struct PxStep { int out_r, out_c, add_r, add_c, mask_r, mask_c; };
-template <int CW>
+//   FULL: every pixel of the chunk is valid (interior tiles): the validity predicates fold away at compile time.
+template <int CW, bool FULL = false>
 __device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxStep& st, int nvr, int nvc, int ch, int lane,
                                          float b, int flags, const Img32& add, const Img32& mask, const Img32& out,
                                          bool want_stats, double& s1, double& s2) {
   constexpr int W = CW ? CW : 1;
   // idx may depend on the lane (bf16 store path): ONE shuffle / one affine evaluation per use
 #define PX_OFF(f, idx) (CW ? off.f + ((idx) / W) * st.f##_r + ((idx) % W) * st.f##_c : __shfl_sync(0xffffffffu, off.f, (idx)))
-#define PX_VALID(idx) (CW ? ((idx) / W < nvr && (idx) % W < nvc) : __shfl_sync(0xffffffffu, off.out, (idx)) >= 0)
+#define PX_VALID(idx) (FULL ? true : (CW ? ((idx) / W < nvr && (idx) % W < nvc) : __shfl_sync(0xffffffffu, off.out, (idx)) >= 0))
   if (want_stats) {
     // InstanceNorm sums of this thread's channel over the chunk: centred on the chunk mean in fp32 (no cancellation),
     // merged into double running sums (sum x, sum x^2 = M2 + cnt * mean^2)
-    float sum = 0.f;
+    // four independent partial sums: the epilogue warps are latency bound (2-4 warps per scheduler)
+    float sa[4] = {0.f, 0.f, 0.f, 0.f};
     int cnt = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e)
-      if (PX_VALID(e)) { sum += v[e]; ++cnt; }
+      if (PX_VALID(e)) { sa[e & 3] += v[e]; ++cnt; }
+    const float sum = (sa[0] + sa[1]) + (sa[2] + sa[3]);
     if (cnt > 0) {
       const float mu = sum / (float)cnt;
-      float m2 = 0.f;
+      float ma[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int e = 0; e < 32; ++e)
-        if (PX_VALID(e)) { const float dlt = v[e] - mu; m2 = fmaf(dlt, dlt, m2); }
+        if (PX_VALID(e)) { const float dlt = v[e] - mu; ma[e & 3] = fmaf(dlt, dlt, ma[e & 3]); }
+      const float m2 = (ma[0] + ma[1]) + (ma[2] + ma[3]);
       s1 += (double)sum;
       s2 += (double)m2 + (double)cnt * ((double)mu * (double)mu);
     }
@@ -87,7 +91,7 @@ __device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxSte
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       const int o = PX_OFF(out, e);
-      if (CW ? PX_VALID(e) : o >= 0) reinterpret_cast<float*>(out.ptr)[o + ch] = v[e];
+      if (FULL || (CW ? PX_VALID(e) : o >= 0)) reinterpret_cast<float*>(out.ptr)[o + ch] = v[e];
     }
   } else {
     // bf16: neighbouring lanes trade values so that every lane stores TWO channels (4 bytes) of one pixel: even lanes
@@ -99,7 +103,7 @@ __device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxSte
       const float give = odd ? v[e] : v[e + 1];          // my channel, the pixel the neighbour stores
       const float got = __shfl_xor_sync(0xffffffffu, give, 1);
       const int o = PX_OFF(out, e + odd);
-      const bool ok = CW ? PX_VALID(e + odd) : o >= 0;
+      const bool ok = FULL || (CW ? PX_VALID(e + odd) : o >= 0);
       const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine) : __floats2bfloat162_rn(mine, got);
       if (ok) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + o + (ch & ~1)) = pk;
     }

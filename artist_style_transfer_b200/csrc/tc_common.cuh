@@ -200,6 +200,15 @@ __device__ __forceinline__ void tc_epi_stats_reduce(const float* v, bool valid, 
   }
   sum = a[0]; sumsq = b[0];
 }
+// conv_st.cu: persistent CTAs walk a CONTIGUOUS range of the tile list (not a grid-strided one): all tiles of a launch
+// cost the same, so the ranges are balanced, and consecutive tiles of a CTA belong to the same image - the running
+// InstanceNorm sums are then flushed once or twice per CTA.  (With the strided order and fewer tiles per image than CTAs
+// every tile started a new image: 2 fp64 atomics per thread and tile onto 2*cout addresses cost the 32-channel 256^2
+// layers ~60 us.)  Measured SLOWER for conv_hx / conv_ws (residual 3x3 44 -> 48 us, VGG conv2_2 223 -> 230 us): their
+// concurrently running CTAs share halo rows and streamed weights in L2 when they work on neighbouring tiles.
+__device__ __forceinline__ long long tile_begin(long long total) { return total * (long long)blockIdx.x / (long long)gridDim.x; }
+__device__ __forceinline__ long long tile_end(long long total) { return total * ((long long)blockIdx.x + 1) / (long long)gridDim.x; }
+
 // Per-thread running sums of the persistent epilogue: (sum x, sum x^2) of up to two 32-channel chunks, kept in DOUBLE across
 // the tiles of one image and flushed with one atomic per quantity when the image changes (a persistent CTA walks the tiles
 // of an image consecutively).  At 1080p a plane has ~16,000 tiles: flushing per tile made 33 M double atomics contend for

@@ -70,8 +70,8 @@ def _vgg_forward(x, module, upto, shift, only_last, need_grad):
             ops.row_im2col(cur, xr, 3, 1, 1, 0, False, shift=shift, round_tf32=True)
             launches = [cg.Launch(h, w, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]
             out = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev)
-            wp, bias = packed[idx]
-            ops.conv_gather(xr, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True)
+            wst, stk, bias = module._packed_conv11_stacked(launches[0])
+            ops.conv_stacked(xr, wst, stk, out, bias=bias, relu=True, round_tf32=True)
             plan.append((idx, "conv", cur, out, None))
             cur = out
         elif kind == "conv":
@@ -159,7 +159,8 @@ def _vgg_backward(module, plan, tensor, tapg):
                 part = torch.empty((out.shape[0], hh, ww + 2, 32), dtype=torch.float32, device=g.device)
                 taps = [(1 - ky, -1) for ky in range(3)]
                 lv = [cg.Launch(hh, ww + 2, 1, 1, 0, 0, taps, [(ky, 0) for ky in range(3)], 0)]
-                ops.conv_gather(g, module._packed_conv11_vdgrad(g.dtype), lv, part, tensor=True)
+                wst, stk = module._packed_conv11_vdgrad_stacked(g.dtype, lv[0])
+                ops.conv_stacked(g, wst, stk, part)
                 ops.fold_rows(part, gx.permute(0, 2, 3, 1), 3)
             else:
                 launches = cg.conv_dgrad(3, 1, 1, out.shape[1], out.shape[2])
@@ -293,6 +294,28 @@ class VGG16(nn.Module, _cnn._Precision):
             pk[:, :9, :] = wv
             self._pack_cache["c11v_key"], self._pack_cache["c11v"] = key, pk.to(dtype).contiguous()
         return self._pack_cache["c11v"]
+
+    def _packed_conv11_stacked(self, launch):
+        """conv1_1's 3-vertical-tap filter stacked for ast_conv_stacked: two interleaved output rows x 64 channels fill the
+        128 TMEM lanes (4 virtual taps instead of 2 x 3 N=64 MMAs per pixel pair)."""
+        stk = cg.stack_rows(launch, 2)
+        key = self._cache_key("c11s", True)
+        if self._pack_cache.get("c11s_key") != key:
+            wp, bias = self._packed(True)[0]                                    # [dy][64][16], TF32-rounded
+            self._pack_cache["c11s_key"] = key
+            self._pack_cache["c11s"] = (ops.stack_filter(lambda pos: wp[pos[0]], stk, 64, 16, torch.float32, wp.device), bias)
+        wst, bias = self._pack_cache["c11s"]
+        return wst, stk, bias
+
+    def _packed_conv11_vdgrad_stacked(self, dtype, launch):
+        """The vertical-tap data-gradient filter of conv1_1 ([ky][32][64]) stacked over four interleaved output rows."""
+        stk = cg.stack_rows(launch, 4)
+        key = self._cache_key("c11vs", dtype)
+        if self._pack_cache.get("c11vs_key") != key:
+            pk = self._packed_conv11_vdgrad(dtype)
+            self._pack_cache["c11vs_key"] = key
+            self._pack_cache["c11vs"] = ops.stack_filter(lambda pos: pk[pos[0]], stk, 32, pk.shape[2], dtype, pk.device)
+        return self._pack_cache["c11vs"], stk
 
     def forward(self, x, shift=None, upto=None, only_last=False):
         if self.just_content or upto == "relu2_2":

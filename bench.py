@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 GF_PER_IMG = {"total": 137.86, "conv_gather": 16.803 + 15.784 + 36.465 + 36.465 + 12.306 + 2.147,
               "wgrad_gather": 16.803, "gram": 1.082}
 IN_ELEMS_PER_IMG = 13.107e6   # elements through the 17 InstanceNorm layers at 256^2
-CONV_FAMILIES = ("conv_hx", "conv_px", "conv_ws", "conv_tc", "conv_simt")
+CONV_FAMILIES = ("conv_hx", "conv_st", "conv_px", "conv_ws", "conv_tc", "conv_simt")
 
 
 def read_peaks():
@@ -148,7 +148,7 @@ def kernel_family(name):
     """Kernel name (as CUPTI reports it) -> family of ast_family_stats, or 'torch/other' for anything not ours."""
     if "ast::" not in name and "fold_rows" not in name:
         return "nccl" if "nccl" in name.lower() else "torch/other"
-    for key, fam in (("conv_hx_kernel", "conv_hx"), ("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"), ("conv_tc_kernel", "conv_tc"),
+    for key, fam in (("conv_hx_kernel", "conv_hx"), ("conv_st_kernel", "conv_st"), ("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"), ("conv_tc_kernel", "conv_tc"),
                      ("conv_gather_simt", "conv_simt"), ("contract_thin", "wgrad_thin"),
                      ("contract_tc_kernel<0>", "wgrad_tc"), ("contract_tc_kernel<1>", "gram_tc"),
                      ("contract_tc_kernel<(int)0>", "wgrad_tc"), ("contract_tc_kernel<(int)1>", "gram_tc"),
@@ -451,7 +451,7 @@ def run_ours(args):
     # bf16: TransformerNet forward / dgrad and the VGG dgrad (36.465)
     tf32_share = (36.465 + 12.306 + 2.147) / GF_PER_IMG["conv_gather"]
     mix_peak = None if not tf32_peak else 1.0 / (tf32_share / tf32_peak + (1 - tf32_share) / peaks["bf16_tflops"])
-    roofline_conv = {"kernel": "all conv fwd/dgrad launches of one step (conv_hx + conv_px + conv_ws + conv_tc kernels)",
+    roofline_conv = {"kernel": "all conv fwd/dgrad launches of one step (conv_hx + conv_st + conv_px + conv_ws + conv_tc kernels)",
                      "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "ms_per_step": conv_ms, "peak_source": f"{peaks['src']} bf16 sustained",
                      "tf32_tflops_measured_here_cublas_8192": tf32_peak, "tf32_flop_share": tf32_share,

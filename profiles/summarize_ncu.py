@@ -17,7 +17,7 @@ KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__cycles_elapsed.
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem"]
-FAMILY = (("conv_hx_kernel", "conv_hx"), ("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"),
+FAMILY = (("conv_hx_kernel", "conv_hx"), ("conv_st_kernel", "conv_st"), ("conv_px_kernel", "conv_px"), ("conv_ws_kernel", "conv_ws"),
           ("conv_tc_kernel", "conv_tc"), ("contract_thin", "wgrad_thin"), ("contract_tc_kernel<(int)0>", "wgrad_tc"),
           ("contract_tc_kernel<(int)1>", "gram_tc"), ("contract_tc_kernel<0>", "wgrad_tc"), ("contract_tc_kernel<1>", "gram_tc"),
           ("in_apply", "in_apply"), ("in_bwd", "in_bwd"), ("maxpool2_bwd", "pool"), ("maxpool2_fwd", "pool_fwd"), ("mse", "mse"), ("adam_pack", "optim"),

@@ -65,7 +65,7 @@ def run(name, dtype, odt, cin, cout, hin, win, launches, hout, wout, mode, stats
     t_old, t_new = timeit(old, sets), timeit(new, sets)
     gf = 2.0 * n * sum(l.mi * l.mj * len(l.taps) for l in launches) * cin * cout / 1e9
     mb = (xs[0].numel() * xs[0].element_size() + ys[0].numel() * ys[0].element_size()) / 1e6
-    print(f"{name:40s} {str(fam):14s} old {t_old:7.1f} us  new {t_new:7.1f} us ({gf/t_new*1e-3:6.1f} TF/s {mb/t_new*1e-3:5.2f} TB/s)  "
+    print(f"{name:40s} {str(fam):14s} old {t_old:7.1f} us  new {t_new:7.1f} us ({gf/t_new*1e3:6.1f} TF/s {mb/t_new:5.2f} TB/s)  "
           f"max|diff| {err:.3e} of {ref:.2f}  stats rel {serr:.1e}  vt={[len(s.vt) for s in stks]}", flush=True)
 
 
@@ -83,4 +83,3 @@ vt3b = [cg.Launch(256, 258, 1, 1, 0, 0, [(1, 0), (0, 0), (-1, 0)], [(0, 0), (1, 
 run("VGG conv1_1 dgrad vt3 64->32 bf16", bf, bf, 64, 32, 256, 258, vt3b, 256, 258, "rows")
 run("T deconv1 3x3 s2 128->64 64^2->128^2 +stats", bf, bf, 128, 64, 64, 64, cg.convT_fwd(3, 2, 1, 1, 64, 64), 128, 128, "phases", stats=True)
 run("T conv3 dgrad 128->64 64^2->130^2", bf, bf, 128, 64, 64, 64, cg.conv_dgrad(3, 2, 0, 130, 130), 130, 130, "phases")
-run("VGG dgrad conv1_2 64->64 bf16 +mask", bf, bf, 64, 64, 256, 256, cg.conv_dgrad(3, 1, 1, 256, 256), 256, 256, "rows", mask=True)

@@ -263,3 +263,77 @@ def test_gram_mse_fused(env, c, h, w, n, shared):
     assert not torch.isnan(d).any()
     assert rel(d, 3.0 * diff) < 1e-3                              # D is rounded to TF32 (it feeds a kind::tf32 conv)
     assert float((d - d.transpose(1, 2)).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Block-stacked kernel (ast_conv_stacked, conv_st.cu): same results as the plain gather launches it replaces.
+STACKED_CASES = [
+    # name, dtype, cin, cout, n, (hin, win), (hout, wout), launches builder
+    ("convT 64->32", torch.bfloat16, 64, 32, 2, (9, 13), (18, 26), lambda cg: cg.convT_fwd(3, 2, 1, 1, 9, 13)),
+    ("convT 128->64", torch.bfloat16, 128, 64, 1, (16, 16), (32, 32), lambda cg: cg.convT_fwd(3, 2, 1, 1, 16, 16)),
+    ("s2 dgrad 64->32 odd", torch.bfloat16, 64, 32, 2, (8, 11), (19, 25), lambda cg: cg.conv_dgrad(3, 2, 0, 19, 25)),
+    ("s2 dgrad 128->64", torch.bfloat16, 128, 64, 1, (16, 8), (34, 18), lambda cg: cg.conv_dgrad(3, 2, 0, 34, 18)),
+    ("rows 9 taps 32->32", torch.bfloat16, 32, 32, 2, (41, 20), (33, 20),
+     lambda cg: [cg.Launch(33, 20, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]),
+    ("rows 9 taps up 32->32", torch.bfloat16, 32, 32, 1, (20, 17), (28, 17),
+     lambda cg: [cg.Launch(28, 17, 1, 1, 0, 0, [(-d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]),
+    ("rows 3 taps 16->64 tf32", torch.float32, 16, 64, 2, (21, 24), (21, 24),
+     lambda cg: [cg.Launch(21, 24, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]),
+    ("rows 3 taps dx -1 64->32", torch.bfloat16, 64, 32, 1, (16, 30), (16, 32),
+     lambda cg: [cg.Launch(16, 32, 1, 1, 0, 0, [(1, -1), (0, -1), (-1, -1)], [(0, 0), (1, 0), (2, 0)], 0)]),
+    ("rows tall 9 taps 32->32", torch.bfloat16, 32, 32, 1, (272, 8), (264, 8),
+     lambda cg: [cg.Launch(264, 8, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]),
+]
+
+
+@pytest.mark.parametrize("name,dtype,cin,cout,n,hw_in,hw_out,build", STACKED_CASES, ids=[c[0] for c in STACKED_CASES])
+@pytest.mark.parametrize("epi", ["plain", "stats", "bias_relu_mask_add"])
+def test_conv_stacked_matches_the_plain_launches(env, name, dtype, cin, cout, n, hw_in, hw_out, build, epi):
+    cg, ops = env
+    from artist_style_transfer_b200 import _lib, arena
+    torch.manual_seed(len(name) + cin)
+    launches = build(cg)
+    nt = sum(len(l.taps) for l in launches)
+    x = tf32_round(torch.randn(n, *hw_in, cin, device="cuda")).to(dtype)
+    wp = tf32_round(torch.randn(nt, cout, cin, device="cuda") / (cin * 4) ** 0.5).to(dtype)
+    tidx = {wt: l.woff + t for l in launches for t, wt in enumerate(l.wtaps)}
+    odt = torch.float32 if dtype == torch.float32 or epi == "plain" else torch.bfloat16
+    kw = {}
+    if epi == "bias_relu_mask_add":
+        kw = dict(bias=torch.randn(cout, device="cuda"), relu=True,
+                  mask=torch.randn(n, *hw_out, cout, device="cuda").to(torch.bfloat16),
+                  add=torch.randn(n, *hw_out, cout, device="cuda").to(odt))
+    ref = torch.full((n, *hw_out, cout), float("nan"), device="cuda", dtype=odt)
+    got = torch.full_like(ref, float("nan"))
+    s_ref = torch.zeros(n, cout, 2, dtype=torch.float64, device="cuda") if epi == "stats" else None
+    s_got = torch.zeros_like(s_ref) if epi == "stats" else None
+    ops.conv_gather(x, wp, launches, ref, tensor=True, stats=s_ref, **kw)
+    before = _lib.family_stats()
+    for stk in arena.stack_groups(launches, cout):
+        ws = ops.stack_filter(lambda pos: wp[tidx[pos]], stk, cout, cin, dtype, "cuda")
+        ops.conv_stacked(x, ws, stk, got, stats=s_got, **kw)
+    delta = _lib.family_delta(before)
+    assert delta["conv_st"][0] == (1 if len(launches) == 1 or cout == 32 else 2)
+    flops = 2.0 * n * sum(l.mi * l.mj * len(l.taps) for l in launches) * cin * cout
+    assert abs(delta["conv_st"][1] - flops) <= 0.1 * flops      # interleaved rows round mi up to a multiple of nblk
+    torch.cuda.synchronize()
+    assert not torch.isnan(got.float()).any()
+    # same operands, fp32 accumulation: only the summation order differs (one bf16 rounding when the output is bf16)
+    tol = 1e-5 if odt == torch.float32 else 6e-3
+    assert rel(got, ref) < tol, rel(got, ref)
+    if odt == torch.bfloat16:
+        assert float((got.float() - ref.float()).abs().max()) <= 2 ** -7 * float(ref.float().abs().max())
+    if epi == "stats":
+        assert rel(s_got, s_ref) < 1e-6
+
+
+def test_conv_stacked_argument_errors(env):
+    cg, ops = env
+    stk = cg.stack_phases(cg.convT_fwd(3, 2, 1, 1, 8, 8))
+    x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(len(stk.vt), 128, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="contiguous channels"):
+        ops.conv_stacked(x, w, stk, torch.zeros(1, 16, 16, 64, device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="64 bytes or a multiple of 128"):
+        ops.conv_stacked(x[..., :48].contiguous(), w[..., :48].contiguous(), stk,
+                         torch.zeros(1, 16, 16, 32, device="cuda", dtype=torch.bfloat16))

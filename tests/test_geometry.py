@@ -168,8 +168,7 @@ def test_sizes():
 
 
 def _emulate_pack(w, pack, dims):
-    """What ast_adam_step writes for one packed copy: element (a,b,u,v) -> a*s0 + b*s1 + taps[u*V+v] (include/ast.h)."""
-    import torch
+    """What ast_adam_step writes: element (a, b, u, v) -> off + a*stride[0] + b*stride[1] + taps[u*V + v] (+ r*rep_stride)."""
     A, B, U, V = dims
     n = 1
     for d in pack.shape:
@@ -178,10 +177,29 @@ def _emulate_pack(w, pack, dims):
     ib = torch.arange(B).view(1, B, 1) * pack.stride[1]
     it = torch.tensor(pack.taps, dtype=torch.int64).view(1, 1, U * V)
     offs = (ia + ib + it).reshape(-1)
-    assert int(torch.bincount(offs, minlength=n).max()) == 1, "two master elements map to the same packed slot"
     flat = torch.zeros(n, dtype=torch.float64)
-    flat[offs] = w.reshape(-1)
+    count = torch.zeros(n, dtype=torch.int64)
+    for r in range(pack.rep):
+        count += torch.bincount(offs + r * pack.rep_stride, minlength=n)
+        flat[offs + r * pack.rep_stride] = w.reshape(-1)
+    assert int(count.max()) == 1, "two master elements map to the same packed slot"
     return flat.view(pack.shape)
+
+
+def _check_stacked(got, pack, cb, tile_of):
+    """A stacked filter holds tile_of(kernel position) in rows [b*cb, (b+1)*cb) of virtual tap v wherever the canonical
+    conv_geometry.Stacked launch lists that position, and zeros everywhere else."""
+    seen = 0
+    for grp, vb in zip(pack.stacked, pack.vbase):
+        for v, row in enumerate(grp.src):
+            for b, pos in enumerate(row):
+                blk = got[vb + v, b * cb:(b + 1) * cb]
+                if pos is None:
+                    assert float(blk.abs().sum()) == 0.0
+                else:
+                    assert torch.equal(blk, tile_of(pos)), (v, b, pos)
+                    seen += 1
+    assert seen == sum(g.ntaps for g in pack.stacked)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fast"])
@@ -202,7 +220,26 @@ def test_arena_layouts_match_the_gather_kernels_operand_layouts(mode):
         conv = st.kind == "conv"
         # ---- forward pack
         got = _emulate_pack(w, pl.fwd, dims)
-        if pl.thin_in:
+        if pl.fwd.stacked is not None:
+            assert mode == "fast"
+            if pl.thin_in:
+                def tile(pos):
+                    t = torch.zeros(co, 32, dtype=torch.float64)
+                    for dx in range(k):
+                        t[:, dx * ci:(dx + 1) * ci] = w[:, :, pos[0], dx]
+                    return t
+                _check_stacked(got, pl.fwd, co, tile)
+            elif pl.thin_out:
+                def tile(pos):
+                    t = torch.zeros(32, ci, dtype=torch.float64)
+                    for dx in range(k):
+                        t[dx * co:(dx + 1) * co] = w[:, :, pos[0], dx]
+                    return t
+                _check_stacked(got, pl.fwd, 32, tile)
+            else:
+                assert not conv and st.stride == 2
+                _check_stacked(got, pl.fwd, co, lambda pos: w[:, :, pos[0], pos[1]].t())
+        elif pl.thin_in:
             for dy in range(k):
                 for dx in range(k):
                     assert torch.equal(got[dy, :, dx * ci:(dx + 1) * ci], w[:, :, dy, dx])
@@ -221,7 +258,18 @@ def test_arena_layouts_match_the_gather_kernels_operand_layouts(mode):
         # ---- data-gradient pack
         if pl.dgrad is not None:
             got = _emulate_pack(w, pl.dgrad, dims)
-            if pl.thin_out:
+            if pl.dgrad.stacked is not None:
+                if pl.thin_out:
+                    def tile(pos):
+                        t = torch.zeros(ci, 32, dtype=torch.float64)
+                        for dx in range(k):
+                            t[:, dx * co:(dx + 1) * co] = w[:, :, pos[0], dx].t()
+                        return t
+                    _check_stacked(got, pl.dgrad, ci, tile)
+                else:
+                    assert conv and st.stride == 2
+                    _check_stacked(got, pl.dgrad, ci, lambda pos: w[:, :, pos[0], pos[1]].t())
+            elif pl.thin_out:
                 for dy in range(k):
                     for dx in range(k):
                         assert torch.equal(got[dy, :, dx * co:(dx + 1) * co], w[:, :, dy, dx].t())

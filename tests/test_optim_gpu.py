@@ -65,6 +65,12 @@ def test_fused_adam_matches_oracle_and_repacks(ast, precision):
             want = ops.pack_weights(w, launches, st.cout, st.cin, st.cin * k2, k2, st.k, 1, adt)
         else:
             want = ops.pack_weights(w, launches, st.cout, st.cin, k2, st.cout * k2, st.k, 1, adt)
+        if pl.fwd.stacked is not None:      # block-stacked filter (ConvTranspose phases): the same tiles, re-arranged
+            tidx = {wt: l.woff + t for l in launches for t, wt in enumerate(l.wtaps)}
+            for grp, vb in zip(pl.fwd.stacked, pl.fwd.vbase):
+                ws = ops.stack_filter(lambda pos: want[tidx[pos]], grp, st.cout, st.cin, adt, want.device)
+                assert torch.equal(pl.fwd.tensor[vb:vb + len(grp.vt)], ws), (st.kind, st.k, st.stride)
+            continue
         assert torch.equal(pl.fwd.tensor, want), (st.kind, st.k, st.stride)
 
 
