@@ -68,10 +68,13 @@ __device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxSte
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] += t[e];
   }
+  // the layers under an InstanceNorm have neither bias nor activation here: skip the 64 instructions
+  if (flags & AST_CONV_RELU) {
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    v[e] += b;
-    if (flags & AST_CONV_RELU) v[e] = fmaxf(v[e], 0.f);
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e] + b, 0.f);
+  } else if (b != 0.f) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] += b;
   }
   if (mask.ptr) {
     float t[32];
@@ -97,15 +100,18 @@ __device__ __forceinline__ void px_chunk(float* v, const PxOff& off, const PxSte
     // bf16: neighbouring lanes trade values so that every lane stores TWO channels (4 bytes) of one pixel: even lanes
     // serve pixel e, odd lanes pixel e+1 -> 16 store instructions of 2 x 64 B instead of 32 of 64 B
     const int odd = lane & 1;
+    __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(out.ptr) + (ch & ~1);
+    // CW > 0: the offset of pixel e + odd is affine in compile-time (e / CW, e % CW) plus one lane-dependent term
+    const int lane_off = CW ? off.out + odd * st.out_c : 0;
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       const float mine = odd ? v[e + 1] : v[e];          // my channel, the pixel I store
       const float give = odd ? v[e] : v[e + 1];          // my channel, the pixel the neighbour stores
       const float got = __shfl_xor_sync(0xffffffffu, give, 1);
-      const int o = PX_OFF(out, e + odd);
+      const int o = CW ? lane_off + (e / W) * st.out_r + (e % W) * st.out_c : PX_OFF(out, e + odd);
       const bool ok = FULL || (CW ? PX_VALID(e + odd) : o >= 0);
       const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine) : __floats2bfloat162_rn(mine, got);
-      if (ok) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out.ptr) + o + (ch & ~1)) = pk;
+      if (ok) *reinterpret_cast<__nv_bfloat162*>(obase + o) = pk;
     }
   }
 #undef PX_VALID
