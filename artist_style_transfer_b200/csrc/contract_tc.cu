@@ -13,7 +13,26 @@
 
 namespace ast {
 
-constexpr int CT_THREADS = 192;
+constexpr int CT_MAX_PROD = 4;                  // TMA producer warps: warp 0 and warps 6..8
+constexpr int CT_THREADS = 192 + 32 * (CT_MAX_PROD - 1);
+// A thread pays ~500 cycles per TMA instruction (wait + expect_tx + issue), and the filter-gradient stages need 2 to 10
+// of them for 8 to 16 MMAs: with one producer the 32/64-channel layers ran at ~500 clk per MMA.  The stages are dealt
+// round-robin to `nprod` producer WARPS (lanes of one warp do not help: divergent spin loops time-slice each other);
+// nprod divides the stage count, so consecutive uses of one stage belong to the same producer and the 1-bit mbarrier
+// parity cannot alias.
+// (Measured and removed: a "halo" mode loading ONE (th + hy) x (tw + hx) patch per 64-channel box for all taps of a CTA
+// and addressing the taps through shifted MN-major descriptors.  It halves the L2 -> shared memory traffic of the 3x3
+// filter gradients but ran 1.8x SLOWER (residual layers 61 -> 107 us, results identical) - presumably MN-major operands
+// that do not start on a 1024-byte swizzle atom are fetched at a fraction of the aligned rate; not investigated further.)
+__device__ __forceinline__ int ct_producer_index(int warp) { return warp == 0 ? 0 : (warp >= 6 ? warp - 5 : -1); }
+// most producers first, then most stages: gives up at most two stages to make the stage count divisible
+inline void ct_pick_producers(int& stages, int& nprod) {
+  int best_d = 1, best_s = stages;
+  for (int st = stages; st >= 2 && st >= stages - 2; --st)
+    for (int d = CT_MAX_PROD; d >= 2; --d)
+      if (st % d == 0 && d > best_d) { best_d = d; best_s = st; }
+  stages = best_s; nprod = best_d;
+}
 constexpr int CT_MAX_STAGES = 8;
 
 struct CtParams {
@@ -25,7 +44,7 @@ struct CtParams {
   long long chunks_total;           // per image when per_img, else over all images
   long long out_img_stride, s_m, s_n;
   float scale;
-  int stages, box_bytes, stage_bytes, umma_k_bytes, kmma, upper_only;
+  int stages, nprod, box_bytes, stage_bytes, umma_k_bytes, kmma, upper_only;
   int tg, ngroups;                  // taps handled by one CTA (rows operand loaded once per stage for all of them)
   int same;                         // Gram: rows and cols are the SAME tensor at the same pixels (see shared_r below)
   unsigned sbo, layout_type;
@@ -115,10 +134,13 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
   // column boxes: no second TMA load of the same pixels (rows past m_valid read whatever follows and are ignored)
   const bool shared_r = p.same && m0 >= n0 && min(m0 + 128, p.m_valid) <= n0 + p.bn;
 
-  if (warp == 0) {
-    int s = 0; unsigned ph = 0;
+  const int prod = ct_producer_index(warp);
+  if (prod >= 0) {
+    if (prod < p.nprod) {
     const int per_img_chunks = p.tiles_i * p.tiles_j;
-    for (long long c = cbeg; c < cend; ++c) {
+    for (long long c = cbeg + prod; c < cend; c += p.nprod) {
+      const int s = (int)((c - cbeg) % p.stages);
+      const unsigned ph = (unsigned)(((c - cbeg) / p.stages) & 1);
       int img, rem;
       if (p.per_img) { img = img_fixed; rem = (int)c; }
       else { img = (int)(c / per_img_chunks); rem = (int)(c % per_img_chunks); }
@@ -137,7 +159,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_consta
                         p.c_s * j0 + p.dx[t0 + u], p.c_s * i0 + p.dy[t0 + u], img);
       }
       __syncwarp();
-      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
     }
   } else if (warp == 1) {
     int s = 0; unsigned ph = 0;
@@ -391,7 +413,7 @@ static int check_operand(const char* who, const ast_image* im) {
 struct CtThinParams {
   int mi, mj, tw, th, tiles_i, tiles_j, n_img;
   int r_s, r_oy, r_ox, c_s;
-  int ntaps, ngrp, r_valid, c_valid, chunks_per_cta, stages, stage_bytes;
+  int ntaps, ngrp, r_valid, c_valid, chunks_per_cta, stages, nprod, stage_bytes;
   int vstack;                       // all taps are consecutive rows of one column and a chunk is one 64-pixel row segment:
                                     // ONE box of ntaps rows replaces ntaps loads (tap t = 4 KB further into it)
   long long chunks_total, s_m, s_n;
@@ -435,10 +457,10 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
   const unsigned tmem_base = tmem_slot;
   const int padded_taps = p.ngrp * 4;          // box slots of the shifted operand per stage (slots >= ntaps stay unwritten)
 
-  if (warp == 0) {
-    int s = 0; unsigned ph = 0;
+  const int prod = ct_producer_index(warp);
+  if (prod >= 0) {
     const int per_img_chunks = p.tiles_i * p.tiles_j;
-    if (lane == 0) {       // unwritten tap slots feed only ignored accumulator rows, but keep them finite: zero once
+    if (warp == 0 && lane == 0) {   // unwritten tap slots feed only ignored accumulator rows, but keep them finite: zero once
       for (int st = 0; st < p.stages; ++st)
         for (int t = p.ntaps; t < padded_taps; ++t) {
           uint4* z = (uint4*)(smem + (size_t)st * p.stage_bytes + (1 + t) * THIN_BOX);
@@ -447,7 +469,10 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    for (long long c = cbeg; c < cend; ++c) {
+    if (prod < p.nprod) {
+    for (long long c = cbeg + prod; c < cend; c += p.nprod) {
+      const int s = (int)((c - cbeg) % p.stages);
+      const unsigned ph = (unsigned)(((c - cbeg) / p.stages) & 1);
       const int img = (int)(c / per_img_chunks), rem = (int)(c % per_img_chunks);
       const int ti = rem / p.tiles_j, tj = rem % p.tiles_j;
       const int i0 = ti * p.th, j0 = tj * p.tw;
@@ -463,7 +488,7 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
             tma_load_4d(sr + (1 + t) * THIN_BOX, &tm_c, &full_bar[s], 0, p.c_s * j0 + p.dx[t], p.c_s * i0 + p.dy[t], img);
       }
       __syncwarp();
-      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
     }
   } else if (warp == 1) {
     int s = 0; unsigned ph = 0;
@@ -546,6 +571,7 @@ static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, i
   p.stage_bytes = (1 + 4 * p.ngrp) * THIN_BOX;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
+  ct_pick_producers(p.stages, p.nprod);
   if (p.stages < 2) return 0;
   // bf16 A/B (1), both MN-major (bits 15, 16), N = 32, M = 128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
@@ -626,6 +652,7 @@ int contract_tc(const ast_image* rows, int r_s, int r_oy, int r_ox, const ast_im
   p.stage_bytes = (p.m_boxes + p.tg * p.n_boxes) * p.box_bytes;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
+  ct_pick_producers(p.stages, p.nprod);
   AST_CHECK_ARG(p.stages >= 2, "contract_tc: tile does not fit shared memory");
   p.umma_k_bytes = (32 / esz) * 128;                 // UMMA_K pixel rows (16 bf16 / 8 tf32) x 128 B
   p.kmma = p.kp / (32 / esz);

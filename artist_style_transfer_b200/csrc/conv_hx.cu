@@ -39,7 +39,10 @@ constexpr int HX_TW = 8;
 struct HxParams {
   int mi, mj, tiles_i, tiles_j, n_img, n_slices, R;
   int ntaps, kchunks, kc, cout, flags;
-  int so, oy0, ox0;
+  // output mapping: the 128 TMEM lanes of a slice are nblk blocks of cb channels (plain launches: one block of 128);
+  // block g writes pixel (oy[g] + soy * i, ox[g] + sox * j) for grid point (i, j), which reads input row sy * i + dy
+  int nblk, cb, sy, soy, sox, cstat;                         // cstat: channels per image in the statistics array
+  int oy[4], ox[4];
   int dy_min, dx_min, ph, pw;
   int patch_bytes, patch_tx, n_pbuf, n_wbuf, tg, ngroups;   // tg taps per weight slot (one TMA instruction), ngroups per cin-chunk
   unsigned idesc;
@@ -102,7 +105,7 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int slice, tj, ti, img;
         hx_tile(p, tile, slice, tj, ti, img);
-        const int x0 = tj * HX_TW + p.dx_min, y0 = ti * p.R + p.dy_min;
+        const int x0 = tj * HX_TW + p.dx_min, y0 = ti * p.R * p.sy + p.dy_min;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&pempty[s], ph ^ 1);
           mbar_expect_tx(&pfull[s], (unsigned)p.patch_tx);
@@ -132,7 +135,7 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // ============================ MMA issuer ============================
     int ps = 0; unsigned pph = 0; int ws = 0; unsigned wph = 0; int as = 0; unsigned aph = 0;
     const unsigned hi_w = ((8u * 128u) >> 4) | (1u << 14) | (2u << 29);                 // weights: dense 128-byte rows
-    const unsigned hi_p = (((unsigned)p.pw * 128u) >> 4) | (1u << 14) | (2u << 29);     // patch: 8-pixel tile rows, SBO = row pitch
+    const unsigned hi_p = (((unsigned)(p.sy * p.pw) * 128u) >> 4) | (1u << 14) | (2u << 29);   // patch: 8-pixel tile rows, SBO = sy row pitches
     const unsigned w_base = smem_u32(smem_w), p_base = smem_u32(smem_p);
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
@@ -172,20 +175,24 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;                        // TMEM lane quarter -> output channels slice*128 + q*32 ..
     const int par = (warp - 2) >> 2;               // 32-column chunks (4 tile rows each) k = par, par + HX_EPI_WARPS/4, ..
+    const int L = q * 32 + lane;
+    const int blk = L / p.cb, chl = L % p.cb;      // lane block (warp-uniform: cb >= 32) and channel inside the block
+    const int oy_g = p.oy[blk], ox_g = p.ox[blk];
     PxStep st;
-    st.out_r = p.so * out.sh; st.out_c = p.so * out.sw;
-    st.add_r = p.so * add.sh; st.add_c = p.so * add.sw;
-    st.mask_r = p.so * mask.sh; st.mask_c = p.so * mask.sw;
-    const int jlim = min(p.mj, (out.w - p.ox0 + p.so - 1) / p.so), ilim = min(p.mi, (out.h - p.oy0 + p.so - 1) / p.so);
+    st.out_r = p.soy * out.sh; st.out_c = p.sox * out.sw;
+    st.add_r = p.soy * add.sh; st.add_c = p.sox * add.sw;
+    st.mask_r = p.soy * mask.sh; st.mask_c = p.sox * mask.sw;
+    const int jlim = min(p.mj, ox_g < out.w ? (out.w - ox_g + p.sox - 1) / p.sox : 0);
+    const int ilim = min(p.mi, oy_g < out.h ? (out.h - oy_g + p.soy - 1) / p.soy : 0);
     int as = 0; unsigned aph = 0;
     double s1 = 0.0, s2 = 0.0;                     // running InstanceNorm sums of (image, channel): flushed when either changes
     int s_img = -1, s_ch = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int slice, tj, ti, img;
       hx_tile(p, tile, slice, tj, ti, img);
-      const int ch = slice * 128 + q * 32 + lane;
+      const int ch = slice * 128 + chl;
       if (stats && (img != s_img || ch != s_ch)) {
-        if (s_img >= 0) { double* srow = stats + ((long long)s_img * p.cout + s_ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
+        if (s_img >= 0) { double* srow = stats + ((long long)s_img * p.cstat + s_ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
         s1 = s2 = 0.0; s_img = img; s_ch = ch;
       }
       const float b = bias ? bias[ch] : 0.f;
@@ -202,7 +209,7 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         tc_ld32(taddr0 + c0, v);
         const int i0 = ti * p.R + r0;
         const int nvr = max(0, min(min(4, p.R - r0), ilim - i0));
-        const int oy = p.oy0 + p.so * i0, ox = p.ox0 + p.so * j0;
+        const int oy = oy_g + p.soy * i0, ox = ox_g + p.sox * j0;
         PxOff off;
         off.out = img * out.sn + oy * out.sh + ox * out.sw;
         off.add = add.ptr ? img * add.sn + oy * add.sh + ox * add.sw : 0;
@@ -216,7 +223,7 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-    if (stats && s_img >= 0) { double* srow = stats + ((long long)s_img * p.cout + s_ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
+    if (stats && s_img >= 0) { double* srow = stats + ((long long)s_img * p.cstat + s_ch) * 2; atomicAdd(srow, s1); atomicAdd(srow + 1, s2); }
   }
 
   tc_fence_before();
@@ -227,50 +234,63 @@ conv_hx_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   }
 }
 
-// 1 = launched, 0 = not applicable (the caller continues with conv_px / conv_tc), other = error.
-int conv_gather_hx(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
-                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
-                   cudaStream_t stream) {
-  static const int enabled = [] { const char* e = getenv("AST_CONV_HX"); return e ? atoi(e) : 1; }();   // A/B switch
-  if (!enabled) return 0;
-  if (thin || g->pooled || g->w_img_stride != 0 || g->si != 1 || cpad % 128 != 0 || out->c != cpad) return 0;
+// Geometry of one launch in the kernel's general form (plain gather launches and block-stacked ones, include/ast.h).
+struct HxGeom {
+  int mi, mj, ntaps, flags;
+  int nblk, cb, sy, soy, sox, cstat;                         // cstat: channels per image in the statistics array
+  int oy[4], ox[4];
+  const int16_t* dy;
+  const int16_t* dx;
+  double* stats;
+};
+
+// 1 = launched, 0 = not applicable, other = error.  cout = rows of the packed filter per tap (128 * slices).
+static int hx_launch(const ast_image* in, const void* weights, const float* bias, const ast_image* add, const ast_image* mask,
+                     const ast_image* out, const HxGeom& g, int cout, cudaStream_t stream) {
   if (!img32_ok(out) || !img32_ok(add) || !img32_ok(mask)) return 0;
   const int esz = in->dtype == AST_F32 ? 4 : 2;
-  if ((in->c * esz) % 128 != 0) return 0;
+  if ((in->c * esz) % 128 != 0 || cout % 128 != 0) return 0;
   int dy_min = 1 << 30, dy_max = -(1 << 30), dx_min = 1 << 30, dx_max = -(1 << 30);
-  for (int t = 0; t < g->ntaps; ++t) {
-    dy_min = g->dy[t] < dy_min ? g->dy[t] : dy_min; dy_max = g->dy[t] > dy_max ? g->dy[t] : dy_max;
-    dx_min = g->dx[t] < dx_min ? g->dx[t] : dx_min; dx_max = g->dx[t] > dx_max ? g->dx[t] : dx_max;
+  for (int t = 0; t < g.ntaps; ++t) {
+    dy_min = g.dy[t] < dy_min ? g.dy[t] : dy_min; dy_max = g.dy[t] > dy_max ? g.dy[t] : dy_max;
+    dx_min = g.dx[t] < dx_min ? g.dx[t] : dx_min; dx_max = g.dx[t] > dx_max ? g.dx[t] : dx_max;
   }
-  if (dx_max - dx_min > 4 || dy_max - dy_min > 4) return 0;
+  if (dx_max - dx_min > 4 || dy_max - dy_min > 8) return 0;
   HxParams p;
   memset(&p, 0, sizeof(p));
   p.kc = 128 / esz;
   p.kchunks = in->c / p.kc;
-  if (g->ntaps * p.kchunks < 8) return 0;          // short K loops are epilogue bound: conv_px / conv_tc take them
+  if (g.ntaps * p.kchunks < 8) return 0;           // short K loops are epilogue bound: conv_px / conv_tc take them
   EncodeTiledFn encode = get_encode();
   if (!encode) return 0;
-  p.mi = g->mi; p.mj = g->mj; p.so = g->so; p.oy0 = g->oy0; p.ox0 = g->ox0;
-  p.ntaps = g->ntaps; p.flags = g->flags; p.cout = cpad; p.n_img = in->n; p.n_slices = cpad / 128;
+  p.mi = g.mi; p.mj = g.mj;
+  p.nblk = g.nblk; p.cb = g.cb; p.sy = g.sy; p.soy = g.soy; p.sox = g.sox;
+  for (int b = 0; b < 4; ++b) { p.oy[b] = g.oy[b]; p.ox[b] = g.ox[b]; }
+  p.cstat = g.nblk == 1 ? cout : g.cb;
+  p.ntaps = g.ntaps; p.flags = g.flags; p.cout = cout; p.n_img = in->n; p.n_slices = cout / 128;
   p.dy_min = dy_min; p.dx_min = dx_min;
-  for (int t = 0; t < g->ntaps; ++t) { p.tdy[t] = g->dy[t] - dy_min; p.tdx[t] = g->dx[t] - dx_min; }
-  // tile rows: as few row tiles as possible, split evenly (66 rows -> 3 x 22 instead of 32 + 32 + 2).  (N = 128 tiles,
-  // 5 x 16 rows, were measured SLOWER for the 66-row gradients, 68 vs 50 us: an N = 128 MMA needs 126 B/clk of operand
-  // fetch for its 65 clk and loses more to the concurrent TMA / epilogue shared-memory traffic than an N = 176 one.)
-  p.tiles_i = (p.mi + 31) / 32;
+  for (int t = 0; t < g.ntaps; ++t) { p.tdy[t] = g.dy[t] - dy_min; p.tdx[t] = g.dx[t] - dx_min; }
+  p.pw = HX_TW + (dx_max - dx_min);
+  const int budget = 225 * 1024 - 1024;
+  p.tg = g.ntaps % 3 == 0 ? 3 : (g.ntaps % 2 == 0 ? 2 : (g.ntaps >= 3 ? 3 : g.ntaps));
+  p.ngroups = (g.ntaps + p.tg - 1) / p.tg;
+  const int w_slot = p.tg * 128 * 128;
+  // tile rows: as few row tiles as possible, split evenly (66 rows -> 3 x 22 instead of 32 + 32 + 2); fewer rows per tile
+  // when two patches (sy > 1: taller halos) and two weight slots would not fit.  (N = 128 tiles, 5 x 16 rows, were
+  // measured SLOWER for the 66-row gradients, 68 vs 50 us: an N = 128 MMA needs 126 B/clk of operand fetch for its 65
+  // clk and loses more to the concurrent TMA / epilogue shared-memory traffic than an N = 176 one.)
+  auto patch_rows = [&](int R) { return (R - 1) * p.sy + (dy_max - dy_min) + 1; };
+  int rmax = 32;
+  while (rmax > 2 && (2 * ((p.pw * patch_rows(rmax) * 128 + 1023) & ~1023) + 2 * w_slot > budget || patch_rows(rmax) > 256)) rmax -= 2;
+  p.tiles_i = (p.mi + rmax - 1) / rmax;
   p.R = (p.mi + p.tiles_i - 1) / p.tiles_i;
   p.R = (p.R + 1) & ~1;                             // N = 8 R must be a multiple of 16
   p.tiles_i = (p.mi + p.R - 1) / p.R;
   p.tiles_j = (p.mj + HX_TW - 1) / HX_TW;
   p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j * p.n_slices;
-  p.pw = HX_TW + (dx_max - dx_min);
-  p.ph = p.R + (dy_max - dy_min);
+  p.ph = patch_rows(p.R);
   p.patch_tx = p.pw * p.ph * 128;
   p.patch_bytes = (p.patch_tx + 1023) & ~1023;
-  const int budget = 225 * 1024 - 1024;
-  p.tg = g->ntaps % 3 == 0 ? 3 : (g->ntaps % 2 == 0 ? 2 : (g->ntaps >= 3 ? 3 : g->ntaps));
-  p.ngroups = (g->ntaps + p.tg - 1) / p.tg;
-  const int w_slot = p.tg * 128 * 128;
   p.n_pbuf = 2;
   p.n_wbuf = (budget - p.n_pbuf * p.patch_bytes) / w_slot;
   if (p.n_wbuf < 2) return 0;
@@ -290,8 +310,8 @@ int conv_gather_hx(const ast_image* in, const void* weights, const float* bias, 
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return r;
   }
   {   // packed weights [tap][cout][cin] as a 3-D tensor: a box is tg taps x 128 output channels x one cin-chunk
-    cuuint64_t dims[3] = {(cuuint64_t)in->c, (cuuint64_t)cpad, (cuuint64_t)g->ntaps};
-    cuuint64_t strides[2] = {(cuuint64_t)in->c * esz, (cuuint64_t)cpad * in->c * esz};
+    cuuint64_t dims[3] = {(cuuint64_t)in->c, (cuuint64_t)cout, (cuuint64_t)g.ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)in->c * esz, (cuuint64_t)cout * in->c * esz};
     cuuint32_t box[3] = {(cuuint32_t)p.kc, 128, (cuuint32_t)p.tg};
     cuuint32_t estr[3] = {1, 1, 1};
     if (int r = cached_tensor_map(encode, &tm_w, dt, 3, const_cast<void*>(weights), dims, strides, box, estr,
@@ -302,16 +322,50 @@ int conv_gather_hx(const ast_image* in, const void* weights, const float* bias, 
   cudaError_t e;
   if (in->dtype == AST_BF16) {
     e = set_max_smem(conv_hx_kernel<0>, smem);
-    if (e == cudaSuccess) launch_k(conv_hx_kernel<0>, grid, HX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+    if (e == cudaSuccess) launch_k(conv_hx_kernel<0>, grid, HX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g.stats);
   } else {
     e = set_max_smem(conv_hx_kernel<1>, smem);
-    if (e == cudaSuccess) launch_k(conv_hx_kernel<1>, grid, HX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
+    if (e == cudaSuccess) launch_k(conv_hx_kernel<1>, grid, HX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g.stats);
   }
   if (e != cudaSuccess) { set_error("conv_hx: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
+  return 1;
+}
+
+// 1 = launched, 0 = not applicable (the caller continues with conv_px / conv_tc), other = error.
+int conv_gather_hx(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                   const ast_image* mask, const ast_image* out, const ast_gather_geom* g, int cpad, bool thin,
+                   cudaStream_t stream) {
+  static const int enabled = [] { const char* e = getenv("AST_CONV_HX"); return e ? atoi(e) : 1; }();   // A/B switch
+  if (!enabled) return 0;
+  if (thin || g->pooled || g->w_img_stride != 0 || g->si != 1 || cpad % 128 != 0 || out->c != cpad) return 0;
+  int dy_min = 1 << 30, dy_max = -(1 << 30);
+  for (int t = 0; t < g->ntaps; ++t) { dy_min = g->dy[t] < dy_min ? g->dy[t] : dy_min; dy_max = g->dy[t] > dy_max ? g->dy[t] : dy_max; }
+  if (dy_max - dy_min > 4) return 0;
+  HxGeom hg;
+  memset(&hg, 0, sizeof(hg));
+  hg.mi = g->mi; hg.mj = g->mj; hg.ntaps = g->ntaps; hg.flags = g->flags;
+  hg.nblk = 1; hg.cb = 128; hg.sy = 1; hg.soy = hg.sox = g->so;
+  hg.oy[0] = g->oy0; hg.ox[0] = g->ox0;
+  hg.dy = g->dy; hg.dx = g->dx; hg.stats = g->stats;
+  const int r = hx_launch(in, weights, bias, add, mask, out, hg, cpad, stream);
+  if (r != 1) return r;
   count_work(FAM_CONV_HX, conv_flops(in, out, g), conv_bytes(in, out, g, add, mask));
   AST_CUDA_LAUNCH_CHECK();
   return 1;
+}
+
+// Block-stacked launches whose filter does not fit in shared memory (conv_st.cu keeps it resident): the same kernel with
+// the 128 lanes split into g->nblk output blocks and the filter streamed.  1 = launched, 0 = not applicable.
+int conv_stacked_hx(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                    const ast_image* mask, const ast_image* out, const ast_stacked_geom* g, cudaStream_t stream) {
+  HxGeom hg;
+  memset(&hg, 0, sizeof(hg));
+  hg.mi = g->mi; hg.mj = g->mj; hg.ntaps = g->nvt; hg.flags = g->flags;
+  hg.nblk = g->nblk; hg.cb = 128 / g->nblk; hg.sy = g->sy; hg.soy = g->soy; hg.sox = g->sox;
+  for (int b = 0; b < g->nblk; ++b) { hg.oy[b] = g->oy[b]; hg.ox[b] = g->ox[b]; }
+  hg.dy = g->dy; hg.dx = g->dx; hg.stats = g->stats;
+  return hx_launch(in, weights, bias, add, mask, out, hg, 128, stream);
 }
 
 }  // namespace ast

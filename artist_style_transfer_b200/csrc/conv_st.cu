@@ -215,6 +215,11 @@ conv_st_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
 using namespace ast;
 
+namespace ast {
+int conv_stacked_hx(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
+                    const ast_image* mask, const ast_image* out, const ast_stacked_geom* g, cudaStream_t stream);   // conv_hx.cu
+}
+
 extern "C" int ast_conv_stacked(const ast_image* in, const void* weights, const float* bias, const ast_image* add,
                                 const ast_image* mask, const ast_image* out, const ast_stacked_geom* g, void* stream) {
   AST_CHECK_ARG(in && weights && out && g, "ast_conv_stacked: null argument");
@@ -261,7 +266,23 @@ extern "C" int ast_conv_stacked(const ast_image* in, const void* weights, const 
   for (int nb = 3; nb >= 2 && !rmax; --nb)
     for (int R = 32; R >= (nb == 3 ? 16 : 2); R -= 2)
       if (nb * patch_bytes(R) <= budget && (R - 1) * p.sy + (dy_max - dy_min) + 1 <= 256) { rmax = R; break; }
-  AST_CHECK_ARG(rmax > 0, "ast_conv_stacked: the stacked filter (%d bytes) does not fit in shared memory next to two patches", p.w_total_bytes);
+  const double taps = (double)g->ntaps;          // real filter taps over all blocks (zero rows of the stacked filter do not count)
+  const double pix = (double)in->n * g->mi * g->mj;
+  const double flops = 2.0 * pix * taps * in->c * cb;
+  double pix_in = (double)g->mi * g->sy * g->mj;
+  if (pix_in > (double)in->h * in->w) pix_in = (double)in->h * in->w;
+  const double bytes = in->n * pix_in * in->c * esize(in) +
+                       pix * g->nblk * cb * (esize(out) + (add ? esize(add) : 0) + (mask ? esize(mask) : 0));
+  if (rmax < 12) {         // the filter leaves no room for two useful patches: stream it (conv_hx.cu)
+    const int r = conv_stacked_hx(in, weights, bias, add, mask, out, g, (cudaStream_t)stream);
+    AST_CHECK_ARG(r != 0 || rmax > 0, "ast_conv_stacked: the stacked filter (%d bytes) neither fits in shared memory nor suits the streaming kernel", p.w_total_bytes);
+    if (r == 1) {
+      count_work(FAM_CONV_HX, flops, bytes);
+      AST_CUDA_LAUNCH_CHECK();
+      return 0;
+    }
+    if (r != 0) return r;
+  }
   p.tiles_i = (p.mi + rmax - 1) / rmax;
   p.R = (p.mi + p.tiles_i - 1) / p.tiles_i;
   p.R = (p.R + 1) & ~1;                              // N = 8R must be a multiple of 16
@@ -309,13 +330,6 @@ extern "C" int ast_conv_stacked(const ast_image* in, const void* weights, const 
   }
   if (e != cudaSuccess) { set_error("ast_conv_stacked: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
   count_launch();
-  const double taps = (double)g->ntaps;          // real filter taps over all blocks (zero rows of the stacked filter do not count)
-  const double pix = (double)in->n * g->mi * g->mj;
-  const double flops = 2.0 * pix * taps * in->c * cb;
-  double pix_in = (double)g->mi * g->sy * g->mj;
-  if (pix_in > (double)in->h * in->w) pix_in = (double)in->h * in->w;
-  const double bytes = in->n * pix_in * in->c * esize(in) +
-                       pix * g->nblk * cb * (esize(out) + (add ? esize(add) : 0) + (mask ? esize(mask) : 0));
   count_work(FAM_CONV_ST, flops, bytes);
   AST_CUDA_LAUNCH_CHECK();
   return 0;

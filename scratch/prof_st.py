@@ -83,3 +83,5 @@ vt3b = [cg.Launch(256, 258, 1, 1, 0, 0, [(1, 0), (0, 0), (-1, 0)], [(0, 0), (1, 
 run("VGG conv1_1 dgrad vt3 64->32 bf16", bf, bf, 64, 32, 256, 258, vt3b, 256, 258, "rows")
 run("T deconv1 3x3 s2 128->64 64^2->128^2 +stats", bf, bf, 128, 64, 64, 64, cg.convT_fwd(3, 2, 1, 1, 64, 64), 128, 128, "phases", stats=True)
 run("T conv3 dgrad 128->64 64^2->130^2", bf, bf, 128, 64, 64, 64, cg.conv_dgrad(3, 2, 0, 130, 130), 130, 130, "phases")
+run("VGG conv1_2 64->64 tf32 +relu+bias", f32, f32, 64, 64, 256, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, 256, "rows", relu=True, bias=True, round_tf32=True)
+run("VGG dgrad conv1_2 64->64 bf16 +mask", bf, bf, 64, 64, 256, 256, cg.conv_dgrad(3, 1, 1, 256, 256), 256, 256, "rows", mask=True)

@@ -281,6 +281,9 @@ STACKED_CASES = [
      lambda cg: [cg.Launch(21, 24, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]),
     ("rows 3 taps dx -1 64->32", torch.bfloat16, 64, 32, 1, (16, 30), (16, 32),
      lambda cg: [cg.Launch(16, 32, 1, 1, 0, 0, [(1, -1), (0, -1), (-1, -1)], [(0, 0), (1, 0), (2, 0)], 0)]),
+    # filters that do not fit in shared memory: the streaming kernel (conv_hx.cu) takes the stacked launch
+    ("rows 3x3 64->64 tf32 streamed", torch.float32, 64, 64, 2, (20, 24), (20, 24), lambda cg: cg.conv_fwd(3, 1, 1, 20, 24)),
+    ("rows 3x3 64->64 bf16 streamed", torch.bfloat16, 64, 64, 1, (37, 19), (37, 19), lambda cg: cg.conv_dgrad(3, 1, 1, 37, 19)),
     ("rows tall 9 taps 32->32", torch.bfloat16, 32, 32, 1, (272, 8), (264, 8),
      lambda cg: [cg.Launch(264, 8, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]),
 ]
@@ -313,9 +316,10 @@ def test_conv_stacked_matches_the_plain_launches(env, name, dtype, cin, cout, n,
         ws = ops.stack_filter(lambda pos: wp[tidx[pos]], stk, cout, cin, dtype, "cuda")
         ops.conv_stacked(x, ws, stk, got, stats=s_got, **kw)
     delta = _lib.family_delta(before)
-    assert delta["conv_st"][0] == (1 if len(launches) == 1 or cout == 32 else 2)
+    fam = "conv_hx" if "streamed" in name else "conv_st"
+    assert delta[fam][0] == (1 if len(launches) == 1 or cout == 32 else 2)
     flops = 2.0 * n * sum(l.mi * l.mj * len(l.taps) for l in launches) * cin * cout
-    assert abs(delta["conv_st"][1] - flops) <= 0.1 * flops      # interleaved rows round mi up to a multiple of nblk
+    assert abs(delta[fam][1] - flops) <= 0.1 * flops      # interleaved rows round mi up to a multiple of nblk
     torch.cuda.synchronize()
     assert not torch.isnan(got.float()).any()
     # same operands, fp32 accumulation: only the summation order differs (one bf16 rounding when the output is bf16)
