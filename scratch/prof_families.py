@@ -28,7 +28,27 @@ def conv(name, dtype, cin, cout, hin, launches, hout, stats=False, mask=False, p
 
 vt9 = [cg.Launch(256, 256, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]
 conv("conv_ws tf32 VGG conv1_2 64->64 256^2 +ReLU +fused MaxPool +window codes", f32, 64, 64, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, pooled=True, relu=True)
-conv("conv_ws bf16 T first layer (9 vertical taps over row-im2col) 32->32 256^2 +stats", bf, 32, 32, 264, vt9, 256, stats=True)
+conv("conv_ws bf16 VGG dgrad conv1_2 64->64 256^2 +mask", bf, 64, 64, 256, cg.conv_dgrad(3, 1, 1, 256, 256), 256, mask=True)
+
+def stacked(name, dtype, odt, cin, cout, hw_in, hw_out, launches, stats=False, relu=False):
+    from artist_style_transfer_b200 import arena as arena_mod
+    x = torch.randn(n, hw_in[0], hw_in[1], cin, device=dev).to(dtype)
+    y = torch.empty(n, hw_out[0], hw_out[1], cout, device=dev, dtype=odt)
+    nt = sum(len(l.taps) for l in launches)
+    wp = (torch.randn(nt, cout, cin, device=dev) / (cin * nt) ** 0.5).to(dtype)
+    tidx = {wt: l.woff + t for l in launches for t, wt in enumerate(l.wtaps)}
+    groups = arena_mod.stack_groups(launches, cout)
+    ws = [ops.stack_filter(lambda pos: wp[tidx[pos]], g, cout, cin, dtype, dev) for g in groups]
+    sums = torch.zeros(2 * n * cout, dtype=torch.float64, device=dev) if stats else None
+    def go():
+        for g, w in zip(groups, ws):
+            ops.conv_stacked(x, w, g, y, stats=sums, relu=relu, round_tf32=dtype == f32)
+    todo.append((name, go))
+
+stacked("conv_st bf16 T first layer (9 vertical taps over row-im2col, 4 interleaved rows) 32->32 256^2 +stats", bf, bf, 32, 32, (264, 256), (256, 256), vt9, stats=True)
+stacked("conv_st bf16 T ConvTranspose 3x3 s2 64->32 128^2->256^2 (4 phases stacked) +stats", bf, bf, 64, 32, (128, 128), (256, 256), cg.convT_fwd(3, 2, 1, 1, 128, 128), stats=True)
+stacked("conv_st tf32 VGG conv1_1 (3 vertical taps, 2 interleaved rows) 16->64 256^2 +ReLU", f32, f32, 16, 64, (256, 256), (256, 256),
+        [cg.Launch(256, 256, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)], relu=True)
 conv("conv_hx bf16 T residual 3x3 128->128 64^2 +stats", bf, 128, 128, 66, cg.conv_fwd(3, 1, 0, 66, 66), 64, stats=True)
 conv("conv_hx tf32 VGG conv2_2 128->128 128^2", f32, 128, 128, 128, cg.conv_fwd(3, 1, 1, 128, 128), 128, relu=True)
 conv("conv_hx tf32 VGG conv4_2 512->512 32^2", f32, 512, 512, 32, cg.conv_fwd(3, 1, 1, 32, 32), 32, relu=True)
