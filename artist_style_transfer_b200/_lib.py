@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AST_B200_LIB points at another build of the same library (kernel A/B experiments); default: the in-tree build
 LIB_PATH = os.environ.get("AST_B200_LIB") or os.path.join(_HERE, "libast_b200.so")
 
-AST_F32, AST_BF16, AST_TF32, AST_U8 = 0, 1, 2, 3
+AST_F32, AST_BF16, AST_TF32, AST_U8, AST_F16 = 0, 1, 2, 3, 4
 AST_MAX_TAPS = 81
 CONV_RELU, CONV_REFLECT, CONV_TENSOR = 1, 2, 4
 CONV_POOL_ONLY = 16
@@ -19,7 +19,7 @@ CONV_ROUND_TF32 = 8
 IN_SUMS_ZEROED = 2
 GRAM_COUNTERS_PER_IMAGE = 16
 
-_DTYPES = {torch.float32: AST_F32, torch.bfloat16: AST_BF16, torch.uint8: AST_U8}
+_DTYPES = {torch.float32: AST_F32, torch.bfloat16: AST_BF16, torch.uint8: AST_U8, torch.float16: AST_F16}
 
 
 class Image(ctypes.Structure):

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -101,14 +102,27 @@ template <> struct DT<__nv_bfloat16> {
 
 // AST_U8 (host-boundary images): loads widen exactly; stores follow numpy's `.clip(0, 255).astype('uint8')`
 // (inference.py:116, train_cnn.py:112): clamp, then truncate toward zero.
+// AST_F16 stores saturate (an fp32 value beyond +-65504 must not become inf)
+__device__ __forceinline__ __half f2h_sat(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// two values as one 32-bit word of 16-bit elements, a in the low half.  F16 is a COMPILE-TIME choice: callers test the
+// element type once per chunk, never per element (a per-element test doubles the conversion instructions of the epilogue)
+template <bool F16>
+__device__ __forceinline__ unsigned pack2(float a, float b) {
+  if (F16) { const __half2 h = __halves2half2(f2h_sat(a), f2h_sat(b)); return *reinterpret_cast<const unsigned*>(&h); }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&h);
+}
+__device__ __forceinline__ unsigned pack2_16(int dtype, float a, float b) { return dtype == AST_F16 ? pack2<true>(a, b) : pack2<false>(a, b); }
 __device__ __forceinline__ float ld_elem(const Img& im, long long off) {
   if (im.dtype == AST_F32) return ((const float*)im.ptr)[off];
   if (im.dtype == AST_U8) return (float)((const unsigned char*)im.ptr)[off];
+  if (im.dtype == AST_F16) return __half2float(((const __half*)im.ptr)[off]);
   return __bfloat162float(((const __nv_bfloat16*)im.ptr)[off]);
 }
 __device__ __forceinline__ void st_elem(const Img& im, long long off, float v) {
   if (im.dtype == AST_F32) ((float*)im.ptr)[off] = v;
   else if (im.dtype == AST_U8) ((unsigned char*)im.ptr)[off] = (unsigned char)__float2uint_rz(fminf(fmaxf(v, 0.f), 255.f));
+  else if (im.dtype == AST_F16) ((__half*)im.ptr)[off] = f2h_sat(v);
   else ((__nv_bfloat16*)im.ptr)[off] = __float2bfloat16_rn(v);
 }
 __device__ __forceinline__ long long img_off(const Img& im, int n, int y, int x, int c) {
@@ -177,12 +191,21 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, const float* v) {
   h[1] = __floats2bfloat162_rn(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = u;
 }
+__device__ __forceinline__ void ld4(const __half* p, float* v) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+  v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+}
 __device__ __forceinline__ void ld4_img(const Img& im, long long off, float* v) {
   if (im.dtype == AST_F32) ld4((const float*)im.ptr + off, v);
+  else if (im.dtype == AST_F16) ld4((const __half*)im.ptr + off, v);
   else ld4((const __nv_bfloat16*)im.ptr + off, v);
 }
 __device__ __forceinline__ void st4_img(const Img& im, long long off, const float* v) {
   if (im.dtype == AST_F32) st4((float*)im.ptr + off, v);
+  else if (im.dtype == AST_F16)
+    *reinterpret_cast<uint2*>((__half*)im.ptr + off) = make_uint2(pack2_16(AST_F16, v[0], v[1]), pack2_16(AST_F16, v[2], v[3]));
   else st4((__nv_bfloat16*)im.ptr + off, v);
 }
 

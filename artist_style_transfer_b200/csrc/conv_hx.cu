@@ -296,11 +296,11 @@ static int hx_launch(const ast_image* in, const void* weights, const float* bias
   if (p.n_wbuf < 2) return 0;
   if (p.n_wbuf > HX_MAX_WBUF) p.n_wbuf = HX_MAX_WBUF;
   if (budget - p.n_pbuf * p.patch_bytes - p.n_wbuf * w_slot >= p.patch_bytes) p.n_pbuf = 3;
-  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
+  const unsigned fmt = tc_operand_fmt(in->dtype);
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)((8 * p.R) >> 3) << 17) | ((128u >> 4) << 24);
 
   alignas(64) CUtensorMap tm_in, tm_w;
-  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = tc_tmap_dtype(in->dtype);
   {
     cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
     cuuint64_t strides[3] = {(cuuint64_t)in->sw * esz, (cuuint64_t)in->sh * esz, (cuuint64_t)in->sn * esz};
@@ -320,7 +320,7 @@ static int hx_launch(const ast_image* in, const void* weights, const float* bias
   const size_t smem = 1024 + (size_t)p.n_pbuf * p.patch_bytes + (size_t)p.n_wbuf * w_slot;
   const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   cudaError_t e;
-  if (in->dtype == AST_BF16) {
+  if (in->dtype != AST_F32) {          // kind::f16 (bf16 or fp16 operands, the format is in the instruction descriptor)
     e = set_max_smem(conv_hx_kernel<0>, smem);
     if (e == cudaSuccess) launch_k(conv_hx_kernel<0>, grid, HX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g.stats);
   } else {

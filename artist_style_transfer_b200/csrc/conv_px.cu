@@ -209,6 +209,7 @@ int conv_gather_px(const ast_image* in, const void* weights, const float* bias, 
                    cudaStream_t stream) {
   if (thin || g->pooled || (cpad != 64 && cpad != 128) || out->c != cpad) return 0;
   if (!img32_ok(out) || !img32_ok(add) || !img32_ok(mask)) return 0;
+  if (in->dtype == AST_F16) return 0;
   const int esz = in->dtype == AST_F32 ? 4 : 2;
   EncodeTiledFn encode = get_encode();
   if (!encode) return 0;
@@ -237,13 +238,13 @@ int conv_gather_px(const ast_image* in, const void* weights, const float* bias, 
   if (p.stages > PX_MAX_STAGES) p.stages = PX_MAX_STAGES;
   p.layout_type = p.rowb == 128 ? 2u : 4u;
   p.sbo = 8u * p.rowb;
-  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
+  const unsigned fmt = tc_operand_fmt(in->dtype);
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
   p.pairs_per_img = (p.tiles_i * p.tiles_j + 1) / 2;
   p.total_pairs = (long long)p.n_img * p.pairs_per_img;
 
   alignas(64) CUtensorMap tm_in, tm_w;
-  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = tc_tmap_dtype(in->dtype);
   const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
@@ -263,7 +264,7 @@ int conv_gather_px(const ast_image* in, const void* weights, const float* bias, 
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const int grid = (int)(p.total_pairs < num_sms() ? p.total_pairs : num_sms());
   cudaError_t e;
-  if (in->dtype == AST_BF16) {
+  if (in->dtype != AST_F32) {          // kind::f16 (bf16 or fp16 operands, the format is in the instruction descriptor)
     e = set_max_smem(conv_px_kernel<0>, smem);
     if (e == cudaSuccess) launch_k(conv_px_kernel<0>, grid, PX_THREADS, smem, stream, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
   } else {

@@ -227,8 +227,8 @@ extern "C" int ast_conv_stacked(const ast_image* in, const void* weights, const 
   AST_CHECK_ARG(g->nvt >= 1 && g->nvt <= AST_MAX_VTAPS, "ast_conv_stacked: nvt %d out of range", g->nvt);
   AST_CHECK_ARG(in->n == out->n, "ast_conv_stacked: batch mismatch %d vs %d", in->n, out->n);
   AST_CHECK_ARG(g->mi > 0 && g->mj > 0 && g->sy >= 1 && g->soy >= 1 && g->sox >= 1, "ast_conv_stacked: bad geometry");
-  AST_CHECK_ARG(in->dtype == AST_F32 || in->dtype == AST_BF16, "ast_conv_stacked: bad input dtype");
-  AST_CHECK_ARG(out->dtype == AST_F32 || out->dtype == AST_BF16, "ast_conv_stacked: bad output dtype");
+  AST_CHECK_ARG(in->dtype == AST_F32 || in->dtype == AST_BF16 || in->dtype == AST_F16, "ast_conv_stacked: bad input dtype");
+  AST_CHECK_ARG(out->dtype == AST_F32 || out->dtype == AST_BF16 || out->dtype == AST_F16, "ast_conv_stacked: bad output dtype");
   AST_CHECK_ARG(!add || same_shape(add, out), "ast_conv_stacked: add image shape mismatch");
   AST_CHECK_ARG(!mask || same_shape(mask, out), "ast_conv_stacked: mask image shape mismatch");
   const int cb = 128 / g->nblk;
@@ -295,12 +295,12 @@ extern "C" int ast_conv_stacked(const ast_image* in, const void* weights, const 
   p.n_pbuf = budget / p.patch_bytes;
   if (p.n_pbuf > ST_MAX_PBUF) p.n_pbuf = ST_MAX_PBUF;
   p.layout_type = p.rowb == 128 ? 2u : 4u;
-  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
+  const unsigned fmt = tc_operand_fmt(in->dtype);
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)((8 * p.R) >> 3) << 17) | ((128u >> 4) << 24);
 
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "ast_conv_stacked: cuTensorMapEncodeTiled entry point not available");
-  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = tc_tmap_dtype(in->dtype);
   const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap tm_in, tm_w;
   {
@@ -321,7 +321,7 @@ extern "C" int ast_conv_stacked(const ast_image* in, const void* weights, const 
   const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e;
-  if (in->dtype == AST_BF16) {
+  if (in->dtype != AST_F32) {          // kind::f16 (bf16 or fp16 operands, the format is in the instruction descriptor)
     e = set_max_smem(conv_st_kernel<0>, smem);
     if (e == cudaSuccess) launch_k(conv_st_kernel<0>, grid, ST_THREADS, smem, s, tm_in, tm_w, p, bias, to_img32(add), to_img32(mask), to_img32(out), g->stats);
   } else {

@@ -227,6 +227,9 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   AST_CHECK_ARG(thin || (out->sw % 4 == 0 && out->sh % 4 == 0 && out->sn % 4 == 0), "conv_tc: output strides must be multiples of 4 elements");
   AST_CHECK_ARG(thin || !add || (add->sc == 1 && add->sw % 4 == 0 && add->sh % 4 == 0 && add->sn % 4 == 0), "conv_tc: add layout");
   AST_CHECK_ARG(thin || !mask || (mask->sc == 1 && mask->sw % 4 == 0 && mask->sh % 4 == 0 && mask->sn % 4 == 0), "conv_tc: mask layout");
+  // 16-bit add / mask operands are read with 16-byte loads
+  AST_CHECK_ARG(thin || !mask || mask->dtype == AST_F32 || (mask->sw % 8 == 0 && mask->sh % 8 == 0 && mask->sn % 8 == 0 && ((uintptr_t)mask->ptr & 15) == 0), "conv_tc: 16-bit mask strides must be multiples of 8 elements");
+  AST_CHECK_ARG(thin || !add || add->dtype == AST_F32 || (add->sw % 8 == 0 && add->sh % 8 == 0 && add->sn % 8 == 0 && ((uintptr_t)add->ptr & 15) == 0), "conv_tc: 16-bit add strides must be multiples of 8 elements");
   if (in->n == 0) return 0;
   EncodeTiledFn encode = get_encode();
   AST_CHECK_ARG(encode, "conv_tc: cuTensorMapEncodeTiled entry point not available");
@@ -237,6 +240,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   AST_CHECK_ARG(!g->pooled, "conv_tc: a pooled output needs the weight-stationary kernel (stride 1, filter resident in smem)");
   if (int hr = conv_gather_hx(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return hr == 1 ? 0 : hr;
   if (int pr = conv_gather_px(in, weights, bias, add, mask, out, g, cpad, thin, stream)) return pr == 1 ? 0 : pr;
+  AST_CHECK_ARG(in->dtype != AST_F16, "conv_tc: fp16 operands are supported by the weight-stationary and halo kernels only (stride 1)");
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -263,13 +267,13 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.layout_type = p.rowb == 128 ? 2u : 4u;       // SWIZZLE_128B / SWIZZLE_64B
   p.sbo = 8u * p.rowb;
-  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;   // TF32 / BF16
+  const unsigned fmt = tc_operand_fmt(in->dtype);
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
   p.total_tiles = (long long)p.n_img * p.tiles_i * p.tiles_j * p.n_tiles_n;
 
   // ---- tensor maps
   alignas(64) CUtensorMap tm_in, tm_w;
-  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = tc_tmap_dtype(in->dtype);
   const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     cuuint64_t dims[4] = {(cuuint64_t)in->c, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
@@ -290,7 +294,7 @@ int conv_gather_tc(const ast_image* in, const void* weights, const float* bias, 
   const int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();
   cudaError_t e;
-  if (in->dtype == AST_BF16) {
+  if (in->dtype != AST_F32) {          // kind::f16 (bf16 or fp16 operands, the format is in the instruction descriptor)
     e = set_max_smem(conv_tc_kernel<0>, smem);
     if (e == cudaSuccess) launch_k(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats);
   } else {

@@ -282,6 +282,9 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   }
   if (dx_max - dx_min > 8 || dy_max - dy_min > 15) return 0;
   if (cpad > 256) return 0;
+  // multi-tap layers with >= 128 output channels belong to the halo pixels-as-N kernel (conv_hx.cu) even when their 16-bit
+  // filter would fit here (VGG conv2_1 with fp16 operands: 146 vs 122 us)
+  if (cpad % 128 == 0 && g->ntaps >= 8 && !thin && !g->pooled && (in->c * esz) % 128 == 0) return 0;
   WsParams p;
   memset(&p, 0, sizeof(p));
   p.rowb = (in->c * esz) % 128 == 0 ? 128 : 64;
@@ -325,10 +328,10 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   p.sbo = (unsigned)(p.pw * p.rowb);
   // Measured on B200: the tensor core applies the 128B/64B swizzle XOR on ABSOLUTE shared-memory address bits, so a
   // start address shifted by whole pixels needs base_offset = 0 (setting it to (addr>>7)&7 gives wrong results).
-  const unsigned fmt = in->dtype == AST_F32 ? 2u : 1u;
+  const unsigned fmt = tc_operand_fmt(in->dtype);
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
 
-  const CUtensorMapDataType dt = in->dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = tc_tmap_dtype(in->dtype);
   const CUtensorMapSwizzle sw = p.rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap tm_in, tm_w;
   {
@@ -365,7 +368,7 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
 #define WS_LAUNCH(K, B)                                                                                          \
   e = set_max_smem(conv_ws_kernel<K, B>, smem);                                                                   \
   if (e == cudaSuccess) launch_k(conv_ws_kernel<K, B>, grid, WS_THREADS, smem, stream, tm_in, tm_w, p, bias, addi, maski, to_img(out), g->stats, pooli, codei)
-  if (in->dtype == AST_BF16) {
+  if (in->dtype != AST_F32) {          // kind::f16 (bf16 or fp16 operands, the format is in the instruction descriptor)
     if (two) { WS_LAUNCH(0, 2); } else { WS_LAUNCH(0, 1); }
   } else {
     if (two) { WS_LAUNCH(1, 2); } else { WS_LAUNCH(1, 1); }

@@ -307,7 +307,8 @@ extern "C" int ast_conv_gather(const ast_image* in, const void* weights, const f
   AST_CHECK_ARG(geom->mi > 0 && geom->mj > 0 && geom->si >= 1 && geom->so >= 1, "ast_conv_gather: bad geometry");
   AST_CHECK_ARG(!add || same_shape(add, out), "ast_conv_gather: add image shape mismatch");
   AST_CHECK_ARG(!mask || same_shape(mask, out), "ast_conv_gather: mask image shape mismatch");
-  AST_CHECK_ARG(in->dtype == AST_F32 || in->dtype == AST_BF16, "ast_conv_gather: bad input dtype");
+  AST_CHECK_ARG(in->dtype == AST_F32 || in->dtype == AST_BF16 || (in->dtype == AST_F16 && (geom->flags & AST_CONV_TENSOR)),
+                "ast_conv_gather: bad input dtype (fp16 operands are a tensor-core feature)");
   AST_CHECK_ARG(!geom->stats || (geom->flags & AST_CONV_TENSOR), "ast_conv_gather: fused statistics are a tensor-core epilogue feature");
   AST_CHECK_ARG(!geom->pooled || (geom->flags & AST_CONV_TENSOR), "ast_conv_gather: the pooled output is a tensor-core epilogue feature");
   if (geom->flags & AST_CONV_TENSOR)

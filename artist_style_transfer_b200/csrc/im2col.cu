@@ -100,7 +100,10 @@ row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw_
       for (int e = 0; e < OUTC; e += 4) st4((float*)out.ptr + oo + e, v + e);
     } else {
 #pragma unroll
-      for (int e = 0; e < OUTC; e += 8) Vec16<__nv_bfloat16>::store((__nv_bfloat16*)out.ptr + oo + e, v + e);
+      for (int e = 0; e < OUTC; e += 8)     // bf16 or fp16 elements
+        *reinterpret_cast<uint4*>((unsigned short*)out.ptr + oo + e) =
+            make_uint4(pack2_16(out.dtype, v[e], v[e + 1]), pack2_16(out.dtype, v[e + 2], v[e + 3]),
+                       pack2_16(out.dtype, v[e + 4], v[e + 5]), pack2_16(out.dtype, v[e + 6], v[e + 7]));
     }
   }
 }
@@ -198,6 +201,7 @@ extern "C" int ast_row_im2col(const ast_image* src, const ast_image* out, const 
 #define RIK(O, K, C) launch_k(row_im2col_pix_kernel<O, K, C>, (int)pb, 256, 0, (cudaStream_t)stream, to_img(src), to_img(out), shift, kw, sign, px, py, reflect, round_tf32)
     if (out->c == 32 && kw == 9 && src->c == 3) RIK(32, 9, 3);
     else if (out->c == 16 && kw == 3 && src->c == 3) RIK(16, 3, 3);
+    else if (out->c == 32 && kw == 3 && src->c == 3) RIK(32, 3, 3);
     else if (out->c == 32) RIK(32, 0, 0);
     else RIK(16, 0, 0);
 #undef RIK

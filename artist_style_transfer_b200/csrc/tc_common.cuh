@@ -106,6 +106,38 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 
 
+// eight 4-channel vectors of one pixel, BODY applied to each (t[0..3] = channels e..e+3); element type tested once
+#define LD4_EACH_T(im, off, T, BODY)                                                          \
+  { _Pragma("unroll") for (int e = 0; e < 32; e += 4) { float t[4]; ld4((const T*)im.ptr + (off) + e, t); BODY } }
+#define LD4_EACH(im, off, BODY)                                                               \
+  if (im.dtype == AST_F32) LD4_EACH_T(im, off, float, BODY)                                   \
+  else if (im.dtype == AST_F16) LD4_EACH_T(im, off, __half, BODY)                             \
+  else LD4_EACH_T(im, off, __nv_bfloat16, BODY)
+// 32 consecutive channels of one pixel as floats.  The element type is tested ONCE (not per vector): with a per-load type
+// dispatch of three types the compiler no longer batches the loads.
+__device__ __forceinline__ void ld32_img(const Img& im, long long off, float* t) {
+  if (im.dtype == AST_F32) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) ld4((const float*)im.ptr + off + e, t + e);
+  } else if (im.dtype == AST_F16) {       // 16-bit types: four 16-byte loads (offsets are multiples of 8 elements here)
+#pragma unroll
+    for (int e = 0; e < 32; e += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>((const __half*)im.ptr + off + e);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); t[e + 2 * k] = f.x; t[e + 2 * k + 1] = f.y; }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; e += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)im.ptr + off + e);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); t[e + 2 * k] = f.x; t[e + 2 * k + 1] = f.y; }
+    }
+  }
+}
+
 // Fused epilogue for 32 consecutive output channels of one pixel held in registers (conv_ws.cu):
 // bias -> tap-gradient add -> ReLU -> ReLU mask -> TF32 rounding -> 16-byte stores (or scalar "thin" stores).
 __device__ __forceinline__ void tc_epilogue32(float* v, int co, int img, int oy, int ox, bool thin, int cout,
@@ -133,8 +165,7 @@ __device__ __forceinline__ void tc_epilogue32(float* v, int co, int img, int oy,
   }
   if (add.ptr) {
     const long long o = img_off(add, img, oy, ox, co);
-#pragma unroll
-    for (int e = 0; e < 32; e += 4) { float t[4]; ld4_img(add, o + e, t); v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3]; }
+    LD4_EACH(add, o, v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3];)
   }
   if (flags & AST_CONV_RELU) {
 #pragma unroll
@@ -142,12 +173,7 @@ __device__ __forceinline__ void tc_epilogue32(float* v, int co, int img, int oy,
   }
   if (mask.ptr) {
     const long long o = img_off(mask, img, oy, ox, co);
-#pragma unroll
-    for (int e = 0; e < 32; e += 4) {
-      float t[4]; ld4_img(mask, o + e, t);
-      v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f;
-      v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;
-    }
+    LD4_EACH(mask, o, v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f; v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;)
   }
   if (flags & AST_CONV_ROUND_TF32) {
 #pragma unroll
@@ -159,14 +185,17 @@ __device__ __forceinline__ void tc_epilogue32(float* v, int co, int img, int oy,
 #pragma unroll
     for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
   } else {
-    __nv_bfloat16* op = (__nv_bfloat16*)out.ptr + oo;
+    unsigned short* op = (unsigned short*)out.ptr + oo;      // bf16 or fp16 elements
+    if (out.dtype == AST_F16) {
 #pragma unroll
-    for (int e = 0; e < 32; e += 8) {
-      uint4 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-      h[0] = __floats2bfloat162_rn(v[e], v[e + 1]); h[1] = __floats2bfloat162_rn(v[e + 2], v[e + 3]);
-      h[2] = __floats2bfloat162_rn(v[e + 4], v[e + 5]); h[3] = __floats2bfloat162_rn(v[e + 6], v[e + 7]);
-      *reinterpret_cast<uint4*>(op + e) = u;
+      for (int e = 0; e < 32; e += 8)
+        *reinterpret_cast<uint4*>(op + e) = make_uint4(pack2<true>(v[e], v[e + 1]), pack2<true>(v[e + 2], v[e + 3]),
+                                                       pack2<true>(v[e + 4], v[e + 5]), pack2<true>(v[e + 6], v[e + 7]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; e += 8)
+        *reinterpret_cast<uint4*>(op + e) = make_uint4(pack2<false>(v[e], v[e + 1]), pack2<false>(v[e + 2], v[e + 3]),
+                                                       pack2<false>(v[e + 4], v[e + 5]), pack2<false>(v[e + 6], v[e + 7]));
     }
   }
 }
@@ -252,8 +281,7 @@ __device__ __forceinline__ void tc_epi_row_offsets(long long my_off, int lane, b
 __device__ __forceinline__ void tc_epi_prefetch_mask(const Img& mask, int img, int oy, int ox, int co, bool valid, float* m) {
   if (!mask.ptr || !valid) return;
   const long long o = img_off(mask, img, oy, ox, co);
-#pragma unroll
-  for (int e = 0; e < 32; e += 4) ld4_img(mask, o + e, m + e);
+  ld32_img(mask, o, m);
 }
 
 __device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int img, int oy, int ox, bool valid, int cout,
@@ -271,8 +299,7 @@ __device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int im
     }
     if (add.ptr) {
       const long long o = img_off(add, img, oy, ox, co);
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) { float t[4]; ld4_img(add, o + e, t); v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3]; }
+      LD4_EACH(add, o, v[e] += t[0]; v[e + 1] += t[1]; v[e + 2] += t[2]; v[e + 3] += t[3];)
     }
     if (flags & AST_CONV_RELU) {
 #pragma unroll
@@ -283,12 +310,7 @@ __device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int im
       for (int e = 0; e < 32; ++e) v[e] = pre_mask[e] > 0.f ? v[e] : 0.f;
     } else if (mask.ptr) {
       const long long o = img_off(mask, img, oy, ox, co);
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        float t[4]; ld4_img(mask, o + e, t);
-        v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f;
-        v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;
-      }
+      LD4_EACH(mask, o, v[e] = t[0] > 0.f ? v[e] : 0.f; v[e + 1] = t[1] > 0.f ? v[e + 1] : 0.f; v[e + 2] = t[2] > 0.f ? v[e + 2] : 0.f; v[e + 3] = t[3] > 0.f ? v[e + 3] : 0.f;)
     }
     if (flags & AST_CONV_ROUND_TF32) {
 #pragma unroll
@@ -318,18 +340,21 @@ __device__ __forceinline__ void tc_epilogue32_coalesced(float* v, int co, int im
       __syncwarp();
     }
   } else {                                                  // stage: [8 rows][4 chunks of 16 B]
-    __nv_bfloat16* base = (__nv_bfloat16*)out.ptr + co + 8 * (lane & 3);
+    unsigned short* base = (unsigned short*)out.ptr + co + 8 * (lane & 3);      // bf16 or fp16 elements
+    unsigned w[16];                                          // this lane's 32 channels as 16-bit pairs; type tested once
+    if (out.dtype == AST_F16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack2<true>(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack2<false>(v[2 * i], v[2 * i + 1]);
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       if ((lane >> 3) == p) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-          h[0] = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]); h[1] = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
-          h[2] = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]); h[3] = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
-          sts128(st + 16u * (r8 * 4 + (c ^ (r8 & 3))), u);
-        }
+        for (int c = 0; c < 4; ++c)
+          sts128(st + 16u * (r8 * 4 + (c ^ (r8 & 3))), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
       }
       __syncwarp();
       {
@@ -370,6 +395,12 @@ cudaError_t set_max_smem_impl(const void* kernel, size_t smem);
 template <typename K> inline cudaError_t set_max_smem(K kernel, size_t smem) { return set_max_smem_impl((const void*)kernel, smem); }
 
 // power-of-two (w x h = area) pixel box that wastes the fewest positions of an mi x mj grid
+// operand dtype -> TMA element type / tcgen05 operand format (kind::tf32 for fp32 storage, kind::f16 with bf16 or fp16)
+inline CUtensorMapDataType tc_tmap_dtype(int dtype) {
+  return dtype == AST_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == AST_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+inline unsigned tc_operand_fmt(int dtype) { return dtype == AST_F32 ? 2u : (dtype == AST_F16 ? 0u : 1u); }
+
 inline void pick_tile(int mi, int mj, int area, int* tw, int* th) {
   double best = -1;
   for (int w = area; w >= 1; w >>= 1) {

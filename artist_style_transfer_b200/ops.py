@@ -286,9 +286,9 @@ def _instnorm_bwd_impl(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, 
     return s12
 
 
-def _maxpool2_fwd_impl(x, codes=None):
+def _maxpool2_fwd_impl(x, codes=None, out_dtype=None):
     n, h, w, c = x.shape
-    y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+    y = torch.empty((n, h // 2, w // 2, c), dtype=out_dtype or x.dtype, device=x.device)
     xi, yi, ci = image(x), image(y), image(codes)
     check(_lib.load().ast_maxpool2_fwd(ref(xi), ref(yi), ref(ci), stream_ptr()), "ast_maxpool2_fwd")
     return y
@@ -382,10 +382,11 @@ def instnorm_bwd(x, mean, rstd, gamma, beta, gpad, pad, gextra, relu, dx, gtotal
                                   zeroed=zeroed, arrive=arrive)
 
 
-def maxpool2_fwd(x, codes=None):
-    """MaxPool2d(2,2); codes: optional uint8 (N,H/2,W/2,C) output with the window codes the backward can use instead of x."""
+def maxpool2_fwd(x, codes=None, out_dtype=None):
+    """MaxPool2d(2,2); codes: optional uint8 (N,H/2,W/2,C) output with the window codes the backward can use instead of x.
+    out_dtype: e.g. torch.float16 for a pooled tensor that only feeds the next fast-mode VGG convolution."""
     with _timed(_pw("maxpool_fwd", x)):
-        return _maxpool2_fwd_impl(x, codes=codes)
+        return _maxpool2_fwd_impl(x, codes=codes, out_dtype=out_dtype)
 
 
 def maxpool2_bwd(x, gy, gadd=None, codes=None):

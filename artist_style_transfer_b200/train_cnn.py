@@ -60,18 +60,25 @@ def _vgg_forward(x, module, upto, shift, only_last, need_grad):
     taps, plan = [], []
     pooled_next, codes_next = None, None
     packed = module._packed(tensor)
+    # fast mode: every activation that only feeds the next convolution (and the ReLU masks of the backward) is stored as
+    # fp16 - the 10 mantissa bits a kind::tf32 MMA keeps of an fp32 operand, at half the bytes and twice the MMA rate
+    # (kind::f16, fp32 accumulate); the four tap activations stay fp32 (TF32-rounded) for the Gram / MSE kernels
+    act16 = torch.float16 if tensor else torch.float32
+    packed16 = module._packed_half() if tensor else None
     for idx, kind, cin, cout in module._layout:
         if idx > upto:
             break
+        is_tap = (idx + 1) in _TAPS
+        odt = torch.float32 if (is_tap or not tensor) else act16
         if kind == "conv" and idx == 0 and tensor:
             # conv1_1 on the tensor cores: fold the 3 horizontal taps (and the mean shift, applied before the
-            # zero padding like train_cnn.py:300-301) into a 16-channel TF32 tensor, then a 3-tap vertical conv
-            xr = torch.empty((n, h, w, 16), dtype=torch.float32, device=dev)
-            ops.row_im2col(cur, xr, 3, 1, 1, 0, False, shift=shift, round_tf32=True)
+            # zero padding like train_cnn.py:300-301) into a 32-channel fp16 tensor (9 used), then a 3-tap vertical conv
+            xr = torch.empty((n, h, w, 32), dtype=act16, device=dev)
+            ops.row_im2col(cur, xr, 3, 1, 1, 0, False, shift=shift)
             launches = [cg.Launch(h, w, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)]
-            out = torch.empty((n, h, w, cout), dtype=torch.float32, device=dev)
+            out = torch.empty((n, h, w, cout), dtype=odt, device=dev)
             wst, stk, bias = module._packed_conv11_stacked(launches[0])
-            ops.conv_stacked(xr, wst, stk, out, bias=bias, relu=True, round_tf32=True)
+            ops.conv_stacked(xr, wst, stk, out, bias=bias, relu=True)
             plan.append((idx, "conv", cur, out, None))
             cur = out
         elif kind == "conv":
@@ -80,27 +87,32 @@ def _vgg_forward(x, module, upto, shift, only_last, need_grad):
                 ops.copy_image(cur, f32)
                 cur = f32
             launches = cg.conv_fwd(3, 1, 1, cur.shape[1], cur.shape[2])
-            out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=torch.float32, device=dev)
+            out = torch.empty((n, cur.shape[1], cur.shape[2], cout), dtype=odt, device=dev)
             wp, bias = packed[idx]
             use_tc = tensor and ops.tc_eligible(cur, cout)
+            if tensor:
+                if not use_tc:
+                    raise RuntimeError(f"VGG16 fast mode: conv {idx} ({cin}->{cout}) is not eligible for the tensor-core kernels")
+                wp = packed16[idx]
+            rnd = tensor and odt == torch.float32        # fp32 tap outputs are rounded to TF32 for the Gram / MSE kernels
             # conv1_2 -> ReLU -> MaxPool2d: the weight-stationary kernel also writes the pooled tensor (saves the pool
-            # kernel's 537 MB read at B=32) and, when a backward will follow, the 1-byte window codes it needs instead
+            # kernel's read of relu1_2 at B=32) and, when a backward will follow, the 1-byte window codes it needs instead
             # of the activations; when nothing needs the full-resolution relu1_2 (no-grad content branch asking only
             # for its last tap) it is not even stored
             fuse_pool = (use_tc and cin == 64 and cout == 64 and idx + 2 <= upto
                          and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0)
             if fuse_pool:
                 hp, wp_ = cur.shape[1] // 2, cur.shape[2] // 2
-                pooled_next = torch.empty((n, hp, wp_, cout), dtype=torch.float32, device=dev)
+                pooled_next = torch.empty((n, hp, wp_, cout), dtype=act16, device=dev)
                 codes_next = torch.empty((n, hp, wp_, cout), dtype=torch.uint8, device=dev) if need_grad else None
                 skip_full = only_last and not need_grad
-                ops.conv_gather(cur, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=True,
+                ops.conv_gather(cur, wp, launches, out, bias=bias, relu=True, tensor=True, round_tf32=rnd,
                                 pooled=pooled_next, pool_only=skip_full, pool_codes=codes_next)
                 if skip_full:
                     out = None
             else:
                 ops.conv_gather(cur, wp, launches, out, bias=bias, in_shift=shift if idx == 0 else None, relu=True,
-                                tensor=use_tc, round_tf32=tensor)
+                                tensor=use_tc, round_tf32=rnd)
             plan.append((idx, "conv", cur, out, None))
             cur = out
         elif kind == "pool":
@@ -110,7 +122,7 @@ def _vgg_forward(x, module, upto, shift, only_last, need_grad):
             else:
                 if need_grad and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0 and cur.shape[3] % 8 == 0:
                     codes = torch.empty((n, cur.shape[1] // 2, cur.shape[2] // 2, cur.shape[3]), dtype=torch.uint8, device=dev)
-                out = ops.maxpool2_fwd(cur, codes=codes)
+                out = ops.maxpool2_fwd(cur, codes=codes, out_dtype=act16 if tensor else None)
             plan.append((idx, "pool", cur, out, codes))
             cur = out
         if idx in _TAPS and cur is not None:
@@ -295,6 +307,14 @@ class VGG16(nn.Module, _cnn._Precision):
             self._pack_cache["c11v_key"], self._pack_cache["c11v"] = key, pk.to(dtype).contiguous()
         return self._pack_cache["c11v"]
 
+    def _packed_half(self):
+        """fp16 copies of the forward packs (TF32-rounded values are exactly representable in fp16 inside its range)."""
+        key = self._cache_key("fwd16", True)
+        if self._pack_cache.get("fwd16_key") != key:
+            self._pack_cache["fwd16_key"] = key
+            self._pack_cache["fwd16"] = {i: wp.half() for i, (wp, _) in self._packed(True).items() if i != 0}
+        return self._pack_cache["fwd16"]
+
     def _packed_conv11_stacked(self, launch):
         """conv1_1's 3-vertical-tap filter stacked for ast_conv_stacked: two interleaved output rows x 64 channels fill the
         128 TMEM lanes (4 virtual taps instead of 2 x 3 N=64 MMAs per pixel pair)."""
@@ -302,8 +322,10 @@ class VGG16(nn.Module, _cnn._Precision):
         key = self._cache_key("c11s", True)
         if self._pack_cache.get("c11s_key") != key:
             wp, bias = self._packed(True)[0]                                    # [dy][64][16], TF32-rounded
+            wp32 = torch.zeros((wp.shape[0], 64, 32), dtype=torch.float16, device=wp.device)   # fp16, K padded to 64 bytes
+            wp32[:, :, :16] = wp.half()
             self._pack_cache["c11s_key"] = key
-            self._pack_cache["c11s"] = (ops.stack_filter(lambda pos: wp[pos[0]], stk, 64, 16, torch.float32, wp.device), bias)
+            self._pack_cache["c11s"] = (ops.stack_filter(lambda pos: wp32[pos[0]], stk, 64, 32, torch.float16, wp.device), bias)
         wst, bias = self._pack_cache["c11s"]
         return wst, stk, bias
 

@@ -30,7 +30,11 @@ extern "C" {
 typedef enum {
   AST_F32 = 0, AST_BF16 = 1,
   AST_TF32 = 2, /* fp32 storage rounded to TF32; weight packing only */
-  AST_U8 = 3    /* uint8 images at the host boundary (dataset.py:97-108 / inference.py:110,116): ast_row_im2col input, ast_fold_rows output */
+  AST_U8 = 3,   /* uint8 images at the host boundary (dataset.py:97-108 / inference.py:110,116): ast_row_im2col input, ast_fold_rows output */
+  AST_F16 = 4   /* IEEE half: the frozen VGG's non-tap activations and pooled tensors in fast mode.  10 mantissa bits = exactly
+                   the precision a kind::tf32 MMA keeps of an fp32 operand, at half the bytes and twice the MMA rate
+                   (kind::f16, fp32 accumulate).  Stores saturate at +-65504.  Tensor-core conv kernels, ast_maxpool2_fwd,
+                   ast_row_im2col outputs and ReLU-mask operands only. */
 } ast_dtype;
 
 /* strided 4-D view; strides in ELEMENTS.  */
