@@ -115,15 +115,15 @@ __device__ __forceinline__ unsigned pack2(float a, float b) {
 __device__ __forceinline__ unsigned pack2_16(int dtype, float a, float b) { return dtype == AST_F16 ? pack2<true>(a, b) : pack2<false>(a, b); }
 __device__ __forceinline__ float ld_elem(const Img& im, long long off) {
   if (im.dtype == AST_F32) return ((const float*)im.ptr)[off];
-  if (im.dtype == AST_U8) return (float)((const unsigned char*)im.ptr)[off];
+  if (im.dtype == AST_BF16) return __bfloat162float(((const __nv_bfloat16*)im.ptr)[off]);
   if (im.dtype == AST_F16) return __half2float(((const __half*)im.ptr)[off]);
-  return __bfloat162float(((const __nv_bfloat16*)im.ptr)[off]);
+  return (float)((const unsigned char*)im.ptr)[off];
 }
 __device__ __forceinline__ void st_elem(const Img& im, long long off, float v) {
   if (im.dtype == AST_F32) ((float*)im.ptr)[off] = v;
-  else if (im.dtype == AST_U8) ((unsigned char*)im.ptr)[off] = (unsigned char)__float2uint_rz(fminf(fmaxf(v, 0.f), 255.f));
+  else if (im.dtype == AST_BF16) ((__nv_bfloat16*)im.ptr)[off] = __float2bfloat16_rn(v);
   else if (im.dtype == AST_F16) ((__half*)im.ptr)[off] = f2h_sat(v);
-  else ((__nv_bfloat16*)im.ptr)[off] = __float2bfloat16_rn(v);
+  else ((unsigned char*)im.ptr)[off] = (unsigned char)__float2uint_rz(fminf(fmaxf(v, 0.f), 255.f));
 }
 __device__ __forceinline__ long long img_off(const Img& im, int n, int y, int x, int c) {
   return (long long)n * im.sn + (long long)y * im.sh + (long long)x * im.sw + (long long)c * im.sc;
@@ -199,14 +199,13 @@ __device__ __forceinline__ void ld4(const __half* p, float* v) {
 }
 __device__ __forceinline__ void ld4_img(const Img& im, long long off, float* v) {
   if (im.dtype == AST_F32) ld4((const float*)im.ptr + off, v);
-  else if (im.dtype == AST_F16) ld4((const __half*)im.ptr + off, v);
-  else ld4((const __nv_bfloat16*)im.ptr + off, v);
+  else if (im.dtype == AST_BF16) ld4((const __nv_bfloat16*)im.ptr + off, v);
+  else ld4((const __half*)im.ptr + off, v);
 }
 __device__ __forceinline__ void st4_img(const Img& im, long long off, const float* v) {
   if (im.dtype == AST_F32) st4((float*)im.ptr + off, v);
-  else if (im.dtype == AST_F16)
-    *reinterpret_cast<uint2*>((__half*)im.ptr + off) = make_uint2(pack2_16(AST_F16, v[0], v[1]), pack2_16(AST_F16, v[2], v[3]));
-  else st4((__nv_bfloat16*)im.ptr + off, v);
+  else if (im.dtype == AST_BF16) st4((__nv_bfloat16*)im.ptr + off, v);
+  else *reinterpret_cast<uint2*>((__half*)im.ptr + off) = make_uint2(pack2<true>(v[0], v[1]), pack2<true>(v[2], v[3]));
 }
 
 inline int num_sms() {

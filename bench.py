@@ -447,9 +447,10 @@ def run_ours(args):
     rooflines = [r for r in rooflines if r]
     conv_ms = sum(fam_ms.get(f, 0.0) for f in CONV_FAMILIES)
     conv_tf = conv_algo_total / (conv_ms / 1e3) / 1e12
-    # TF32: VGG forward on the generated batch (36.465) and on the content batch (12.306) + the Gram backward (2.147);
-    # bf16: TransformerNet forward / dgrad and the VGG dgrad (36.465)
-    tf32_share = (36.465 + 12.306 + 2.147) / GF_PER_IMG["conv_gather"]
+    # kind::tf32: only the Gram backward (2.147 GF/img; its F operand is an fp32 tap).  kind::f16: TransformerNet forward /
+    # dgrad and the VGG dgrad in bf16, the VGG forward (36.465 + 12.306) with fp16 operands - the 10 mantissa bits TF32
+    # keeps of an fp32 value, at the 16-bit MMA rate.
+    tf32_share = 2.147 / GF_PER_IMG["conv_gather"]
     mix_peak = None if not tf32_peak else 1.0 / (tf32_share / tf32_peak + (1 - tf32_share) / peaks["bf16_tflops"])
     roofline_conv = {"kernel": "all conv fwd/dgrad launches of one step (conv_hx + conv_st + conv_px + conv_ws + conv_tc kernels)",
                      "bound": "tensor", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
@@ -498,7 +499,10 @@ def run_ours(args):
                                f"precision={args.precision}, random-init TransformerNet+VGG16, fused Adam(L2)",
                    "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
                    "input": f"{args.input} BGR [B,3,{S},{S}] (dataset.py:97-108 images are uint8-derived)",
-                   "l2": "per-step working set (GBs of activations) >> 126 MB L2; inputs rotate over 4 buffers"},
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2; inputs rotate over 4 buffers",
+                   "arithmetic": ("TransformerNet + VGG gradient chain bf16, VGG forward fp16 operands (10-bit mantissa, the "
+                                  "precision of TF32) with fp32 taps, Grams TF32; fp32 accumulation everywhere"
+                                  if args.precision == "fast" else "fp32 FFMA")},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 12, "steps": ke},
         "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step), "clocks": clocks,
         "roofline": dominant, "roofline_conv": roofline_conv, "roofline_instnorm": roofline_in, "rooflines": rooflines,

@@ -8,27 +8,29 @@ from artist_style_transfer_b200 import _lib, ops, conv_geometry as cg
 torch.manual_seed(0)
 dev = torch.device('cuda')
 n = 32
-bf, f32 = torch.bfloat16, torch.float32
+bf, f32, f16 = torch.bfloat16, torch.float32, torch.float16
 todo = []
 
-def conv(name, dtype, cin, cout, hin, launches, hout, stats=False, mask=False, pooled=False, w_img=False, relu=False):
+def conv(name, dtype, cin, cout, hin, launches, hout, stats=False, mask=False, pooled=False, w_img=False, relu=False, odt=None,
+         mask_dtype=f32):
+    odt = odt or dtype
     x = torch.randn(n, hin, hin, cin, device=dev).to(dtype)
-    y = torch.empty(n, hout, hout, cout, device=dev, dtype=dtype)
+    y = torch.empty(n, hout, hout, cout, device=dev, dtype=odt)
     nt = sum(len(l.taps) for l in launches)
     if w_img:
         wp = (torch.randn(n, nt, cout, cin, device=dev) / cin ** 0.5).to(dtype)
     else:
         wp = (torch.randn(nt, cout, cin, device=dev) / (cin * nt) ** 0.5).to(dtype)
     sums = torch.zeros(2 * n * cout, dtype=torch.float64, device=dev) if stats else None
-    m = torch.randn(n, hout, hout, cout, device=dev) if mask else None
-    pool = torch.empty(n, hout // 2, hout // 2, cout, device=dev, dtype=dtype) if pooled else None
+    m = torch.randn(n, hout, hout, cout, device=dev).to(mask_dtype) if mask else None
+    pool = torch.empty(n, hout // 2, hout // 2, cout, device=dev, dtype=dtype) if pooled else None   # fp16 in production
     pcodes = torch.empty(n, hout // 2, hout // 2, cout, device=dev, dtype=torch.uint8) if pooled else None
     todo.append((name, lambda: ops.conv_gather(x, wp, launches, y, tensor=True, stats=sums, mask=m, pooled=pool, pool_codes=pcodes, relu=relu,
-                                               w_img_stride=cout * cin * nt if w_img else 0, round_tf32=dtype == f32)))
+                                               w_img_stride=cout * cin * nt if w_img else 0, round_tf32=odt == f32 and dtype != bf)))
 
 vt9 = [cg.Launch(256, 256, 1, 1, 0, 0, [(d, 0) for d in range(9)], [(d, 0) for d in range(9)], 0)]
-conv("conv_ws tf32 VGG conv1_2 64->64 256^2 +ReLU +fused MaxPool +window codes", f32, 64, 64, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, pooled=True, relu=True)
-conv("conv_ws bf16 VGG dgrad conv1_2 64->64 256^2 +mask", bf, 64, 64, 256, cg.conv_dgrad(3, 1, 1, 256, 256), 256, mask=True)
+conv("conv_ws fp16 VGG conv1_2 64->64 256^2 (fp32 tap out) +ReLU +fused MaxPool (fp16) +window codes", f16, 64, 64, 256, cg.conv_fwd(3, 1, 1, 256, 256), 256, pooled=True, relu=True, odt=f32)
+conv("conv_ws bf16 VGG dgrad conv1_2 64->64 256^2 +fp16 mask", bf, 64, 64, 256, cg.conv_dgrad(3, 1, 1, 256, 256), 256, mask=True, mask_dtype=f16)
 
 def stacked(name, dtype, odt, cin, cout, hw_in, hw_out, launches, stats=False, relu=False):
     from artist_style_transfer_b200 import arena as arena_mod
@@ -47,12 +49,12 @@ def stacked(name, dtype, odt, cin, cout, hw_in, hw_out, launches, stats=False, r
 
 stacked("conv_st bf16 T first layer (9 vertical taps over row-im2col, 4 interleaved rows) 32->32 256^2 +stats", bf, bf, 32, 32, (264, 256), (256, 256), vt9, stats=True)
 stacked("conv_st bf16 T ConvTranspose 3x3 s2 64->32 128^2->256^2 (4 phases stacked) +stats", bf, bf, 64, 32, (128, 128), (256, 256), cg.convT_fwd(3, 2, 1, 1, 128, 128), stats=True)
-stacked("conv_st tf32 VGG conv1_1 (3 vertical taps, 2 interleaved rows) 16->64 256^2 +ReLU", f32, f32, 16, 64, (256, 256), (256, 256),
+stacked("conv_st fp16 VGG conv1_1 (3 vertical taps, 2 interleaved rows) 32->64 256^2 +ReLU", f16, f16, 32, 64, (256, 256), (256, 256),
         [cg.Launch(256, 256, 1, 1, 0, 0, [(-1, 0), (0, 0), (1, 0)], [(0, 0), (1, 0), (2, 0)], 0)], relu=True)
 conv("conv_hx bf16 T residual 3x3 128->128 64^2 +stats", bf, 128, 128, 66, cg.conv_fwd(3, 1, 0, 66, 66), 64, stats=True)
-conv("conv_hx tf32 VGG conv2_2 128->128 128^2", f32, 128, 128, 128, cg.conv_fwd(3, 1, 1, 128, 128), 128, relu=True)
-conv("conv_hx tf32 VGG conv4_2 512->512 32^2", f32, 512, 512, 32, cg.conv_fwd(3, 1, 1, 32, 32), 32, relu=True)
-conv("conv_hx bf16 VGG dgrad conv3_2 256->256 64^2 +mask", bf, 256, 256, 64, cg.conv_dgrad(3, 1, 1, 64, 64), 64, mask=True)
+conv("conv_hx fp16 VGG conv2_2 128->128 128^2 (fp32 tap out)", f16, 128, 128, 128, cg.conv_fwd(3, 1, 1, 128, 128), 128, relu=True, odt=f32)
+conv("conv_hx fp16 VGG conv4_2 512->512 32^2", f16, 512, 512, 32, cg.conv_fwd(3, 1, 1, 32, 32), 32, relu=True)
+conv("conv_hx bf16 VGG dgrad conv3_2 256->256 64^2 +fp16 mask", bf, 256, 256, 64, cg.conv_dgrad(3, 1, 1, 64, 64), 64, mask=True, mask_dtype=f16)
 conv("conv_px bf16 T conv 3x3 stride 2 64->128 130^2->64^2 +stats", bf, 64, 128, 130, cg.conv_fwd(3, 2, 0, 130, 130), 64, stats=True)
 conv("conv_tc tf32 Gram backward relu2_2 (1x1, per-image weights) 128->128 128^2", f32, 128, 128, 128, cg.conv_fwd(1, 1, 0, 128, 128), 128, w_img=True)
 

@@ -341,3 +341,67 @@ def test_conv_stacked_argument_errors(env):
     with pytest.raises(RuntimeError, match="64 bytes or a multiple of 128"):
         ops.conv_stacked(x[..., :48].contiguous(), w[..., :48].contiguous(), stk,
                          torch.zeros(1, 16, 16, 32, device="cuda", dtype=torch.bfloat16))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp16 operands (AST_F16): the fast-mode VGG forward stores its non-tap activations as IEEE half - the 10 mantissa bits a
+# kind::tf32 MMA keeps of an fp32 operand - and runs kind::f16.
+F16_CASES = [
+    # cin, cout, n, h, w, out dtype, expected kernel family
+    (64, 64, 2, 16, 16, torch.float32, "conv_ws"),      # conv1_2 class: fp16 in, fp32 (tap) out
+    (64, 128, 1, 16, 24, torch.float16, "conv_hx"),     # conv2_1 class
+    (128, 128, 2, 16, 16, torch.float16, "conv_hx"),
+    (256, 512, 1, 8, 8, torch.float16, "conv_hx"),
+    (512, 512, 1, 8, 8, torch.float32, "conv_hx"),      # conv4_3 class: tap output
+]
+
+
+@pytest.mark.parametrize("cin,cout,n,h,w,odt,family", F16_CASES)
+def test_conv_fp16_operands(env, cin, cout, n, h, w, odt, family):
+    cg, ops = env
+    from artist_style_transfer_b200 import _lib
+    torch.manual_seed(cin + cout)
+    x = torch.randn(n, h, w, cin, device="cuda").half()
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5)
+    bias = torch.randn(cout, device="cuda")
+    launches = cg.conv_fwd(3, 1, 1, h, w)
+    wp = ops.pack_weights(wt, launches, cout, cin, cin * 9, 9, 3, 1, torch.float32).half()
+    y = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=odt)
+    before = _lib.family_stats()
+    ops.conv_gather(x, wp, launches, y, bias=bias, relu=True, tensor=True)
+    assert _lib.family_delta(before)[family][0] == 1
+    torch.cuda.synchronize()
+    xr = x.double().cpu().permute(0, 3, 1, 2)
+    wr = wp.double().cpu().view(3, 3, cout, cin).permute(2, 3, 0, 1)
+    yr = F.relu(F.conv2d(xr, wr, bias.double().cpu(), padding=1)).permute(0, 2, 3, 1)
+    assert not torch.isnan(y.float()).any()
+    # identical fp16 operands, fp32 accumulation: only summation order (and one fp16 rounding of the result) differs
+    assert rel(y, yr) < (1e-5 if odt == torch.float32 else 4e-4), rel(y, yr)
+
+
+def test_fp16_stores_saturate_and_masks_read_fp16(env):
+    cg, ops = env
+    # a result beyond the fp16 range is stored as +-65504, never inf
+    x = torch.full((1, 8, 8, 64), 200.0, device="cuda").half()
+    wp = torch.full((9, 64, 64), 1.0, device="cuda").half()
+    y = torch.empty(1, 8, 8, 64, device="cuda", dtype=torch.float16)
+    ops.conv_gather(x, wp, cg.conv_fwd(3, 1, 1, 8, 8), y, tensor=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all() and float(y.float().max()) == 65504.0
+    # max-pool writing fp16 (+ window codes) == torch on the same values
+    a = torch.randn(2, 8, 12, 64, device="cuda")
+    codes = torch.empty(2, 4, 6, 64, dtype=torch.uint8, device="cuda")
+    p = ops.maxpool2_fwd(a, codes=codes, out_dtype=torch.float16)
+    ref = F.max_pool2d(a.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert p.dtype == torch.float16 and torch.equal(p, ref.half())
+    # a bf16 data gradient masked by an fp16 activation == the same with the fp32 copy of that activation
+    g = torch.randn(1, 16, 16, 128, device="cuda").bfloat16()
+    act = torch.randn(1, 16, 16, 128, device="cuda")
+    wd = (torch.randn(9, 128, 128, device="cuda") / 34).bfloat16()
+    ls = cg.conv_dgrad(3, 1, 1, 16, 16)
+    o16 = torch.empty(1, 16, 16, 128, device="cuda", dtype=torch.bfloat16)
+    o32 = torch.empty_like(o16)
+    ops.conv_gather(g, wd, ls, o16, mask=act.half(), tensor=True)
+    ops.conv_gather(g, wd, ls, o32, mask=act.half().float(), tensor=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o16, o32)
