@@ -115,9 +115,9 @@ __device__ __forceinline__ unsigned pack2(float a, float b) {
 __device__ __forceinline__ unsigned pack2_16(int dtype, float a, float b) { return dtype == AST_F16 ? pack2<true>(a, b) : pack2<false>(a, b); }
 __device__ __forceinline__ float ld_elem(const Img& im, long long off) {
   if (im.dtype == AST_F32) return ((const float*)im.ptr)[off];
+  if (im.dtype == AST_U8) return (float)((const unsigned char*)im.ptr)[off];
   if (im.dtype == AST_BF16) return __bfloat162float(((const __nv_bfloat16*)im.ptr)[off]);
-  if (im.dtype == AST_F16) return __half2float(((const __half*)im.ptr)[off]);
-  return (float)((const unsigned char*)im.ptr)[off];
+  return __half2float(((const __half*)im.ptr)[off]);
 }
 __device__ __forceinline__ void st_elem(const Img& im, long long off, float v) {
   if (im.dtype == AST_F32) ((float*)im.ptr)[off] = v;

@@ -22,8 +22,11 @@ constexpr int CT_THREADS = 192 + 32 * (CT_MAX_PROD - 1);
 // parity cannot alias.
 // (Measured and removed: a "halo" mode loading ONE (th + hy) x (tw + hx) patch per 64-channel box for all taps of a CTA
 // and addressing the taps through shifted MN-major descriptors.  It halves the L2 -> shared memory traffic of the 3x3
-// filter gradients but ran 1.8x SLOWER (residual layers 61 -> 107 us, results identical) - presumably MN-major operands
-// that do not start on a 1024-byte swizzle atom are fetched at a fraction of the aligned rate; not investigated further.)
+// filter gradients but ran 1.8x SLOWER (residual layers 61 -> 107 us, results identical).  A second variant with ALIGNED
+// shifts only (4 x 16 pixel tiles, the three taps of one filter column sharing a (4 + 2) x 16 patch, every operand start
+// on a 2 KB boundary) was slower as well (61 -> 72 us): these kernels are bound by the MN-major MMAs themselves (both
+// variants issue one N = 128 instruction per tap and K step instead of N = 256 + N = 128), not by the L2 -> shared
+// memory traffic.)
 __device__ __forceinline__ int ct_producer_index(int warp) { return warp == 0 ? 0 : (warp >= 6 ? warp - 5 : -1); }
 // most producers first, then most stages: gives up at most two stages to make the stage count divisible
 inline void ct_pick_producers(int& stages, int& nprod) {

@@ -99,11 +99,18 @@ row_im2col_pix_kernel(Img src, Img out, const float* __restrict__ shift, int kw_
 #pragma unroll
       for (int e = 0; e < OUTC; e += 4) st4((float*)out.ptr + oo + e, v + e);
     } else {
+      unsigned short* op = (unsigned short*)out.ptr + oo;      // bf16 or fp16 elements: type tested once, outside the loop
+      if (out.dtype == AST_F16) {
 #pragma unroll
-      for (int e = 0; e < OUTC; e += 8)     // bf16 or fp16 elements
-        *reinterpret_cast<uint4*>((unsigned short*)out.ptr + oo + e) =
-            make_uint4(pack2_16(out.dtype, v[e], v[e + 1]), pack2_16(out.dtype, v[e + 2], v[e + 3]),
-                       pack2_16(out.dtype, v[e + 4], v[e + 5]), pack2_16(out.dtype, v[e + 6], v[e + 7]));
+        for (int e = 0; e < OUTC; e += 8)
+          *reinterpret_cast<uint4*>(op + e) = make_uint4(pack2<true>(v[e], v[e + 1]), pack2<true>(v[e + 2], v[e + 3]),
+                                                         pack2<true>(v[e + 4], v[e + 5]), pack2<true>(v[e + 6], v[e + 7]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < OUTC; e += 8)
+          *reinterpret_cast<uint4*>(op + e) = make_uint4(pack2<false>(v[e], v[e + 1]), pack2<false>(v[e + 2], v[e + 3]),
+                                                         pack2<false>(v[e + 4], v[e + 5]), pack2<false>(v[e + 6], v[e + 7]));
+      }
     }
   }
 }
