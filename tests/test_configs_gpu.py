@@ -179,3 +179,35 @@ def test_cycle_gram_bank(ast):
                    for j, c in enumerate(content[:i + 1])]
             np.testing.assert_allclose(np.array(got[i]), np.array(ref[i]), rtol=5e-3)
         tr.close()
+
+
+@pytest.mark.parametrize("h,w", [(36, 52), (68, 76), (132, 140)])
+def test_sizes_that_are_not_multiples_of_16_fast_vs_strict(ast, h, w):
+    """Image sizes that are multiples of 4 only (partial tiles in every tensor-core kernel: block-stacked phases and
+    interleaved rows, halo tiles, fp16 activations, pooling codes): the fast path agrees with the strict FFMA path of the
+    same weights - losses to 1e-2 (north_star), gradients to bf16 accuracy."""
+    torch.manual_seed(h * w)
+    x = torch.randint(0, 256, (2, 3, h, w), device="cuda").float()
+    style = torch.randint(0, 256, (3, h, w), device="cuda").float()
+    res = []
+    for precision in ("fast", "fp32"):
+        net, vgg = build(ast, precision)
+        sg = ast.style_grams_single(vgg, style, 2)
+        c, s, _ = ast.perceptual_step(net, vgg, x, sg)
+        g = torch.cat([p.grad.flatten() for p in net.parameters()])
+        res.append((float(c), float(s), g))
+    assert abs(res[0][0] - res[1][0]) <= 1e-2 * abs(res[1][0])
+    assert abs(res[0][1] - res[1][1]) <= 1e-2 * abs(res[1][1])
+    assert rel(res[0][2], res[1][2]) < 5e-2
+
+
+def test_forward_on_sizes_that_are_not_multiples_of_4(ast):
+    """The transform net maps (250, 330) -> (252, 332) like the reference's layers (stride-2 convs round up, the transposed
+    convs double); fast and strict mode agree."""
+    net_f, _ = build(ast, "fast")
+    net_s, _ = build(ast, "fp32")
+    x = torch.randint(0, 256, (1, 3, 250, 330), device="cuda").float()
+    with torch.no_grad():
+        yf, ys = net_f(x), net_s(x)
+    assert tuple(yf.shape) == tuple(ys.shape) == (1, 3, 252, 332)
+    assert rel(yf, ys) < 5e-2
