@@ -419,6 +419,8 @@ struct CtThinParams {
   int ntaps, ngrp, r_valid, c_valid, chunks_per_cta, stages, nprod, stage_bytes;
   int vstack;                       // all taps are consecutive rows of one column and a chunk is one 64-pixel row segment:
                                     // ONE box of ntaps rows replaces ntaps loads (tap t = 4 KB further into it)
+  int merged;                       // vstack + unit row multiplier: ONE MMA per K step for all taps (see contract_thin)
+  int r_rows;                       // merged: rows of the fixed operand's patch = 4 * (ngrp - 1) + 1
   long long chunks_total, s_m, s_n;
   float scale;
   unsigned idesc;
@@ -463,7 +465,7 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
   const int prod = ct_producer_index(warp);
   if (prod >= 0) {
     const int per_img_chunks = p.tiles_i * p.tiles_j;
-    if (warp == 0 && lane == 0) {   // unwritten tap slots feed only ignored accumulator rows, but keep them finite: zero once
+    if (warp == 0 && lane == 0 && !p.merged) {   // unwritten tap slots feed only ignored accumulator rows, but keep them finite: zero once
       for (int st = 0; st < p.stages; ++st)
         for (int t = p.ntaps; t < padded_taps; ++t) {
           uint4* z = (uint4*)(smem + (size_t)st * p.stage_bytes + (1 + t) * THIN_BOX);
@@ -482,13 +484,19 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (lane == 0) {
         unsigned char* sr = smem + (size_t)s * p.stage_bytes;
-        mbar_expect_tx(&full_bar[s], (unsigned)((1 + p.ntaps) * THIN_BOX));
-        tma_load_4d(sr, &tm_r, &full_bar[s], 0, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
-        if (p.vstack)        // a producer pays ~500 cycles per TMA instruction: one 36 KB box instead of nine 4 KB ones
-          tma_load_4d(sr + THIN_BOX, &tm_c, &full_bar[s], 0, j0 + p.dx[0], i0 + p.dy[0], img);
-        else
-          for (int t = 0; t < p.ntaps; ++t)
-            tma_load_4d(sr + (1 + t) * THIN_BOX, &tm_c, &full_bar[s], 0, p.c_s * j0 + p.dx[t], p.c_s * i0 + p.dy[t], img);
+        if (p.merged) {      // fixed operand: rows i0 - (r_rows - 1) .. i0 (rows outside the image read 0); shifted: taps 0..3
+          mbar_expect_tx(&full_bar[s], (unsigned)((p.r_rows + 4 + 2 * (p.th - 1)) * THIN_BOX));
+          tma_load_4d(sr, &tm_r, &full_bar[s], 0, j0 + p.r_ox, i0 - (p.r_rows - 1) + p.r_oy, img);
+          tma_load_4d(sr + (p.r_rows + p.th - 1) * THIN_BOX, &tm_c, &full_bar[s], 0, j0 + p.dx[0], i0 + p.dy[0], img);
+        } else {
+          mbar_expect_tx(&full_bar[s], (unsigned)((1 + p.ntaps) * THIN_BOX));
+          tma_load_4d(sr, &tm_r, &full_bar[s], 0, p.r_s * j0 + p.r_ox, p.r_s * i0 + p.r_oy, img);
+          if (p.vstack)        // a producer pays ~500 cycles per TMA instruction: one 36 KB box instead of nine 4 KB ones
+            tma_load_4d(sr + THIN_BOX, &tm_c, &full_bar[s], 0, j0 + p.dx[0], i0 + p.dy[0], img);
+          else
+            for (int t = 0; t < p.ntaps; ++t)
+              tma_load_4d(sr + (1 + t) * THIN_BOX, &tm_c, &full_bar[s], 0, p.c_s * j0 + p.dx[t], p.c_s * i0 + p.dy[t], img);
+        }
       }
       __syncwarp();
     }
@@ -501,6 +509,18 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
       tc_fence_after();
       if (lane == 0) {
         const unsigned r_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        if (p.merged) {
+          // ONE instruction per K step: A = taps 0..3 of the shifted operand (4 column blocks, one row apart), B = the fixed
+          // operand at rows i0 - 4*(ngrp-1), .., i0 - 4, i0 (ngrp column blocks, four rows = 16 KB apart):
+          //   D[(t1, cc)][(nb, rc)] += sum_p C[p + t1 rows][cc] * R[p - 4*(ngrp-1-nb) rows][rc]   = tap t1 + 4*(ngrp-1-nb)
+          // (a chunk is th rows of 64 pixels: both patches hold th - 1 extra rows and K step k is 16 pixels of row k / 4)
+          const unsigned c_addr = r_addr + (p.r_rows + p.th - 1) * THIN_BOX;
+          for (int k = 0; k < p.th * (THIN_KP / 16); ++k) {
+            const unsigned long long ad = make_mn_desc(c_addr + k * 1024, THIN_BOX, 512, 4u);
+            const unsigned long long bd = make_mn_desc(r_addr + k * 1024, 4 * THIN_BOX, 512, 4u);
+            tc_mma<0>(tmem_base, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+          }
+        } else
         for (int g = 0; g < p.ngrp; ++g) {
           const unsigned c_addr = r_addr + (1 + 4 * g) * THIN_BOX;
           for (int k = 0; k < THIN_KP / 16; ++k) {           // UMMA_K = 16 pixel rows of 64 bytes
@@ -523,7 +543,7 @@ contract_thin_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_cons
     tc_fence_after();
     for (int g = 0; g < p.ngrp; ++g) {
       float v[32];
-      tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(g * 32), v);
+      tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)((p.merged ? p.ngrp - 1 - g : g) * 32), v);
       const int t = 4 * g + q;
       if (t < p.ntaps && lane < p.c_valid) {
         float* o = out + (tap_off ? tap_off[t] : 0) + (long long)lane * p.s_n;
@@ -568,23 +588,33 @@ static int contract_thin(EncodeTiledFn encode, const ast_image* rows, int r_s, i
   p.vstack = c_s == 1 && mj >= THIN_KP / 2;
   for (int t = 1; t < ntaps && p.vstack; ++t) p.vstack = p.dx[t] == p.dx[0] && p.dy[t] == p.dy[0] + t;
   if (p.vstack) { p.tw = THIN_KP; p.th = 1; }
-  p.tiles_i = (mi + p.th - 1) / p.th; p.tiles_j = (mj + p.tw - 1) / p.tw;
+  // merged mode: the three (ntaps = 9) tap groups of a vertical stack become the N blocks of ONE MMA.  The kernel is bound
+  // by its MN-major MMAs (M128 x N32 x K16 at ~125 clk each, three per K step); with the fixed operand loaded as a patch
+  // of r_rows rows (row shifts 0, -4, -8 as column blocks) tap t1 + 4*t2 is block (t1, t2) of a single M128 x N96 MMA.
+  // The chunk rows then run 4*(ngrp-1) rows past the image so that every (row, tap) product is visited.
+  p.merged = p.vstack && r_s == 1 && p.ngrp >= 2 && p.ngrp * 32 <= 256;
+  p.r_rows = 4 * (p.ngrp - 1) + 1;
+  // four image rows per chunk: the row-shifted patches overlap, so the L2 -> shared-memory traffic per image row drops from
+  // 9 + 4 to (12 + 7) / 4 patch rows.  First layer (B = 32, 256^2): 172 us unmerged, merged with 1 / 2 / 3 / 4 rows per chunk
+  // 131 / 87 / 92 / 80 us (two 76 KB stages at 4 rows).
+  if (p.merged) p.th = 4;
+  p.tiles_i = (mi + (p.merged ? p.r_rows - 1 : 0) + p.th - 1) / p.th; p.tiles_j = (mj + p.tw - 1) / p.tw;
   p.chunks_total = (long long)p.tiles_i * p.tiles_j * p.n_img;
   p.s_m = s_m; p.s_n = s_n; p.scale = scale;
-  p.stage_bytes = (1 + 4 * p.ngrp) * THIN_BOX;
+  p.stage_bytes = p.merged ? (p.r_rows + 4 + 2 * (p.th - 1)) * THIN_BOX : (1 + 4 * p.ngrp) * THIN_BOX;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > CT_MAX_STAGES) p.stages = CT_MAX_STAGES;
   ct_pick_producers(p.stages, p.nprod);
   if (p.stages < 2) return 0;
   // bf16 A/B (1), both MN-major (bits 15, 16), N = 32, M = 128
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)((p.merged ? p.ngrp * 32 : 32) >> 3) << 17) | ((128u >> 4) << 24);
   long long ks = num_sms();
   if (ks > p.chunks_total) ks = p.chunks_total;
   p.chunks_per_cta = (int)((p.chunks_total + ks - 1) / ks);
   const int grid = (int)((p.chunks_total + p.chunks_per_cta - 1) / p.chunks_per_cta);
   alignas(64) CUtensorMap tm_r, tm_c;
-  if (int e = encode_thin_operand(encode, &tm_r, rows, p.tw, p.th, r_s)) return e;
-  if (int e = encode_thin_operand(encode, &tm_c, cols, p.tw, p.vstack ? ntaps : p.th, c_s)) return e;
+  if (int e = encode_thin_operand(encode, &tm_r, rows, p.tw, p.merged ? p.r_rows + p.th - 1 : p.th, r_s)) return e;
+  if (int e = encode_thin_operand(encode, &tm_c, cols, p.tw, p.merged ? 4 + p.th - 1 : (p.vstack ? ntaps : p.th), c_s)) return e;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   cudaError_t e = set_max_smem(contract_thin_kernel, smem);
   if (e != cudaSuccess) { set_error("contract_thin: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
