@@ -24,6 +24,7 @@ struct WsParams {
   int dy_min, dx_min, ph, pw;
   int patch_bytes, patch_tx, n_pbuf, w_tile_bytes, w_total_bytes;
   int T;                   // sub-tiles (16 rows x 8 px each, stacked vertically) per pipeline step / TMEM stage
+  int stage_w;             // bytes of the per-warp store-transpose stage: 1 KB, or 4 KB (a whole 32 x 32 fp32 block) when pooling
   unsigned idesc, layout_type, sbo;
   long long total_tiles;
   short tdy[AST_MAX_TAPS];
@@ -34,6 +35,90 @@ __device__ __forceinline__ unsigned long long pack_desc(unsigned lo, unsigned hi
   unsigned long long d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
+}
+
+__device__ __forceinline__ bool valid_window(int iw, int jw, const WsParams& p) { return iw + 1 < p.mi && jw + 1 < p.mj; }
+// window code of (a, b, c, d) = positions (0,0), (0,1), (1,0), (1,1): bits 0-1 arg max (first maximum wins, like ATen),
+// bits 2-5 = (value > 0); m = the maximum (same definition as ast_maxpool2_fwd / pool_code in pointwise.cu)
+__device__ __forceinline__ unsigned pool_code4(float a, float b, float c, float d, float& m) {
+  int arg = 0; m = a;
+  if (b > m) { m = b; arg = 1; }
+  if (c > m) { m = c; arg = 2; }
+  if (d > m) { m = d; arg = 3; }
+  return (unsigned)arg | ((a > 0.f) ? 4u : 0u) | ((b > 0.f) ? 8u : 0u) | ((c > 0.f) ? 16u : 0u) | ((d > 0.f) ? 32u : 0u);
+}
+
+// Epilogue of one 32-pixel x 32-channel chunk WITH the fused nn.MaxPool2d(2, 2) (+ window codes): bias / ReLU / TF32
+// rounding in registers, then the whole fp32 block goes through a 4 KB per-warp shared-memory stage (pixel-major,
+// XOR-swizzled 16-byte chunks).  From the stage (a) the full-resolution output is written with coalesced 16-byte stores
+// and (b) every lane pools ONE 2 x 2 window x 8 channels with plain ALU code: lane = window (0..7) x channel group (0..3).
+// (The first version exchanged the window's values between lanes: 3 shuffles + a compare chain per channel in EVERY
+// lane, ~480 of the ~800 instructions of the chunk - conv1_2 was bound by it once fp16 operands had halved its MMAs.)
+__device__ __forceinline__ void ws_epilogue_pooled(float* v, int co, int img, int i_base, int j_base, bool valid, bool store_out,
+                                                   const WsParams& p, const float* __restrict__ bias, const Img& out,
+                                                   const EpiRows& rows, const Img& pooled, const Img& pcodes,
+                                                   unsigned char* stage, int lane) {
+  if (co >= p.cout) return;                                  // uniform
+  if (bias) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + e));
+      v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+    }
+  }
+  if (p.flags & AST_CONV_RELU) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  if (p.flags & AST_CONV_ROUND_TF32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = round_tf32(v[e]);
+  }
+  const unsigned st = smem_u32(stage);
+  // pixel `lane` -> stage row `lane` (128 B), chunk c at 16 * (c ^ (lane & 7))
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    sts128(st + 128u * lane + 16u * (c ^ (lane & 7)),
+           make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+  __syncwarp();
+  if (store_out && out.dtype == AST_F32) {                   // pixel 4k + lane/8, chunk lane%8: 128-byte runs per pixel
+    float* base = (float*)out.ptr + co + 4 * (lane & 7);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int px = 4 * k + (lane >> 3);
+      const uint4 val = lds128(st + 128u * px + 16u * ((lane & 7) ^ (px & 7)));
+      const long long off = rows.off[k];
+      if (off >= 0) *reinterpret_cast<uint4*>(base + off) = val;
+    }
+  }
+  // ---- pooling: lane = (window wi = lane / 4, channels 8 * (lane % 4) ..); the warp's pixels are 4 tile rows x 8 columns
+  const int wi = lane >> 2, cg = lane & 3;
+  const int wy = wi >> 2, wx = wi & 3;
+  const int iw = i_base + 2 * wy, jw = j_base + 2 * wx;
+  float a[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                              // k = 2 * dy + dx
+    const int px = 8 * (2 * wy + (k >> 1)) + 2 * wx + (k & 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 u = lds128(st + 128u * px + 16u * ((2 * cg + h) ^ (px & 7)));
+      a[k][4 * h] = __uint_as_float(u.x); a[k][4 * h + 1] = __uint_as_float(u.y);
+      a[k][4 * h + 2] = __uint_as_float(u.z); a[k][4 * h + 3] = __uint_as_float(u.w);
+    }
+  }
+  __syncwarp();                                              // the stage is rewritten by the next chunk
+  if (!valid_window(iw, jw, p)) return;
+  float m[8];
+  unsigned c0 = 0, c1 = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const unsigned code = pool_code4(a[0][e], a[1][e], a[2][e], a[3][e], m[e]);
+    if (e < 4) c0 |= code << (8 * e); else c1 |= code << (8 * (e - 4));
+  }
+  const long long po = img_off(pooled, img, iw >> 1, jw >> 1, co + 8 * cg);
+  st4_img(pooled, po, m);
+  st4_img(pooled, po + 4, m + 4);
+  if (pcodes.ptr) *reinterpret_cast<uint2*>(pcodes.ptr + img_off(pcodes, img, iw >> 1, jw >> 1, co + 8 * cg)) = make_uint2(c0, c1);
 }
 
 // MINB = 2: built for two resident CTAs per SM (<= 102 registers): layers whose weights + patches need less than half of
@@ -160,7 +245,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const int cpar = (warp - 2) >> 2;              // which half of the 32-column chunks this warp drains
     const int row = q * 32 + lane;
     const int ty = row / WS_TW, tx = row % WS_TW;
-    unsigned char* stage = smem_p + (size_t)p.n_pbuf * p.patch_bytes + (warp - 2) * 1024;
+    unsigned char* stage = smem_p + (size_t)p.n_pbuf * p.patch_bytes + (warp - 2) * p.stage_w;
     int as = 0; unsigned aph = 0;
     EpiStatAcc sacc;
     sacc.reset(-1);
@@ -197,45 +282,12 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
               if (s_run) { const int k = (c0 - cpar * 32) >> 6; sacc.s[k & 1][0] += (double)su; sacc.s[k & 1][1] += (double)sq; }
               else { double* row = stats + ((long long)img * p.cout_valid + co + lane) * 2; atomicAdd(row, (double)su); atomicAdd(row + 1, (double)sq); }
             }
-            tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
-                                    pm, use_pm && c0 == cpar * 32);
-            if (pooled.ptr) {
-              // nn.MaxPool2d(2, 2) of the finished values (v was updated in place): a tile row is 8 pixels and a warp owns 4
-              // tile rows, so the 2x2 window of pixel (ty, tx) = lanes l, l^1 (x neighbour), l^8 (y neighbour), l^9
-              const bool lead = !(lane & 9) && i + 1 < p.mi && j + 1 < p.mj && co < p.cout;   // even (ty, tx), window inside
-              if (pcodes.ptr) {      // + the 1-byte window codes the backward needs instead of the activations
-                unsigned pk[8];
-  #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                  const float b1 = __shfl_xor_sync(0xffffffffu, v[e], 1), c1 = __shfl_xor_sync(0xffffffffu, v[e], 8);
-                  const float d1 = __shfl_xor_sync(0xffffffffu, v[e], 9);
-                  int arg = 0; float m = v[e];
-                  if (b1 > m) { m = b1; arg = 1; }
-                  if (c1 > m) { m = c1; arg = 2; }
-                  if (d1 > m) { m = d1; arg = 3; }
-                  const unsigned code = (unsigned)arg | ((v[e] > 0.f) ? 4u : 0u) | ((b1 > 0.f) ? 8u : 0u) | ((c1 > 0.f) ? 16u : 0u) |
-                                        ((d1 > 0.f) ? 32u : 0u);
-                  if ((e & 3) == 0) pk[e >> 2] = code; else pk[e >> 2] |= code << (8 * (e & 3));
-                  v[e] = m;
-                }
-                if (lead) {
-                  uint4* cp = reinterpret_cast<uint4*>(pcodes.ptr + img_off(pcodes, img, i >> 1, j >> 1, co));
-                  cp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                  cp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                }
-              } else {
-  #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                  float m = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
-                  v[e] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                }
-              }
-              if (lead) {
-                const long long po = img_off(pooled, img, i >> 1, j >> 1, co);
-  #pragma unroll
-                for (int e = 0; e < 32; e += 4) st4_img(pooled, po + e, v + e);
-              }
-            }
+            if (MINB == 1 && pooled.ptr)           // (pooled launches never use the two-CTA build: 32 KB of stage memory)
+              ws_epilogue_pooled(v, co, img, (ti * p.T + st) * WS_TH + 4 * q, tj * WS_TW, valid, store_out, p, bias, out, rows,
+                                 pooled, pcodes, stage, lane);
+            else
+              tc_epilogue32_coalesced(v, co, img, oy, ox, valid, p.cout, p.flags, bias, add, mask, out, rows, stage, lane,
+                                      pm, use_pm && c0 == cpar * 32);
           }
         }
       }
@@ -269,6 +321,8 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
     AST_CHECK_ARG(q->n == in->n && q->h == g->mi / 2 && q->w == g->mj / 2 && q->c == out->c && q->sc == 1 &&
                   q->sw % 4 == 0 && q->sh % 4 == 0 && q->sn % 4 == 0 && ((uintptr_t)q->ptr & 15) == 0,
                   "conv_ws: pooled must be [n, mi/2, mj/2, cout] NHWC with 16-byte aligned pixels");
+    AST_CHECK_ARG(out->dtype == AST_F32 || (g->flags & AST_CONV_POOL_ONLY), "conv_ws: the pooled launch stores an fp32 full-resolution output (or none: AST_CONV_POOL_ONLY)");
+    AST_CHECK_ARG(!add && !mask, "conv_ws: the pooled launch takes no add / mask operand");
     const ast_image* pc = g->pool_codes;
     AST_CHECK_ARG(!pc || (pc->dtype == AST_U8 && same_shape(pc, q) && pc->sc == 1 && pc->sw % 16 == 0 && pc->sh % 16 == 0 &&
                           pc->sn % 16 == 0 && ((uintptr_t)pc->ptr & 15) == 0 && pc->c % 32 == 0),
@@ -294,7 +348,9 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   p.w_tile_bytes = p.bn * p.rowb;
   p.w_total_bytes = g->ntaps * p.kchunks * p.w_tile_bytes;
   p.pw = (dx_max == dx_min) ? WS_TW : 16;
-  const int avail = 232448 - 1024 - 1024 - 8192;        // align slack, static smem, store-transpose stage
+  p.stage_w = g->pooled ? 4096 : 1024;
+  const int stage_total = 8 * p.stage_w;
+  const int avail = 232448 - 1024 - 1024 - stage_total;  // align slack, static smem, store-transpose stage
   const int budget = avail - ((p.w_total_bytes + 1023) & ~1023);
   // Sub-tiles per pipeline step: T vertically stacked 16 x 8 sub-tiles share one patch load (less halo), one TMEM stage
   // (T x bn columns) and one round of the producer -> MMA -> epilogue barrier chain.  Measured (B=32, 256^2 step): the
@@ -353,12 +409,12 @@ int conv_gather_ws(const ast_image* in, const void* weights, const float* bias, 
   bool two = false;
   {
     const int nb = p.n_pbuf > 3 ? 3 : p.n_pbuf;
-    const size_t need = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)nb * p.patch_bytes + 8192;
+    const size_t need = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)nb * p.patch_bytes + stage_total;
     const int acc2 = 2 * p.T * p.bn;                    // TMEM columns one CTA allocates (rounded up to a power of two)
     const int cols = acc2 <= 32 ? 32 : acc2 <= 64 ? 64 : acc2 <= 128 ? 128 : acc2 <= 256 ? 256 : 512;
-    if (2 * (need + 1024) <= 227 * 1024 && 2 * cols <= 512) { two = true; p.n_pbuf = nb; }
+    if (!g->pooled && 2 * (need + 1024) <= 227 * 1024 && 2 * cols <= 512) { two = true; p.n_pbuf = nb; }
   }
-  const size_t smem = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)p.n_pbuf * p.patch_bytes + 8192;
+  const size_t smem = 1024 + ((p.w_total_bytes + 1023) & ~1023) + (size_t)p.n_pbuf * p.patch_bytes + stage_total;
   const int max_ctas = (two ? 2 : 1) * num_sms();
   const int grid = (int)(p.total_tiles < max_ctas ? p.total_tiles : max_ctas);
   Img addi = add ? to_img(add) : null_img(), maski = mask ? to_img(mask) : null_img();

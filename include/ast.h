@@ -74,8 +74,10 @@ typedef struct {
   const ast_image* pooled; /* optional [n, mi/2, mj/2, cout]: nn.MaxPool2d(2, 2) of the epilogue result, written by the same
                               kernel (torchvision VGG16 features idx 4/9/16 after the conv+ReLU before them,
                               train_cnn.py:54,72-73).  Plain stride-1 launches (so = 1, no phase offset) of the
-                              weight-stationary tensor-core kernel only: any other request is an error.  With
-                              AST_CONV_POOL_ONLY the full-resolution `out` is not written (no-grad content branch). */
+                              weight-stationary tensor-core kernel only, without add / mask, with an fp32 `out`; the
+                              packed filter, two halo patches and a 32 KB pooling stage must fit in shared memory (64 -> 64
+                              channels with 16-bit operands): any other request is an error.  With AST_CONV_POOL_ONLY the
+                              full-resolution `out` is not written (no-grad content branch). */
   const ast_image* pool_codes; /* optional, with `pooled`: uint8 [n, mi/2, mj/2, cout], one byte per pooling window and channel
                               = everything the backward of ReLU + MaxPool2d needs from the forward activations:
                               bits 0-1 = arg max position k = 2*dy + dx (first maximum wins, like ATen), bits 2-5 = (x_k > 0)

@@ -125,16 +125,16 @@ def test_pool_window_codes(env):
     assert torch.equal(ref, got)
     assert torch.equal(ops.maxpool2_bwd(x, gy, None), ops.maxpool2_bwd(None, gy, None, codes=codes))
     # the fused conv + ReLU + pool epilogue writes the same codes as the stand-alone pooling kernel on its own output
-    xin = torch.randn(n, 32, 40, 64, device="cuda")
+    xin = torch.randn(n, 32, 40, 64, device="cuda").half()        # fp16 activations in, fp32 tap + fp16 pooled tensor out
     wt = torch.randn(64, 64, 3, 3, device="cuda") / 24
     launches = cg.conv_fwd(3, 1, 1, 32, 40)
-    wp = ops.pack_weights(wt, launches, 64, 64, 64 * 9, 9, 3, 1, ops.TF32)
+    wp = ops.pack_weights(wt, launches, 64, 64, 64 * 9, 9, 3, 1, torch.float32).half()
     full = torch.empty(n, 32, 40, 64, device="cuda")
-    pooled = torch.empty(n, 16, 20, 64, device="cuda")
+    pooled = torch.empty(n, 16, 20, 64, device="cuda", dtype=torch.float16)
     fcodes = torch.empty(n, 16, 20, 64, dtype=torch.uint8, device="cuda")
     ops.conv_gather(xin, wp, launches, full, relu=True, tensor=True, round_tf32=True, pooled=pooled, pool_codes=fcodes)
     codes2 = torch.empty_like(fcodes)
-    pooled2 = ops.maxpool2_fwd(full, codes=codes2)
+    pooled2 = ops.maxpool2_fwd(full, codes=codes2, out_dtype=torch.float16)
     assert torch.equal(pooled, pooled2) and torch.equal(fcodes, codes2)
 
 
