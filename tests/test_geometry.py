@@ -304,3 +304,30 @@ def test_arena_layouts_match_the_gather_kernels_operand_layouts(mode):
         assert int(next(it)[0]) == pl.g_cb
         if st.norm:
             assert int(next(it)[0]) == pl.g_gam and int(next(it)[0]) == pl.g_bet
+
+
+@pytest.mark.parametrize("ntaps,h", [(9, 11), (9, 4), (5, 7), (12, 6)])
+def test_merged_thin_filter_gradient_blocks(ntaps, h):
+    """Algebra behind contract_thin's merged mode (contract_tc.cu): for a vertical tap stack
+        dW[t][cc][rc] = sum_r X[r + t][cc] * G[r][rc]
+    ONE M128 x N(32*ngrp) product per row chunk i0, A = X rows i0 .. i0+3 (block t1), B = G rows i0 - 4*(ngrp-1-nb)
+    (block nb), accumulated over i0 = 0 .. h + 4*(ngrp-1) - 1 with rows outside the images reading 0, leaves tap
+    t = t1 + 4*(ngrp-1-nb) in block (t1, nb)."""
+    torch.manual_seed(ntaps * h)
+    w, cc, rc = 5, 3, 4
+    ngrp = (ntaps + 3) // 4
+    X = torch.randn(h + ntaps - 1, w, cc, dtype=torch.float64)     # the shifted operand (e.g. the padded layer input)
+    G = torch.randn(h, w, rc, dtype=torch.float64)                 # the fixed operand (the output gradient)
+    ref = torch.stack([torch.einsum("rwc,rwd->cd", X[t:t + h], G) for t in range(ntaps)])
+
+    def row(img, r):
+        return img[r] if 0 <= r < img.shape[0] else torch.zeros_like(img[0])
+
+    acc = torch.zeros(4, cc, ngrp, rc, dtype=torch.float64)
+    for i0 in range(h + 4 * (ngrp - 1)):
+        for t1 in range(4):
+            for nb in range(ngrp):
+                acc[t1, :, nb] += torch.einsum("wc,wd->cd", row(X, i0 + t1), row(G, i0 - 4 * (ngrp - 1 - nb)))
+    for t in range(ntaps):
+        t1, t2 = t % 4, t // 4
+        torch.testing.assert_close(acc[t1, :, ngrp - 1 - t2], ref[t])
