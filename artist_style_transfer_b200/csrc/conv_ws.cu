@@ -7,7 +7,9 @@
 //     addressed through a shifted shared-memory descriptor: tile = 16 rows x 8 pixels, one 8-pixel row = one
 //     swizzle atom, atoms are SBO = 16 pixels apart, the tap shift (dy*16 + dx) pixels moves the start address
 //     (the hardware swizzles on absolute smem address bits, so unaligned starts need no base_offset - measured).
-// Used for: VGG conv1_2-class 64->64 layers, the row-im2col'd 3-channel ends, the 81-tap 9x9 32->3 convolution.
+// Used in the training step for: VGG conv1_2 (64 -> 64, fp16 in, fp32 tap + fused MaxPool out) and its data gradient, and the
+// 1x1 layers; any stride-1 layer whose filter fits in shared memory is accepted (the thin 32/64-channel layers that ran
+// here in round 1 now go through the block-stacked kernel, conv_st.cu, unless a caller asks for the plain launches).
 #include "px_common.cuh"
 
 namespace ast {
